@@ -1,0 +1,207 @@
+/* nm_b200.h -- the C-ABI of the B200-native NiftyMatch feature pipeline.
+ *
+ * Plain C: raw device/host pointers, ints, floats; no C++/torch/thrust types.
+ * Every entry point returns 0 (NM_OK), a negative NM_ERR_* code, or
+ * NM_ERR_CUDA_BASE + cudaError_t; nothing throws or calls exit().  Every entry
+ * point enqueues ALL of its work on the given stream (nm_stream_t = cudaStream_t).
+ * There is no CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Each function names the reference interface it replaces
+ * (paths relative to the reference's src/ directory).
+ */
+#ifndef NM_B200_H
+#define NM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* nm_stream_t;      /* cudaStream_t */
+
+enum {
+    NM_OK              = 0,
+    NM_ERR_INVALID     = -1,    /* bad argument (null pointer, non-positive size, radius > 45, ...) */
+    NM_ERR_ALLOC       = -2,    /* device/host allocation failed */
+    NM_ERR_OVERFLOW    = -3,    /* an index would not fit the addressed range */
+    NM_ERR_UNSUPPORTED = -4,    /* feature not available in this build / on this device */
+    NM_ERR_NO_DEVICE   = -5,    /* no sm_100 CUDA device visible */
+    NM_ERR_CUDA_BASE   = 1000   /* NM_ERR_CUDA_BASE + cudaError_t */
+};
+
+const char* nm_strerror(int code);
+/* Compute capability of the current device (major*10+minor), or a negative error. */
+int nm_device_cc(void);
+const char* nm_version(void);
+
+/* ------------------------------------------------------------------------ */
+/* Parameters: mirror of class SiftParams (gpu/sift/siftparams.h:14-99).     */
+/* ------------------------------------------------------------------------ */
+typedef struct nm_sift_params {
+    int   width, height;
+    int   num_octaves;          /* floor(log2(min(w,h)*2/32)), >= 1        (:36) */
+    int   num_dog_levels;       /* 3                                          (:31) */
+    int   level_max, level_min; /* 4, -1                                   (:34-35) */
+    float sigma_d_0, sigma_k, sigma_0, sigma_n;                         /* (:39-41) */
+    float base_smooth;          /* sqrt(sigma_0^2 k^(2 level_min) - sigma_n^2) (:47) */
+    float sigmas[8];            /* sigma_d_0 * k^i, i = 0..4                  (:50) */
+    int   num_sigmas;
+    float peak_threshold;       /* 0                                          (:32) */
+    float edge_threshold;       /* 10                                         (:32) */
+} nm_sift_params;
+
+/* SiftParams(width, height) (siftparams.h:30-51). */
+int nm_sift_params_init(nm_sift_params* p, int width, int height);
+/* PyramidData::create_kernel_for_sigma (gpu/sift/pyramidata.cu:105-123): host taps,
+ * taps_host must hold >= 91 floats; *radius = ceil(4 sigma). */
+int nm_gaussian_taps(float sigma, float* taps_host, int* radius);
+
+/* ------------------------------------------------------------------------ */
+/* Per-stage operators (device pointers; dense row-major images).            */
+/* ------------------------------------------------------------------------ */
+
+/* convolve<float> (gpu/kernels/convolution.h:20; convolution.cu:141-159).
+ * result = G_col * (G_row * image), zero padded; bitwise the reference's order of
+ * operations.  `buffer` (width*height floats) is only touched when radius > 16. */
+int nm_blur_f32(float* result, const float* image, float* buffer, int width, int height,
+                const float* taps_dev, int radius, nm_stream_t stream);
+
+/* downsample_by_2<float> (gpu/kernels/downsample.h; downsample.cu:20-29). */
+int nm_downsample2_f32(float* result, int result_width, int result_height,
+                       const float* source, int source_width, int source_height,
+                       nm_stream_t stream);
+
+/* subtract<float> (gpu/kernels/cudamath.h:57; cudamath.cu:57-67): C = A - B. */
+int nm_subtract_f32(const float* A, const float* B, float* C, int width, int height,
+                    nm_stream_t stream);
+
+/* gradient<float> (gpu/kernels/cudamath.h:72; cudamath.cu:72-79): interior pixels
+ * get (0.5*|grad|, angle in [0,2pi]); border pixels are left untouched like the
+ * reference.  grad = float2 per pixel. */
+int nm_gradient_f32(const float* source, float* grad2, int width, int height,
+                    nm_stream_t stream);
+
+/* find_keypoints, unmasked (gpu/kernels/keypoint.h:25; keypoint.cu:240-251), on linear
+ * DoG images instead of texture objects.  result4 = dense float4 per pixel; entries of
+ * rejected pixels are left untouched (caller pre-fills with -1 like siftfunctions.cu:120). */
+int nm_keypoints_dense_f32(const float* dog_cur, const float* dog_down, const float* dog_up,
+                           int width, int height, float peak_threshold, float edge_threshold,
+                           float xper, float sigma_0, int num_dogs, int level,
+                           float* result4, nm_stream_t stream);
+
+/* find_keypoints on cudaTextureObject_t handles, unmasked and masked
+ * (gpu/kernels/keypoint.h:25,52).  mask = 0 selects the unmasked variant. */
+int nm_keypoints_dense_tex(unsigned long long tex_cur, unsigned long long tex_mask,
+                           unsigned long long tex_down, unsigned long long tex_up,
+                           int width, int height, float peak_threshold, float edge_threshold,
+                           float xper, float sigma_0, int num_dogs, int level,
+                           float* result4, nm_stream_t stream);
+
+/* PyramidData::gpu_collate_keypoints_for_level (gpu/sift/pyramidata.cu:84-91): stable
+ * compaction of the float4 entries with w >= 0; *count_dev receives the count (device
+ * int).  Also fills orient2_fill (if non-null, >= num_pixels float2) with (-1,-1). */
+int nm_collate_f32(const float* dense4, int num_pixels, float* out4, int* count_dev,
+                   nm_stream_t stream);
+
+/* detect_orientations (gpu/kernels/orientation.h:19; orientation.cu:219-230).
+ * grad2 = the octave's gradient maps, level-major (level * oh*ow + y*ow + x). */
+int nm_orientations_f32(const float* kpts4, const float* grad2, int num_pts, int octave_width,
+                        int octave_height, float gauss_factor, float xper, float* result2,
+                        nm_stream_t stream);
+
+/* compute_sift_descriptors (gpu/kernels/descriptor.h:25; descriptor.cu:243-255). */
+int nm_descriptors_f32(const float* kpts4, const float* orient2, const float* grad2, int num_pts,
+                       int octave_width, int octave_height, int num_dogs, float xper,
+                       float* desc, float* x, float* y, nm_stream_t stream);
+
+/* transpose<float> (gpu/kernels/transpose.h:17; transpose.cu:33-40). */
+int nm_transpose_f32(float* odata, const float* idata, int width, int height, nm_stream_t stream);
+
+/* compute_brute_force_distance<float> (gpu/kernels/match.h:19; match.cu:120-135):
+ * A_t is dim-major (vector_dim x size_A), result is D^T (size_B x size_A). */
+int nm_dist2_f32(const float* A_t, int size_A, const float* B, int size_B, int vector_dim,
+                 float* result_t, nm_stream_t stream);
+
+/* get_sift_matches<float> (gpu/kernels/match.h:41; match.cu:141-150). */
+int nm_set_matches_f32(const float* distance, int rows, int cols, int buffer_width,
+                       int* result, float ambiguity, nm_stream_t stream);
+
+/* ------------------------------------------------------------------------ */
+/* Fused matcher (replaces compute_sift_matches, gpu/sift/siftfunctions.h:19; */
+/* siftfunctions.cu:15-40) without materialising the distance matrix.          */
+/* ------------------------------------------------------------------------ */
+
+/* A: nA x 128, B: nB x 128 fp32 row-major on the device; match_io[nA] in/out with the
+ * reference's rule (match.cu:88-116).  The candidate search runs on the tensor cores
+ * (tcgen05, fp16 operands); the top candidates are re-ranked with the reference's exact
+ * fp32 arithmetic, so indices equal the reference's.  distance (nA*nB floats) may be
+ * NULL; when given, the exact fp32 matrix is also written (compat). */
+int nm_match_f32(const float* A, int nA, const float* B, int nB, float ambiguity,
+                 int* match_io, float* distance, nm_stream_t stream);
+
+/* Per-shard records for a sharded database: rec4[a] = (d1, bits(i1 + index_offset), d2, 0)
+ * with exact fp32 distances, reference tie rules.  nB may be 0 (d1 = d2 = +inf marker). */
+int nm_match_top2_f32(const float* A, int nA, const float* B, int nB, int index_offset,
+                      float* rec4, nm_stream_t stream);
+
+/* Merge n_shards record arrays (shard-major: recs[s*nA + a]) and apply the ratio rule;
+ * bit-identical to a single-GPU nm_match_f32 over the concatenated database. */
+int nm_match_merge_top2(const float* recs4, int n_shards, int nA, float ambiguity,
+                        int* match_io, nm_stream_t stream);
+
+/* Which candidate-search engine nm_match_* uses: 0 = exact fp32 SIMT scan,
+ * 1 = tcgen05 contraction + fp32 re-rank (default when the device is sm_100). */
+int nm_match_set_engine(int engine);
+int nm_match_get_engine(void);
+
+/* ------------------------------------------------------------------------ */
+/* Batched SIFT detect+describe: the client loop of the reference             */
+/* (compute_dog/_gradients/_keypoints/_orientations/_descriptors,             */
+/* gpu/sift/siftfunctions.h:30-101, driven per octave) for a batch of frames, */
+/* without host synchronisation inside.                                       */
+/* ------------------------------------------------------------------------ */
+typedef struct nm_sift_ctx nm_sift_ctx;
+
+/* capacity = descriptor slots per frame (SiftData capacity, gpu/sift/siftdata.h:15). */
+int nm_sift_create(nm_sift_ctx** ctx, const nm_sift_params* params, int max_batch, int capacity);
+int nm_sift_destroy(nm_sift_ctx* ctx);
+
+/* frames_dev: n_frames dense width*height fp32 images on the device.  Results stay in
+ * the context's device buffers (accessors below). */
+int nm_sift_run(nm_sift_ctx* ctx, const float* frames_dev, int n_frames, nm_stream_t stream);
+
+/* End-to-end: frames in (pinned or pageable) HOST memory; copies H2D, runs, and copies
+ * counts[n_frames], desc[n_frames*capacity*128], x/y[n_frames*capacity] back to the host
+ * (any of desc/x/y may be NULL).  Synchronises the stream before returning. */
+int nm_sift_run_host(nm_sift_ctx* ctx, const float* frames_host, int n_frames,
+                     int* counts_host, float* desc_host, float* x_host, float* y_host,
+                     nm_stream_t stream);
+
+/* Device-side results of the last run (valid until the next run / destroy).
+ * desc: [max_batch][capacity][128]; x, y: [max_batch][capacity]; kpts4/orient2 likewise;
+ * counts: [max_batch] descriptors per frame; seg_counts: [max_batch][num_octaves*3]
+ * collated keypoints per (octave, level) after the early-return rule
+ * (siftfunctions.cu:145,160). */
+int nm_sift_results(nm_sift_ctx* ctx, const float** desc, const float** x, const float** y,
+                    const int** counts, const float** kpts4, const float** orient2,
+                    const int** seg_counts);
+/* Pyramid level `level` (0..5) of `octave` for `frame`: pointer, pitch (floats), w, h. */
+int nm_sift_level(nm_sift_ctx* ctx, int frame, int octave, int level, const float** ptr,
+                  int* pitch, int* w, int* h);
+/* Gradient map (float2) of DoG level `level` (0..2) of `octave` for `frame`. */
+int nm_sift_grad(nm_sift_ctx* ctx, int frame, int octave, int level, const float** ptr2,
+                 int* pitch, int* w, int* h);
+/* Number of kernels the last nm_sift_run enqueued (for launch accounting). */
+int nm_sift_last_launches(nm_sift_ctx* ctx);
+/* Stage timing of the next run: when enabled, nm_sift_run records CUDA events around
+ * the stages and nm_sift_stage_ms returns {pyramid, extrema+gradient, compaction,
+ * orientation, descriptor, total} in milliseconds after synchronising. */
+int nm_sift_enable_timing(nm_sift_ctx* ctx, int enable);
+/* Descriptor arithmetic: 0 (default) = fp32 evaluation of the reference formulas,
+ * 1 = the reference's mixed fp64/fp32 expression shapes (validation mode). */
+int nm_sift_set_exact_descriptor(nm_sift_ctx* ctx, int exact);
+int nm_sift_stage_ms(nm_sift_ctx* ctx, float* ms6);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NM_B200_H */

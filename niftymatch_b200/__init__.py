@@ -1,0 +1,11 @@
+"""niftymatch_b200 -- B200-native (sm_100a) SIFT detect/describe + brute-force k=2 matching
+behind the public API of gift-surg/NiftyMatch.
+
+The product is the C-ABI shared library (include/nm_b200.h, niftymatch_b200/csrc/) and
+the C++ drop-in headers (include/nm/).  This Python package is plumbing for tests and
+benchmarks: it binds the C-ABI with ctypes and uses torch only for device memory,
+streams and torch.distributed.
+"""
+from ._lib import load, NmError, LIB_PATH, SiftParamsC  # noqa: F401
+from .sift import SiftParams, SiftBatch, gaussian_taps  # noqa: F401
+from .match import match, match_top2, merge_top2, match_sharded, set_engine, get_engine  # noqa: F401

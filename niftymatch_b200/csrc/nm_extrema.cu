@@ -1,0 +1,375 @@
+// nm_extrema.cu -- DoG + 3x3x3 extrema + sub-pixel refinement + edge/contrast rejection
+// + gradient maps, and the ordered compaction of the accepted keypoints.
+//
+// Replaces, for a whole batch and without host synchronisation:
+//   compute_dog        (gpu/sift/siftfunctions.cu:42-51   -> 5x subtract, cudamath.cu:26)
+//   compute_gradients  (gpu/sift/siftfunctions.cu:53-63   -> 3x gradient, cudamath.cu:38)
+//   compute_keypoints  (gpu/sift/siftfunctions.cu:100-134 -> 5x cudaMallocArray + texture,
+//                       3x thrust::fill + detect_keypoints, keypoint.cu:183-200)
+//   PyramidData::gpu_collate_keypoints_for_level (gpu/sift/pyramidata.cu:84-91, copy_if)
+//
+// Design: one fused stencil pass reads the 6 Gaussian levels of a tile once, forms the 5
+// DoG values in shared memory (never materialised in HBM), tests the 3 detection levels,
+// refines/rejects candidates and writes (a) the 3 gradient maps and (b) ONE BIT per pixel
+// and level (warp ballot -> one 32-bit store per 32 pixels).  The ordered keypoint list
+// ("copy_if order": raster within a level, levels ascending, octaves ascending) is then
+// produced from the bitmaps: a per-segment popcount scan gives every word its rank, a tiny
+// planning kernel applies the reference's early-return and capacity rules, and an emit
+// kernel re-runs the (deterministic) refinement for the set bits only and writes each
+// keypoint at its final slot.  No dense float4 maps (16 B/pixel/level in the reference),
+// no thrust::fill, no device->host count round trips.
+#include "nm_sift_internal.cuh"
+#include "nm_refine.cuh"
+
+namespace {
+
+constexpr int EX_TW = 32, EX_TH = 32, EX_P = EX_TW + 2;
+
+struct SmemDogFetch {
+    const float (*dog)[EX_TH + 2][EX_P];   // [5]
+    int l, r, c;                           // detection level (0..2), tile row/col of the centre
+    __device__ __forceinline__ float cur(int dx, int dy) const { return dog[l + 1][r + dy][c + dx]; }
+    __device__ __forceinline__ float down(int dx, int dy) const { return dog[l][r + dy][c + dx]; }
+    __device__ __forceinline__ float up(int dx, int dy) const { return dog[l + 2][r + dy][c + dx]; }
+};
+
+__global__ void __launch_bounds__(256) extrema_grad_kernel(const NmOctave oc, const NmDetectParams dp)
+{
+    __shared__ float s_dog[5][EX_TH + 2][EX_P];
+    __shared__ float s_lev[3][EX_TH + 2][EX_P];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int f = blockIdx.z, x0 = blockIdx.x * EX_TW, y0 = blockIdx.y * EX_TH;
+    const float* __restrict__ L = oc.levels + (long long)f * 6 * oc.level_elems;
+
+    for (int i = tid; i < (EX_TH + 2) * EX_P; i += 256) {
+        const int r = i / EX_P, c = i - r * EX_P;
+        const int gy = y0 - 1 + r, gx = x0 - 1 + c;
+        float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (gy >= 0 && gy < oc.h && gx >= 0 && gx < oc.w) {
+            const float* p = L + (long long)gy * oc.pitch + gx;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) v[k] = __ldg(p + k * oc.level_elems);
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) s_dog[k][r][c] = __fsub_rn(v[k + 1], v[k]);   // cudamath.cu:34
+        s_lev[0][r][c] = v[1]; s_lev[1][r][c] = v[2]; s_lev[2][r][c] = v[3];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x;
+    const int gx = x0 + lane;
+    float2* __restrict__ G = oc.grad + (long long)f * 3 * oc.level_elems;
+    const long long bm_words = (long long)oc.h * oc.wpr;
+    uint32_t* __restrict__ BM = oc.bitmap + (long long)f * 3 * bm_words;
+#pragma unroll 1
+    for (int i = 0; i < EX_TH / 8; ++i) {
+        const int ly = threadIdx.y * (EX_TH / 8) + i;
+        const int gy = y0 + ly;
+        if (gy >= oc.h) break;                                  // warp uniform
+        const bool inx = gx < oc.w;
+        const bool interior = gx >= 1 && gx <= oc.w - 2 && gy >= 1 && gy <= oc.h - 2;
+        const int r = ly + 1, c = lane + 1;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            float2 g = make_float2(0.f, 0.f);
+            if (interior)
+                g = nm_gradient_at(s_lev[l][r][c + 1], s_lev[l][r][c - 1], s_lev[l][r + 1][c], s_lev[l][r - 1][c]);
+            if (inx) G[l * oc.level_elems + (long long)gy * oc.pitch + gx] = g;
+        }
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            bool acc = false;
+            if (interior) {
+                SmemDogFetch ft{s_dog, l, r, c};
+                if (nm_is_extremum(ft, dp.peak)) {
+                    float4 out;
+                    acc = nm_refine(ft, gx, gy, dp.peak, dp.edge, oc.xper, dp.sigma_0, dp.num_dogs, l, out);
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, acc);
+            if (lane == 0) BM[l * bm_words + (long long)gy * oc.wpr + blockIdx.x] = m;
+        }
+    }
+}
+
+// One block per (segment, frame): exclusive prefix of the word popcounts + segment total.
+__global__ void __launch_bounds__(256) rank_kernel(const NmOctaveTable tab, int* __restrict__ seg_raw)
+{
+    __shared__ int s_part[256];
+    const int s = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const NmOctave& oc = tab.o[s / 3];
+    const int l = s % 3;
+    const int nwords = oc.h * oc.wpr;
+    const uint32_t* __restrict__ bm = oc.bitmap + ((long long)f * 3 + l) * nwords;
+    int* __restrict__ wp = oc.wprefix + ((long long)f * 3 + l) * nwords;
+    const int chunk = (nwords + 255) / 256;
+    const int beg = tid * chunk, end = min(beg + chunk, nwords);
+    int sum = 0;
+    for (int i = beg; i < end; ++i) sum += __popc(bm[i]);
+    s_part[tid] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 256 partials
+    for (int d = 1; d < 256; d <<= 1) {
+        int v = tid >= d ? s_part[tid - d] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    int run = s_part[tid] - sum;
+    for (int i = beg; i < end; ++i) { wp[i] = run; run += __popc(bm[i]); }
+    if (tid == 255) seg_raw[f * tab.n_oct * 3 + s] = s_part[255];
+}
+
+// Early-return rule (siftfunctions.cu:145,160: the first empty level ends the octave),
+// output offsets in (octave, level) order, capacity truncation (siftfunctions.cu:166-169).
+__global__ void plan_kernel(const int* __restrict__ seg_raw, int* __restrict__ seg_cnt,
+                            int* __restrict__ seg_off, int* __restrict__ counts, int n_oct, int batch,
+                            int capacity)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= batch) return;
+    const int S = n_oct * 3;
+    int off = 0;
+    for (int o = 0; o < n_oct; ++o) {
+        bool stopped = false;
+        for (int l = 0; l < 3; ++l) {
+            int c = seg_raw[f * S + o * 3 + l];
+            if (stopped) c = 0;
+            if (c == 0) stopped = true;
+            seg_cnt[f * S + o * 3 + l] = c;
+            seg_off[f * S + o * 3 + l] = off;
+            off += c;
+        }
+    }
+    counts[f] = off < capacity ? off : capacity;
+}
+
+struct GlobalDogFetch {
+    const float* L;            // frame's level 0 at the candidate pixel
+    long long le;              // level_elems
+    int pitch, l;
+    __device__ __forceinline__ float dogv(int k, int dx, int dy) const
+    {
+        const float* p = L + (long long)dy * pitch + dx;
+        return __fsub_rn(__ldg(p + (k + 1) * le), __ldg(p + k * le));
+    }
+    __device__ __forceinline__ float cur(int dx, int dy) const { return dogv(l + 1, dx, dy); }
+    __device__ __forceinline__ float down(int dx, int dy) const { return dogv(l, dx, dy); }
+    __device__ __forceinline__ float up(int dx, int dy) const { return dogv(l + 2, dx, dy); }
+};
+
+__global__ void __launch_bounds__(256) emit_kernel(const NmOctave oc, int octave_index, int n_oct,
+                                                   const NmDetectParams dp, const int* __restrict__ seg_cnt,
+                                                   const int* __restrict__ seg_off, int capacity,
+                                                   float4* __restrict__ kpts, int* __restrict__ meta)
+{
+    const int wi = blockIdx.x * 256 + threadIdx.x, l = blockIdx.y, f = blockIdx.z;
+    const int nwords = oc.h * oc.wpr;
+    if (wi >= nwords) return;
+    const int S = n_oct * 3, s = octave_index * 3 + l;
+    if (seg_cnt[f * S + s] == 0) return;
+    uint32_t bits = oc.bitmap[((long long)f * 3 + l) * nwords + wi];
+    if (!bits) return;
+    int pos = seg_off[f * S + s] + oc.wprefix[((long long)f * 3 + l) * nwords + wi];
+    const int y = wi / oc.wpr, xw = wi - y * oc.wpr;
+    while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        if (pos >= capacity) break;
+        const int x = xw * 32 + b;
+        GlobalDogFetch ft{oc.levels + (long long)f * 6 * oc.level_elems + (long long)y * oc.pitch + x,
+                          oc.level_elems, oc.pitch, l};
+        float4 out = make_float4(-1.f, -1.f, -1.f, -1.f);
+        nm_refine(ft, x, y, dp.peak, dp.edge, oc.xper, dp.sigma_0, dp.num_dogs, l, out);
+        kpts[(long long)f * capacity + pos] = out;
+        meta[(long long)f * capacity + pos] = octave_index;
+        ++pos;
+    }
+}
+
+// ------------------------- compat: dense per-pixel maps -------------------------
+struct LinearDogFetch {
+    const float *c, *d, *u;    // at the candidate pixel
+    int w;
+    __device__ __forceinline__ float cur(int dx, int dy) const { return __ldg(c + dy * w + dx); }
+    __device__ __forceinline__ float down(int dx, int dy) const { return __ldg(d + dy * w + dx); }
+    __device__ __forceinline__ float up(int dx, int dy) const { return __ldg(u + dy * w + dx); }
+};
+
+__global__ void keypoints_dense_linear_kernel(const float* __restrict__ cur, const float* __restrict__ down,
+                                              const float* __restrict__ up, int w, int h,
+                                              NmDetectParams dp, float xper, int level, float4* __restrict__ result)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < 1 || x > w - 2 || y < 1 || y > h - 2) return;       // keypoint.cu:191
+    const long long i = (long long)y * w + x;
+    LinearDogFetch ft{cur + i, down + i, up + i, w};
+    if (!nm_is_extremum(ft, dp.peak)) return;
+    float4 out;
+    if (nm_refine(ft, x, y, dp.peak, dp.edge, xper, dp.sigma_0, dp.num_dogs, level, out)) result[i] = out;
+}
+
+struct TexDogFetch {
+    cudaTextureObject_t c, d, u;
+    float ax, ay;
+    __device__ __forceinline__ float cur(int dx, int dy) const { return tex2D<float>(c, ax + dx, ay + dy); }
+    __device__ __forceinline__ float down(int dx, int dy) const { return tex2D<float>(d, ax + dx, ay + dy); }
+    __device__ __forceinline__ float up(int dx, int dy) const { return tex2D<float>(u, ax + dx, ay + dy); }
+};
+
+__global__ void keypoints_dense_tex_kernel(cudaTextureObject_t cur, cudaTextureObject_t mask,
+                                           cudaTextureObject_t down, cudaTextureObject_t up, int w, int h,
+                                           NmDetectParams dp, float xper, int level, float4* __restrict__ result)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < 1 || x > w - 2 || y < 1 || y > h - 2) return;
+    // keypoint.cu:214
+    if (mask != 0 && tex2D<float>(mask, (x + 0.5f) * xper, (y + 0.5f) * xper) < 1.f) return;
+    TexDogFetch ft{cur, down, up, x + 0.5f, y + 0.5f};
+    if (!nm_is_extremum(ft, dp.peak)) return;
+    float4 out;
+    if (nm_refine(ft, x, y, dp.peak, dp.edge, xper, dp.sigma_0, dp.num_dogs, level, out))
+        result[(long long)y * w + x] = out;
+}
+
+// ------------------------- compat: ordered copy_if ------------------------------
+constexpr int COL_CHUNK = 2048;     // pixels per block
+__global__ void __launch_bounds__(256) collate_count_kernel(const float4* __restrict__ dense, int n,
+                                                            int* __restrict__ block_counts)
+{
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int base = blockIdx.x * COL_CHUNK;
+    int c = 0;
+    for (int i = threadIdx.x; i < COL_CHUNK; i += 256) {
+        const int p = base + i;
+        if (p < n && dense[p].w >= 0.f) ++c;                    // pyramidata.cu:13
+    }
+    atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = s_cnt;
+}
+__global__ void collate_scan_kernel(int* __restrict__ block_counts, int nblocks, int* __restrict__ total)
+{
+    // single thread: nblocks is small (n / 2048)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < nblocks; ++i) { int c = block_counts[i]; block_counts[i] = run; run += c; }
+        *total = run;
+    }
+}
+__global__ void __launch_bounds__(256) collate_write_kernel(const float4* __restrict__ dense, int n,
+                                                            const int* __restrict__ block_offsets,
+                                                            float4* __restrict__ out)
+{
+    __shared__ int s_warp[8];
+    __shared__ int s_run;
+    const int base = blockIdx.x * COL_CHUNK;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run = block_offsets[blockIdx.x];
+    __syncthreads();
+    for (int i0 = 0; i0 < COL_CHUNK; i0 += 256) {
+        const int p = base + i0 + threadIdx.x;
+        float4 v = make_float4(-1.f, -1.f, -1.f, -1.f);
+        if (p < n) v = dense[p];
+        const bool keep = p < n && v.w >= 0.f;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[wid] = __popc(m);
+        __syncthreads();
+        int off = s_run;
+        for (int k = 0; k < wid; ++k) off += s_warp[k];
+        if (keep) out[off + __popc(m & ((1u << lane) - 1u))] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < 8; ++k) t += s_warp[k]; s_run += t; }
+        __syncthreads();
+    }
+}
+
+} // namespace
+
+int nm_extrema_launch(const NmOctave& oc, int, int, const NmDetectParams& dp, int batch, cudaStream_t stream)
+{
+    dim3 block(32, 8), grid(nm_div_up(oc.w, EX_TW), nm_div_up(oc.h, EX_TH), batch);
+    extrema_grad_kernel<<<grid, block, 0, stream>>>(oc, dp);
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+int nm_rank_launch(const NmOctaveTable& tab, int batch, int* seg_raw, cudaStream_t stream)
+{
+    dim3 grid(tab.n_oct * 3, batch);
+    rank_kernel<<<grid, 256, 0, stream>>>(tab, seg_raw);
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+int nm_plan_launch(const int* seg_raw, int* seg_cnt, int* seg_off, int* counts, int n_oct, int batch,
+                   int capacity, cudaStream_t stream)
+{
+    plan_kernel<<<nm_div_up(batch, 64), 64, 0, stream>>>(seg_raw, seg_cnt, seg_off, counts, n_oct, batch, capacity);
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+int nm_emit_launch(const NmOctave& oc, int octave_index, int n_oct, const NmDetectParams& dp, int batch,
+                   const int* seg_cnt, const int* seg_off, int capacity, float4* kpts, int* meta,
+                   cudaStream_t stream)
+{
+    dim3 grid(nm_div_up(oc.h * oc.wpr, 256), 3, batch);
+    emit_kernel<<<grid, 256, 0, stream>>>(oc, octave_index, n_oct, dp, seg_cnt, seg_off, capacity, kpts, meta);
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C-ABI (compat granularity)
+// ---------------------------------------------------------------------------
+extern "C" int nm_keypoints_dense_f32(const float* dog_cur, const float* dog_down, const float* dog_up,
+                                      int width, int height, float peak_threshold, float edge_threshold,
+                                      float xper, float sigma_0, int num_dogs, int level, float* result4,
+                                      nm_stream_t stream)
+{
+    if (!dog_cur || !dog_down || !dog_up || !result4 || width <= 0 || height <= 0) return NM_ERR_INVALID;
+    NmDetectParams dp{peak_threshold, edge_threshold, sigma_0, num_dogs};
+    dim3 block(32, 8), grid(nm_div_up(width, 32), nm_div_up(height, 8));
+    keypoints_dense_linear_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+        dog_cur, dog_down, dog_up, width, height, dp, xper, level, reinterpret_cast<float4*>(result4));
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+extern "C" int nm_keypoints_dense_tex(unsigned long long tex_cur, unsigned long long tex_mask,
+                                      unsigned long long tex_down, unsigned long long tex_up, int width,
+                                      int height, float peak_threshold, float edge_threshold, float xper,
+                                      float sigma_0, int num_dogs, int level, float* result4,
+                                      nm_stream_t stream)
+{
+    if (!tex_cur || !tex_down || !tex_up || !result4 || width <= 0 || height <= 0) return NM_ERR_INVALID;
+    NmDetectParams dp{peak_threshold, edge_threshold, sigma_0, num_dogs};
+    dim3 block(32, 8), grid(nm_div_up(width, 32), nm_div_up(height, 8));
+    keypoints_dense_tex_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+        (cudaTextureObject_t)tex_cur, (cudaTextureObject_t)tex_mask, (cudaTextureObject_t)tex_down,
+        (cudaTextureObject_t)tex_up, width, height, dp, xper, level, reinterpret_cast<float4*>(result4));
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+extern "C" int nm_collate_f32(const float* dense4, int num_pixels, float* out4, int* count_dev,
+                              nm_stream_t stream)
+{
+    if (!dense4 || !out4 || !count_dev || num_pixels <= 0) return NM_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblocks = nm_div_up(num_pixels, COL_CHUNK);
+    int* block_counts = nullptr;
+    NM_CUDA_TRY(cudaMallocAsync(&block_counts, sizeof(int) * nblocks, st));
+    collate_count_kernel<<<nblocks, 256, 0, st>>>(reinterpret_cast<const float4*>(dense4), num_pixels, block_counts);
+    collate_scan_kernel<<<1, 32, 0, st>>>(block_counts, nblocks, count_dev);
+    collate_write_kernel<<<nblocks, 256, 0, st>>>(reinterpret_cast<const float4*>(dense4), num_pixels,
+                                                  block_counts, reinterpret_cast<float4*>(out4));
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(block_counts, st);
+    return nm_cuda_err(e);
+}

@@ -1,0 +1,369 @@
+// nm_orient_desc.cu -- dominant orientation and 128-D descriptor per keypoint.
+//
+// Replaces detect_orientations / kernel_orientations_optim (gpu/kernels/orientation.cu:
+// 11-129, 219-230) and compute_sift_descriptors / kernel_descriptor_optim
+// (gpu/kernels/descriptor.cu:32-145, 243-255) for the whole batch.
+//
+// Design: ONE WARP per keypoint (the reference spends a 484-thread and a 256-thread CTA
+// per keypoint).  Histograms are privatised per lane in shared memory (bank = lane, no
+// atomics, no float-atomic order nondeterminism -- the reference uses shared / global
+// float atomics) and reduced across lanes in a fixed order with a swizzled read, so the
+// output is bit-reproducible run to run.  All the reference's quirks that define its
+// numbers are kept: positive-exponent Gaussian windows, the 10-pixel clamp of the
+// orientation window, first-two-peaks-in-bin-order, first orientation only, diagonal-only
+// 16x16 chunks of the descriptor window, no normalisation (SURVEY.md Q5,Q6,Q10,Q12,Q16).
+#include "nm_sift_internal.cuh"
+
+namespace {
+
+constexpr int OR_WARPS = 8;      // warps per block, orientation
+constexpr int NBINS = 36;
+constexpr int OR_HP = 33;        // padded lane pitch of the private histograms
+
+struct KpGeom {
+    float x, y, s;
+    int xi, yi, level;
+};
+
+__device__ __forceinline__ KpGeom kp_geom(const float4 kp, float xper)
+{
+    KpGeom g;
+    g.x = __fdiv_rn(kp.x, xper);                                  // orientation.cu:19-21
+    g.y = __fdiv_rn(kp.y, xper);
+    g.s = __fdiv_rn(kp.z, xper);
+    g.xi = __double2int_rz(__dadd_rn((double)g.x, 0.5));          // :23-24
+    g.yi = __double2int_rz(__dadd_rn((double)g.y, 0.5));
+    g.level = (int)kp.w;
+    return g;
+}
+
+__global__ void __launch_bounds__(OR_WARPS * 32) orient_kernel(const NmOctaveTable tab, int capacity,
+                                                               const int* __restrict__ counts,
+                                                               const float4* __restrict__ kpts,
+                                                               const int* __restrict__ meta,
+                                                               float2* __restrict__ orient)
+{
+    __shared__ float s_priv[OR_WARPS][NBINS * OR_HP];
+    __shared__ float s_hist[OR_WARPS][NBINS + 4];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int f = blockIdx.y;
+    const int j = blockIdx.x * OR_WARPS + wid;
+    if (j >= counts[f]) return;                                   // warp uniform
+    const long long kidx = (long long)f * capacity + j;
+    const float4 kp = kpts[kidx];
+    float2 res = make_float2(-1.f, -1.f);                         // pyramidata.cu:90 fill
+    if (!(kp.w < 0.f)) {                                          // orientation.cu:17
+        const NmOctave& oc = tab.o[meta[kidx]];
+        const KpGeom g = kp_geom(kp, oc.xper);
+        const float sigma_w = __fmul_rn(1.5f, g.s);               // :26, gauss_factor = 1.5 (siftfunctions.cu:150)
+        int W = max((int)floorf(__fmul_rn(3.0f, sigma_w)), 1);    // :27
+        W = min(W, 10);                                           // :29-30 (22x22 block)
+        const float2* __restrict__ G = oc.grad + ((long long)f * 3 + g.level) * oc.level_elems;
+        float* priv = s_priv[wid];
+        float* hist = s_hist[wid];
+#pragma unroll
+        for (int b = 0; b < NBINS; ++b) priv[b * OR_HP + lane] = 0.f;
+        const int xmin = max(-W, -g.xi), xmax = min(W, oc.w - 1 - g.xi);   // :43-46
+        const int ymin = max(-W, -g.yi), ymax = min(W, oc.h - 1 - g.yi);
+        const int nx = xmax - xmin + 1, ny = ymax - ymin + 1;
+        const int total = (nx > 0 && ny > 0) ? nx * ny : 0;
+        const float den = __fmul_rn(sigma_w, __fadd_rn(sigma_w, sigma_w));  // 2*sigma_w*sigma_w
+        const double lim = __dadd_rn((double)(W * W), 0.6);
+        for (int s = lane; s < total; s += 32) {
+            const int cy = ymin + s / nx, cx = xmin + s % nx;
+            const float dx = __fsub_rn((float)(cx + g.xi), g.x);  // :52-53
+            const float dy = __fsub_rn((float)(cy + g.yi), g.y);
+            const float r2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));         // :54
+            if ((double)r2 < lim) {                               // :55
+                const float wgt = expf(__fdiv_rn(r2, den));       // :56 (positive exponent)
+                const float2 gv = __ldg(G + (long long)(g.yi + cy) * oc.pitch + (g.xi + cx));
+                int bin = (int)floorf((float)__ddiv_rn((double)__fmul_rn(36.0f, gv.y), NM_TWO_PI_D));  // :57
+                bin %= NBINS;
+                if (bin < 0) bin += NBINS;
+                float* p = priv + bin * OR_HP + lane;
+                *p = __fadd_rn(*p, __fmul_rn(gv.x, wgt));         // :58
+            }
+        }
+        __syncwarp();
+        // fixed-order reduction: lane b owns bin b (and b+32 for lanes 0..3)
+        for (int b = lane; b < NBINS; b += 32) {
+            float acc = 0.f;
+            const float* p = priv + b * OR_HP;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, p[k]);
+            hist[b] = acc;
+        }
+        __syncwarp();
+        // 6x circular 3-tap box smoothing, Jacobi (intended semantics = orientation.cu:181-192)
+        for (int iter = 0; iter < 6; ++iter) {
+            float n0 = 0.f, n1 = 0.f;
+            {
+                const int b = lane;
+                n0 = __fdiv_rn(__fadd_rn(__fadd_rn(hist[(b + NBINS - 1) % NBINS], hist[b]), hist[(b + 1) % NBINS]), 3.0f);
+            }
+            if (lane < NBINS - 32) {
+                const int b = lane + 32;
+                n1 = __fdiv_rn(__fadd_rn(__fadd_rn(hist[(b + NBINS - 1) % NBINS], hist[b]), hist[(b + 1) % NBINS]), 3.0f);
+            }
+            __syncwarp();
+            hist[lane] = n0;
+            if (lane < NBINS - 32) hist[lane + 32] = n1;
+            __syncwarp();
+        }
+        float m = fmaxf(0.f, hist[lane]);                          // :93-95
+        if (lane < NBINS - 32) m = fmaxf(m, hist[lane + 32]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+        const float thr = (float)__dmul_rn((double)m, 0.8);        // :96
+        float th0 = -1.f, th1 = -1.f;
+        bool pk0 = false, pk1 = false;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int b = lane + 32 * half;
+            if (b < NBINS) {
+                const float h0 = hist[b], hm = hist[(b + NBINS - 1) % NBINS], hp = hist[(b + 1) % NBINS];
+                if (h0 > thr && h0 > hm && h0 > hp) {              // :107
+                    const double num = __dmul_rn(-0.5, (double)__fsub_rn(hp, hm));
+                    const double dn = (double)__fsub_rn(__fadd_rn(hp, hm), __fmul_rn(2.0f, h0));
+                    const float di = (float)__ddiv_rn(num, dn);    // :108
+                    const float th = (float)__ddiv_rn(
+                        __dmul_rn(NM_TWO_PI_D, __dadd_rn((double)__fadd_rn((float)b, di), 0.5)), 36.0);  // :109
+                    if (half == 0) { pk0 = true; th0 = th; } else { pk1 = true; th1 = th; }
+                }
+            }
+        }
+        // first two peaks in ascending bin order (:116-128)
+        const unsigned m0 = __ballot_sync(0xffffffffu, pk0);
+        const unsigned m1 = __ballot_sync(0xffffffffu, pk1);
+        float first = -1.f, second = -1.f;
+        int found = 0;
+        unsigned mm = m0;
+        while (mm && found < 2) {
+            const int src = __ffs(mm) - 1; mm &= mm - 1;
+            const float v = __shfl_sync(0xffffffffu, th0, src);
+            if (found == 0) first = v; else second = v;
+            ++found;
+        }
+        mm = m1;
+        while (mm && found < 2) {
+            const int src = __ffs(mm) - 1; mm &= mm - 1;
+            const float v = __shfl_sync(0xffffffffu, th1, src);
+            if (found == 0) first = v; else second = v;
+            ++found;
+        }
+        res = make_float2(first, second);
+    }
+    if (lane == 0) orient[kidx] = res;
+}
+
+// ------------------------------- descriptor -----------------------------------
+constexpr int DE_WARPS = 4;
+constexpr int DE_BINS = 128;
+
+// EXACT = the reference's mixed double/float expression shapes (descriptor.cu:98-115, with
+// the DFMA contractions of its sm_100a SASS); !EXACT = the same formulas in fp32 (the bins
+// and trilinear weights are continuous in nx, ny, nt, so the fp32 evaluation stays within
+// ~1e-6 relative of the exact one; the tolerance is 1e-3, BASELINE.json).
+template <bool EXACT>
+__global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveTable tab, int capacity,
+                                                                 const int* __restrict__ counts,
+                                                                 const float4* __restrict__ kpts,
+                                                                 const int* __restrict__ meta,
+                                                                 const float2* __restrict__ orient,
+                                                                 float* __restrict__ desc, float* __restrict__ xo,
+                                                                 float* __restrict__ yo, int num_dogs)
+{
+    extern __shared__ __align__(16) float s_h[];      // [DE_WARPS][128][32], swizzled
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int f = blockIdx.y;
+    const int j = blockIdx.x * DE_WARPS + wid;
+    if (j >= counts[f]) return;                                   // warp uniform
+    const long long kidx = (long long)f * capacity + j;
+    const float4 kp = kpts[kidx];
+    const NmOctave& oc = tab.o[meta[kidx]];
+    const KpGeom g = kp_geom(kp, oc.xper);                        // descriptor.cu:41-47
+    float* dout = desc + kidx * DE_BINS;
+    if (g.xi < 0 || g.xi >= oc.w || g.yi < 0 || g.yi >= oc.h || g.level < 0 || g.level >= num_dogs)
+        return;                                                   // :49 (slot left as is)
+    float* hist = s_h + wid * (DE_BINS * 32);
+#pragma unroll 4
+    for (int b = 0; b < DE_BINS; ++b) hist[b * 32 + lane] = 0.f;
+
+    const float SBP = (float)__dadd_rn((double)__fmul_rn(3.0f, g.s), 1.e-07);            // :54
+    const int W = (int)floor(__fma_rn(__dmul_rn(__dmul_rn((double)SBP, 1.4142135623730951), 5.0), 0.5, 0.5));  // :55
+    const int xmin = max(-W, -g.xi), xmax = min(W, oc.w - 1 - g.xi);                     // :57-60
+    const int ymin = max(-W, -g.yi), ymax = min(W, oc.h - 1 - g.yi);
+    const int max_dims = max(xmax - xmin, ymax - ymin);
+    const int chunks = (int)ceilf(__fdiv_rn(__fadd_rn((float)max_dims, 1.f), 16.f));     // :65
+    const float th0 = orient[kidx].x;                                                    // :89
+    const float st0f = sinf(th0), ct0f = cosf(th0);                                      // :90-91 (float overloads)
+    const double st0 = (double)st0f, ct0 = (double)ct0f;
+    const float inv_sbp = __fdiv_rn(1.0f, SBP);
+    const float2* __restrict__ G = oc.grad + ((long long)f * 3 + g.level) * oc.level_elems +
+                                   (long long)g.yi * oc.pitch + g.xi;
+    const int total = chunks * 256;
+    for (int s = lane; s < total; s += 32) {
+        const int c = s >> 8, ty = (s >> 4) & 15, tx = s & 15;
+        const int cx = xmin + tx + 16 * c, cy = ymin + ty + 16 * c;   // diagonal chunks only (:142-143)
+        if (cx > xmax || cy > ymax) continue;                         // :96
+        const float2 gv = __ldg(G + (long long)cy * oc.pitch + cx);
+        const float mod = gv.x;
+        const float theta = nm_mod_2pi_f(__fsub_rn(gv.y, th0));       // :100
+        const float dx = __fsub_rn((float)(g.xi + cx), g.x);          // :102-103
+        const float dy = __fsub_rn((float)(g.yi + cy), g.y);
+        float nx, ny, nt, win, rbinx, rbiny;
+        int binx, biny;
+        if (EXACT) {
+            nx = (float)__ddiv_rn(__fma_rn(ct0, (double)dx, __dmul_rn(st0, (double)dy)), (double)SBP);    // :104
+            ny = (float)__ddiv_rn(__fma_rn(ct0, (double)dy, -__dmul_rn(st0, (double)dx)), (double)SBP);   // :105
+            nt = (float)__ddiv_rn((double)__fmul_rn(8.0f, theta), NM_TWO_PI_D);                           // :107
+            win = (float)exp(__dmul_rn((double)__fmaf_rn(nx, nx, __fmul_rn(ny, ny)), 0.125));             // :108
+            binx = (int)floor(__dadd_rn((double)nx, -0.5));                                               // :110
+            biny = (int)floor(__dadd_rn((double)ny, -0.5));
+            rbinx = (float)__dsub_rn((double)nx, __dadd_rn((double)binx, 0.5));                           // :113
+            rbiny = (float)__dsub_rn((double)ny, __dadd_rn((double)biny, 0.5));
+        } else {
+            nx = __fmul_rn(__fmaf_rn(ct0f, dx, __fmul_rn(st0f, dy)), inv_sbp);
+            ny = __fmul_rn(__fmaf_rn(ct0f, dy, -__fmul_rn(st0f, dx)), inv_sbp);
+            nt = __fmul_rn(theta, 1.2732395447351628f);               // 8 / (2 pi)
+            win = expf(__fmul_rn(__fmaf_rn(nx, nx, __fmul_rn(ny, ny)), 0.125f));
+            const float fx = floorf(__fsub_rn(nx, 0.5f)), fy = floorf(__fsub_rn(ny, 0.5f));
+            binx = (int)fx; biny = (int)fy;
+            rbinx = __fsub_rn(nx, __fadd_rn(fx, 0.5f));
+            rbiny = __fsub_rn(ny, __fadd_rn(fy, 0.5f));
+        }
+        const int bint = (int)floorf(nt);                             // :112
+        const float rbint = __fsub_rn(nt, (float)bint);               // :115
+        const float wm = __fmul_rn(win, mod);                         // :128-129 (left to right)
+#pragma unroll
+        for (int dbx = 0; dbx < 2; ++dbx)
+#pragma unroll
+            for (int dby = 0; dby < 2; ++dby) {
+                const int bx = binx + dbx, by = biny + dby;
+                if (bx >= -2 && bx < 2 && by >= -2 && by < 2) {       // :122-125
+                    const float wxy = __fmul_rn(__fmul_rn(wm, fabsf(__fsub_rn(1.f - dbx, rbinx))),
+                                                fabsf(__fsub_rn(1.f - dby, rbiny)));
+#pragma unroll
+                    for (int dbt = 0; dbt < 2; ++dbt) {
+                        const float wt = __fmul_rn(wxy, fabsf(__fsub_rn(1.f - dbt, rbint)));
+                        const int loc = (by + 2) * 32 + (bx + 2) * 8 + ((bint + dbt) & 7);   // :133
+                        float* p = hist + loc * 32 + ((lane + loc) & 31);
+                        *p = __fadd_rn(*p, wt);                       // :135
+                    }
+                }
+            }
+    }
+    __syncwarp();
+    // fixed-order reduction; lane owns bins lane, lane+32, lane+64, lane+96
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int b = lane + 32 * q;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, hist[b * 32 + ((k + b) & 31)]);
+        dout[b] = acc;
+    }
+    if (lane == 0) { xo[kidx] = kp.x; yo[kidx] = kp.y; }              // :76
+}
+
+// ---------------------- compat: flat keypoint lists (one octave) ----------------------
+__global__ void compat_fill_meta(int* meta, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) meta[i] = 0; }
+
+} // namespace
+
+int nm_orient_launch(const NmOctaveTable& tab, int batch, int capacity, const int* counts,
+                     const float4* kpts, const int* meta, float2* orient, cudaStream_t stream)
+{
+    dim3 grid(nm_div_up(capacity, OR_WARPS), batch);
+    orient_kernel<<<grid, OR_WARPS * 32, 0, stream>>>(tab, capacity, counts, kpts, meta, orient);
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+int nm_describe_launch(const NmOctaveTable& tab, int batch, int capacity, const int* counts,
+                       const float4* kpts, const int* meta, const float2* orient, float* desc,
+                       float* x, float* y, int num_dogs, int exact, cudaStream_t stream)
+{
+    static bool configured = false;
+    constexpr int smem = DE_WARPS * DE_BINS * 32 * (int)sizeof(float);
+    if (!configured) {
+        NM_CUDA_TRY(cudaFuncSetAttribute(describe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        NM_CUDA_TRY(cudaFuncSetAttribute(describe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid(nm_div_up(capacity, DE_WARPS), batch);
+    if (exact)
+        describe_kernel<true><<<grid, DE_WARPS * 32, smem, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
+    else
+        describe_kernel<false><<<grid, DE_WARPS * 32, smem, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C-ABI (compat granularity): one octave, flat keypoint list, dense gradient maps
+// laid out like PyramidData::_grad (level * oh*ow + y*ow + x).
+// ---------------------------------------------------------------------------
+static int compat_table(NmOctaveTable& tab, const float* grad2, int ow, int oh, float xper)
+{
+    tab.n_oct = 1;
+    NmOctave& oc = tab.o[0];
+    oc.levels = nullptr; oc.bitmap = nullptr; oc.wprefix = nullptr;
+    oc.grad = reinterpret_cast<float2*>(const_cast<float*>(grad2));
+    oc.w = ow; oc.h = oh; oc.pitch = ow; oc.wpr = nm_div_up(ow, 32);
+    oc.level_elems = (long long)ow * oh;
+    oc.xper = xper;
+    return NM_OK;
+}
+
+namespace {
+struct CompatScratch { int* counts; int* meta; };
+int compat_scratch(CompatScratch& sc, int n, cudaStream_t st)
+{
+    NM_CUDA_TRY(cudaMallocAsync(&sc.counts, sizeof(int), st));
+    NM_CUDA_TRY(cudaMallocAsync(&sc.meta, sizeof(int) * n, st));
+    NM_CUDA_TRY(cudaMemcpyAsync(sc.counts, &n, sizeof(int), cudaMemcpyHostToDevice, st));
+    compat_fill_meta<<<nm_div_up(n, 256), 256, 0, st>>>(sc.meta, n);
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+} // namespace
+
+extern "C" int nm_orientations_f32(const float* kpts4, const float* grad2, int num_pts, int octave_width,
+                                   int octave_height, float gauss_factor, float xper, float* result2,
+                                   nm_stream_t stream)
+{
+    if (!kpts4 || !grad2 || !result2 || num_pts <= 0 || octave_width <= 0 || octave_height <= 0) return NM_ERR_INVALID;
+    if (gauss_factor != 1.5f) return NM_ERR_UNSUPPORTED;   // the reference hard-codes 1.5f (siftfunctions.cu:150)
+    cudaStream_t st = (cudaStream_t)stream;
+    NmOctaveTable tab; compat_table(tab, grad2, octave_width, octave_height, xper);
+    CompatScratch sc{};
+    int rc = compat_scratch(sc, num_pts, st);
+    if (rc == NM_OK)
+        rc = nm_orient_launch(tab, 1, num_pts, sc.counts, reinterpret_cast<const float4*>(kpts4), sc.meta,
+                              reinterpret_cast<float2*>(result2), st);
+    // the host int `n` passed to cudaMemcpyAsync lives on this frame: make sure it was consumed
+    cudaStreamSynchronize(st);
+    if (sc.counts) cudaFreeAsync(sc.counts, st);
+    if (sc.meta) cudaFreeAsync(sc.meta, st);
+    return rc;
+}
+
+extern "C" int nm_descriptors_f32(const float* kpts4, const float* orient2, const float* grad2, int num_pts,
+                                  int octave_width, int octave_height, int num_dogs, float xper,
+                                  float* desc, float* x, float* y, nm_stream_t stream)
+{
+    if (!kpts4 || !orient2 || !grad2 || !desc || !x || !y || num_pts <= 0 || octave_width <= 0 || octave_height <= 0)
+        return NM_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    NmOctaveTable tab; compat_table(tab, grad2, octave_width, octave_height, xper);
+    CompatScratch sc{};
+    int rc = compat_scratch(sc, num_pts, st);
+    if (rc == NM_OK)
+        rc = nm_describe_launch(tab, 1, num_pts, sc.counts, reinterpret_cast<const float4*>(kpts4), sc.meta,
+                                reinterpret_cast<const float2*>(orient2), desc, x, y, num_dogs, 0, st);
+    cudaStreamSynchronize(st);
+    if (sc.counts) cudaFreeAsync(sc.counts, st);
+    if (sc.meta) cudaFreeAsync(sc.meta, st);
+    return rc;
+}

@@ -1,0 +1,21 @@
+// nm_pyramid.cuh -- internal interface of the Gaussian scale-space kernels.
+#pragma once
+#include "nm_common.cuh"
+
+struct NmBlurArgs {
+    const float* src;       // [batch][h][src_pitch]
+    float*       dst;       // [batch][h][dst_pitch]
+    const float* taps;      // device, 2R+1 floats
+    float*       dst2;      // optional decimated copy dst2[y/2][x/2] (next octave base), or null
+    float*       scratch;   // only for the generic (R > 16) path: [batch][h][w]
+    long long    src_fstride, dst_fstride, dst2_fstride;   // floats between frames
+    int          w, h, src_pitch, dst_pitch, dst2_pitch, batch, radius;
+};
+
+// Fused separable blur (rows then columns, zero padding, reference order of operations).
+int nm_blur_launch(const NmBlurArgs& a, cudaStream_t stream);
+
+// dst[y][x] = src[2y][2x]
+int nm_downsample_launch(float* dst, int dw, int dh, int dpitch, long long dfstride,
+                         const float* src, int spitch, long long sfstride, int batch,
+                         cudaStream_t stream);

@@ -1,0 +1,340 @@
+// nm_sift.cu -- parameters, workspace and the batched detect+describe driver.
+//
+// Host-side equivalents of SiftParams (gpu/sift/siftparams.h:30-51), PyramidData
+// (gpu/sift/pyramidata.cu:24-50, 94-123) and the client's per-octave loop around the
+// seven functions of gpu/sift/siftfunctions.h, for a batch of frames on one stream with
+// no host synchronisation inside nm_sift_run.
+#include "nm_sift_internal.cuh"
+#include "nm_pyramid.cuh"
+#include <cmath>
+#include <cstring>
+#include <cstdio>
+#include <new>
+#include <vector>
+
+struct nm_sift_ctx {
+    nm_sift_params P;
+    int B, capacity, n_oct;
+    NmOctaveTable tab;
+    float* taps[6];          // 0: base kernel, 1..5: level kernels (device)
+    int    radii[6];
+    int *seg_raw, *seg_cnt, *seg_off, *counts, *meta;
+    float4* kpts;
+    float2* orient;
+    float *desc, *x, *y;
+    float* frames_stage;     // device staging for nm_sift_run_host: [B][h][w]
+    float* scratch;          // generic-radius blur scratch (lazily allocated)
+    int exact_desc;
+    int last_launches;
+    int timing;
+    cudaEvent_t ev[6];
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(nm_sift_ctx* c, T** p, size_t count)
+{
+    void* q = nullptr;
+    if (cudaMalloc(&q, count * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return NM_ERR_ALLOC; }
+    c->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return NM_OK;
+}
+
+} // namespace
+
+extern "C" const char* nm_version(void) { return "nm-b200 0.1 (sm_100a)"; }
+
+extern "C" const char* nm_strerror(int code)
+{
+    switch (code) {
+        case NM_OK: return "ok";
+        case NM_ERR_INVALID: return "invalid argument";
+        case NM_ERR_ALLOC: return "allocation failed";
+        case NM_ERR_OVERFLOW: return "index range overflow";
+        case NM_ERR_UNSUPPORTED: return "unsupported";
+        case NM_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+        default: break;
+    }
+    if (code >= NM_ERR_CUDA_BASE) return cudaGetErrorString((cudaError_t)(code - NM_ERR_CUDA_BASE));
+    return "unknown error";
+}
+
+extern "C" int nm_device_cc(void)
+{
+    int dev = 0, n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return NM_ERR_NO_DEVICE; }
+    NM_CUDA_TRY(cudaGetDevice(&dev));
+    int major = 0, minor = 0;
+    NM_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    NM_CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    return major * 10 + minor;
+}
+
+// SiftParams(width, height): gpu/sift/siftparams.h:30-51, same mixed float/double steps.
+extern "C" int nm_sift_params_init(nm_sift_params* p, int width, int height)
+{
+    if (!p || width <= 0 || height <= 0) return NM_ERR_INVALID;
+    std::memset(p, 0, sizeof(*p));
+    p->width = width; p->height = height;
+    p->num_dog_levels = 3; p->sigma_n = 0.5f; p->peak_threshold = 0.f; p->edge_threshold = 10.f;
+    p->level_max = p->num_dog_levels + 1;
+    p->level_min = -1;
+    p->num_octaves = (int)std::floor(std::log(std::min(width, height) * 2.0 / 32) / std::log(2.0));
+    if (p->num_octaves <= 0) p->num_octaves = 1;
+    p->sigma_k = std::pow(2.0f, 1.0f / p->num_dog_levels);
+    p->sigma_0 = 1.6f * p->sigma_k;
+    p->sigma_d_0 = (float)(p->sigma_0 * std::sqrt(1.0 - 1.0 / (p->sigma_k * p->sigma_k)));
+    const float sa = (float)(p->sigma_0 * std::pow((double)p->sigma_k, (double)p->level_min));
+    const float sb = p->sigma_n;
+    if (sa > sb) p->base_smooth = std::sqrt(sa * sa - sb * sb);
+    p->num_sigmas = 0;
+    for (int i = p->level_min + 1; i <= p->level_max && p->num_sigmas < 8; ++i)
+        p->sigmas[p->num_sigmas++] = (float)(p->sigma_d_0 * std::pow((double)p->sigma_k, (double)i));
+    return NM_OK;
+}
+
+// PyramidData::create_kernel_for_sigma: gpu/sift/pyramidata.cu:105-123.
+extern "C" int nm_gaussian_taps(float sigma, float* taps_host, int* radius)
+{
+    if (!taps_host || !radius || !(sigma > 0.f)) return NM_ERR_INVALID;
+    const int r = (int)std::ceil(sigma * 4);
+    if (2 * r + 1 > 91) return NM_ERR_INVALID;                   // MAX_KERNEL_LENGTH, pyramidata.h:9
+    float sum = 0.f;
+    for (int j = 0; j < 2 * r + 1; ++j) {
+        float val = ((float)j - r) / sigma;
+        val = (float)std::exp(-0.5 * (val * val));
+        taps_host[j] = val;
+        sum += val;
+    }
+    for (int j = 0; j < 2 * r + 1; ++j) taps_host[j] = taps_host[j] / sum;
+    *radius = r;
+    return NM_OK;
+}
+
+extern "C" int nm_sift_destroy(nm_sift_ctx* c)
+{
+    if (!c) return NM_OK;
+    for (void* p : c->allocs) cudaFree(p);
+    for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    delete c;
+    return NM_OK;
+}
+
+extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, int max_batch, int capacity)
+{
+    if (!out || !params || max_batch <= 0 || capacity <= 0) return NM_ERR_INVALID;
+    const nm_sift_params& P = *params;
+    if (P.width <= 0 || P.height <= 0 || P.num_octaves <= 0 || P.num_octaves > NM_MAX_OCTAVES ||
+        P.num_dog_levels != 3 || P.num_sigmas != 5)
+        return NM_ERR_INVALID;
+    if ((P.width >> (P.num_octaves - 1)) < 3 || (P.height >> (P.num_octaves - 1)) < 3) return NM_ERR_INVALID;
+    const int cc = nm_device_cc();
+    if (cc < 0) return cc;
+    if (cc / 10 != 10) return NM_ERR_NO_DEVICE;
+    nm_sift_ctx* c = new (std::nothrow) nm_sift_ctx();
+    if (!c) return NM_ERR_ALLOC;
+    c->P = P; c->B = max_batch; c->capacity = capacity; c->n_oct = P.num_octaves;
+    c->scratch = nullptr; c->exact_desc = 0; c->last_launches = 0; c->timing = 0;
+    for (int i = 0; i < 6; ++i) c->ev[i] = nullptr;
+    int rc = NM_OK;
+    // Gaussian kernels
+    for (int i = 0; i < 6 && rc == NM_OK; ++i) {
+        float host[96];
+        rc = nm_gaussian_taps(i == 0 ? P.base_smooth : P.sigmas[i - 1], host, &c->radii[i]);
+        if (rc != NM_OK) break;
+        rc = dev_alloc(c, &c->taps[i], 96);
+        if (rc == NM_OK && cudaMemcpy(c->taps[i], host, sizeof(float) * (2 * c->radii[i] + 1), cudaMemcpyHostToDevice) != cudaSuccess)
+            rc = NM_ERR_ALLOC;
+    }
+    c->tab.n_oct = c->n_oct;
+    const size_t B = (size_t)max_batch;
+    for (int o = 0; o < c->n_oct && rc == NM_OK; ++o) {
+        NmOctave& oc = c->tab.o[o];
+        oc.w = P.width >> o; oc.h = P.height >> o;
+        oc.pitch = (oc.w + 31) / 32 * 32;
+        oc.wpr = (oc.w + 31) / 32;
+        oc.level_elems = (long long)oc.h * oc.pitch;
+        oc.xper = (float)std::pow(2.0, o);                        // siftfunctions.cu:118
+        const size_t nwords = (size_t)oc.h * oc.wpr;
+        if (rc == NM_OK) rc = dev_alloc(c, &oc.levels, B * 6 * (size_t)oc.level_elems);
+        if (rc == NM_OK) rc = dev_alloc(c, &oc.grad, B * 3 * (size_t)oc.level_elems);
+        if (rc == NM_OK) rc = dev_alloc(c, &oc.bitmap, B * 3 * nwords);
+        if (rc == NM_OK) rc = dev_alloc(c, &oc.wprefix, B * 3 * nwords);
+    }
+    const size_t S = (size_t)c->n_oct * 3, cap = (size_t)capacity;
+    if (rc == NM_OK) rc = dev_alloc(c, &c->seg_raw, B * S);
+    if (rc == NM_OK) rc = dev_alloc(c, &c->seg_cnt, B * S);
+    if (rc == NM_OK) rc = dev_alloc(c, &c->seg_off, B * S);
+    if (rc == NM_OK) rc = dev_alloc(c, &c->counts, B);
+    if (rc == NM_OK) rc = dev_alloc(c, &c->meta, B * cap);
+    if (rc == NM_OK) rc = dev_alloc(c, &c->kpts, B * cap);
+    if (rc == NM_OK) rc = dev_alloc(c, &c->orient, B * cap);
+    if (rc == NM_OK) rc = dev_alloc(c, &c->desc, B * cap * 128);
+    if (rc == NM_OK) rc = dev_alloc(c, &c->x, B * cap);
+    if (rc == NM_OK) rc = dev_alloc(c, &c->y, B * cap);
+    if (rc == NM_OK) rc = dev_alloc(c, &c->frames_stage, B * (size_t)P.width * P.height);
+    if (rc == NM_OK) {
+        // descriptor slots start at 0 like SiftData::initialize_data (siftdata.cu:34)
+        if (cudaMemset(c->desc, 0, B * cap * 128 * sizeof(float)) != cudaSuccess) rc = NM_ERR_ALLOC;
+        cudaMemset(c->counts, 0, B * sizeof(int));
+        cudaMemset(c->seg_cnt, 0, B * S * sizeof(int));
+    }
+    for (int i = 0; i < 6 && rc == NM_OK; ++i)
+        if (cudaEventCreate(&c->ev[i]) != cudaSuccess) rc = NM_ERR_ALLOC;
+    if (rc != NM_OK) { nm_sift_destroy(c); return rc; }
+    *out = c;
+    return NM_OK;
+}
+
+extern "C" int nm_sift_run(nm_sift_ctx* c, const float* frames_dev, int n_frames, nm_stream_t stream)
+{
+    if (!c || !frames_dev || n_frames <= 0 || n_frames > c->B) return NM_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const nm_sift_params& P = c->P;
+    int launches = 0, rc;
+    NmDetectParams dp{P.peak_threshold, P.edge_threshold, P.sigma_0, P.num_dog_levels};
+    if (c->timing) cudaEventRecord(c->ev[0], st);
+    // ---- pyramid ---------------------------------------------------------------
+    for (int o = 0; o < c->n_oct; ++o) {
+        const NmOctave& oc = c->tab.o[o];
+        const long long fstride = 6 * oc.level_elems;
+        if (o == 0) {
+            NmBlurArgs a{};
+            a.src = frames_dev; a.src_pitch = P.width; a.src_fstride = (long long)P.width * P.height;
+            a.dst = oc.levels; a.dst_pitch = oc.pitch; a.dst_fstride = fstride;
+            a.taps = c->taps[0]; a.radius = c->radii[0]; a.w = oc.w; a.h = oc.h; a.batch = n_frames;
+            if ((rc = nm_blur_launch(a, st)) != NM_OK) return rc;
+            ++launches;
+        }
+        for (int i = 0; i < 5; ++i) {
+            NmBlurArgs a{};
+            a.src = oc.levels + i * oc.level_elems; a.src_pitch = oc.pitch; a.src_fstride = fstride;
+            a.dst = oc.levels + (i + 1) * oc.level_elems; a.dst_pitch = oc.pitch; a.dst_fstride = fstride;
+            a.taps = c->taps[i + 1]; a.radius = c->radii[i + 1]; a.w = oc.w; a.h = oc.h; a.batch = n_frames;
+            if (i + 1 == P.num_dog_levels && o + 1 < c->n_oct) {
+                // level 3 (sigma doubled) decimated by 2 = next octave's level 0 (downsample.cu:15-16)
+                const NmOctave& nx = c->tab.o[o + 1];
+                a.dst2 = nx.levels; a.dst2_pitch = nx.pitch; a.dst2_fstride = 6 * nx.level_elems;
+            }
+            if ((rc = nm_blur_launch(a, st)) != NM_OK) return rc;
+            ++launches;
+        }
+    }
+    if (c->timing) cudaEventRecord(c->ev[1], st);
+    // ---- DoG + extrema + refinement + gradients ----------------------------------
+    for (int o = 0; o < c->n_oct; ++o) {
+        if ((rc = nm_extrema_launch(c->tab.o[o], o, c->n_oct, dp, n_frames, st)) != NM_OK) return rc;
+        ++launches;
+    }
+    if (c->timing) cudaEventRecord(c->ev[2], st);
+    // ---- ordered compaction --------------------------------------------------------
+    if ((rc = nm_rank_launch(c->tab, n_frames, c->seg_raw, st)) != NM_OK) return rc;
+    if ((rc = nm_plan_launch(c->seg_raw, c->seg_cnt, c->seg_off, c->counts, c->n_oct, n_frames, c->capacity, st)) != NM_OK) return rc;
+    launches += 2;
+    for (int o = 0; o < c->n_oct; ++o) {
+        if ((rc = nm_emit_launch(c->tab.o[o], o, c->n_oct, dp, n_frames, c->seg_cnt, c->seg_off, c->capacity,
+                                 c->kpts, c->meta, st)) != NM_OK) return rc;
+        ++launches;
+    }
+    if (c->timing) cudaEventRecord(c->ev[3], st);
+    // ---- orientation, descriptor -----------------------------------------------------
+    if ((rc = nm_orient_launch(c->tab, n_frames, c->capacity, c->counts, c->kpts, c->meta, c->orient, st)) != NM_OK) return rc;
+    ++launches;
+    if (c->timing) cudaEventRecord(c->ev[4], st);
+    if ((rc = nm_describe_launch(c->tab, n_frames, c->capacity, c->counts, c->kpts, c->meta, c->orient, c->desc,
+                                 c->x, c->y, P.num_dog_levels, c->exact_desc, st)) != NM_OK) return rc;
+    ++launches;
+    if (c->timing) cudaEventRecord(c->ev[5], st);
+    c->last_launches = launches;
+    return NM_OK;
+}
+
+extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_frames, int* counts_host,
+                                float* desc_host, float* x_host, float* y_host, nm_stream_t stream)
+{
+    if (!c || !frames_host || !counts_host || n_frames <= 0 || n_frames > c->B) return NM_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t fpix = (size_t)c->P.width * c->P.height;
+    NM_CUDA_TRY(cudaMemcpyAsync(c->frames_stage, frames_host, fpix * n_frames * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = nm_sift_run(c, c->frames_stage, n_frames, st);
+    if (rc != NM_OK) return rc;
+    NM_CUDA_TRY(cudaMemcpyAsync(counts_host, c->counts, sizeof(int) * n_frames, cudaMemcpyDeviceToHost, st));
+    NM_CUDA_TRY(cudaStreamSynchronize(st));
+    // copy only the filled part of every frame's slots
+    for (int f = 0; f < n_frames; ++f) {
+        const size_t n = (size_t)counts_host[f], off = (size_t)f * c->capacity;
+        if (n == 0) continue;
+        if (desc_host) NM_CUDA_TRY(cudaMemcpyAsync(desc_host + off * 128, c->desc + off * 128, n * 128 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (x_host) NM_CUDA_TRY(cudaMemcpyAsync(x_host + off, c->x + off, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (y_host) NM_CUDA_TRY(cudaMemcpyAsync(y_host + off, c->y + off, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    NM_CUDA_TRY(cudaStreamSynchronize(st));
+    return NM_OK;
+}
+
+extern "C" int nm_sift_results(nm_sift_ctx* c, const float** desc, const float** x, const float** y,
+                               const int** counts, const float** kpts4, const float** orient2,
+                               const int** seg_counts)
+{
+    if (!c) return NM_ERR_INVALID;
+    if (desc) *desc = c->desc;
+    if (x) *x = c->x;
+    if (y) *y = c->y;
+    if (counts) *counts = c->counts;
+    if (kpts4) *kpts4 = reinterpret_cast<const float*>(c->kpts);
+    if (orient2) *orient2 = reinterpret_cast<const float*>(c->orient);
+    if (seg_counts) *seg_counts = c->seg_cnt;
+    return NM_OK;
+}
+
+extern "C" int nm_sift_level(nm_sift_ctx* c, int frame, int octave, int level, const float** ptr, int* pitch,
+                             int* w, int* h)
+{
+    if (!c || frame < 0 || frame >= c->B || octave < 0 || octave >= c->n_oct || level < 0 || level > 5) return NM_ERR_INVALID;
+    const NmOctave& oc = c->tab.o[octave];
+    if (ptr) *ptr = oc.levels + ((long long)frame * 6 + level) * oc.level_elems;
+    if (pitch) *pitch = oc.pitch;
+    if (w) *w = oc.w;
+    if (h) *h = oc.h;
+    return NM_OK;
+}
+
+extern "C" int nm_sift_grad(nm_sift_ctx* c, int frame, int octave, int level, const float** ptr2, int* pitch,
+                            int* w, int* h)
+{
+    if (!c || frame < 0 || frame >= c->B || octave < 0 || octave >= c->n_oct || level < 0 || level > 2) return NM_ERR_INVALID;
+    const NmOctave& oc = c->tab.o[octave];
+    if (ptr2) *ptr2 = reinterpret_cast<const float*>(oc.grad + ((long long)frame * 3 + level) * oc.level_elems);
+    if (pitch) *pitch = oc.pitch;
+    if (w) *w = oc.w;
+    if (h) *h = oc.h;
+    return NM_OK;
+}
+
+extern "C" int nm_sift_last_launches(nm_sift_ctx* c) { return c ? c->last_launches : NM_ERR_INVALID; }
+
+extern "C" int nm_sift_enable_timing(nm_sift_ctx* c, int enable)
+{
+    if (!c) return NM_ERR_INVALID;
+    c->timing = enable ? 1 : 0;
+    return NM_OK;
+}
+
+extern "C" int nm_sift_stage_ms(nm_sift_ctx* c, float* ms6)
+{
+    if (!c || !ms6) return NM_ERR_INVALID;
+    NM_CUDA_TRY(cudaEventSynchronize(c->ev[5]));
+    for (int i = 0; i < 5; ++i) NM_CUDA_TRY(cudaEventElapsedTime(&ms6[i], c->ev[i], c->ev[i + 1]));
+    NM_CUDA_TRY(cudaEventElapsedTime(&ms6[5], c->ev[0], c->ev[5]));
+    return NM_OK;
+}
+
+extern "C" int nm_sift_set_exact_descriptor(nm_sift_ctx* c, int exact)
+{
+    if (!c) return NM_ERR_INVALID;
+    c->exact_desc = exact ? 1 : 0;
+    return NM_OK;
+}

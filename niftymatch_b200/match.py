@@ -1,0 +1,73 @@
+"""Brute-force k=2 ratio-test matching through the C-ABI (nm_match_*)."""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _lib
+from ._lib import check
+from .sift import _stream_ptr
+
+
+def set_engine(engine: int) -> None:
+    """0 = exact fp32 SIMT scan, 1 = tcgen05 candidate search + fp32 re-rank, -1 = auto."""
+    check(_lib.load().nm_match_set_engine(engine), "nm_match_set_engine")
+
+
+def get_engine() -> int:
+    return _lib.load().nm_match_get_engine()
+
+
+def match(A, B, ambiguity: float = 0.8, match_io=None, want_distance: bool = False):
+    """compute_sift_matches semantics (reference src/gpu/sift/siftfunctions.cu:15-40).
+    A: (nA,128), B: (nB,128) cuda float32.  Returns match indices (int32, -1 = rejected),
+    and the nA x nB squared-distance matrix when want_distance."""
+    import torch
+    nA, nB = A.shape[0], B.shape[0]
+    if match_io is None:
+        match_io = torch.full((nA,), -1, dtype=torch.int32, device=A.device)
+    dist = torch.empty((nA, nB), dtype=torch.float32, device=A.device) if want_distance else None
+    check(_lib.load().nm_match_f32(C.c_void_p(A.data_ptr()), nA, C.c_void_p(B.data_ptr()), nB, ambiguity,
+                                   C.c_void_p(match_io.data_ptr()),
+                                   C.c_void_p(dist.data_ptr()) if dist is not None else None, _stream_ptr()), "nm_match_f32")
+    return (match_io, dist) if want_distance else match_io
+
+
+def match_top2(A, B, index_offset: int = 0):
+    """Per-shard records (nA,4) float32: (d1, bits(i1+offset), d2, 0)."""
+    import torch
+    nA, nB = A.shape[0], B.shape[0]
+    rec = torch.empty((nA, 4), dtype=torch.float32, device=A.device)
+    check(_lib.load().nm_match_top2_f32(C.c_void_p(A.data_ptr()), nA, C.c_void_p(B.data_ptr()) if nB else None, nB,
+                                        index_offset, C.c_void_p(rec.data_ptr()), _stream_ptr()), "nm_match_top2_f32")
+    return rec
+
+
+def merge_top2(recs, ambiguity: float = 0.8, match_io=None):
+    """recs: (n_shards, nA, 4) records -> match indices."""
+    import torch
+    n_shards, nA = recs.shape[0], recs.shape[1]
+    if match_io is None:
+        match_io = torch.full((nA,), -1, dtype=torch.int32, device=recs.device)
+    check(_lib.load().nm_match_merge_top2(C.c_void_p(recs.data_ptr()), n_shards, nA, ambiguity,
+                                          C.c_void_p(match_io.data_ptr()), _stream_ptr()), "nm_match_merge_top2")
+    return match_io
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous row range [lo, hi) of shard `rank` (first n % world shards get one more row)."""
+    q, r = divmod(n, world)
+    lo = rank * q + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
+
+
+def match_sharded(A, B_shard, shard_offset: int, ambiguity: float = 0.8, group=None):
+    """Database sharded by rows over the ranks of `group`, queries replicated.  Each rank scans
+    its shard, the 16-byte/query records are all-gathered (NCCL over NVLink) and merged on
+    every rank; the result is bit-identical to match(A, concat(B_shards))."""
+    import torch
+    import torch.distributed as dist
+    rec = match_top2(A, B_shard, shard_offset)
+    world = dist.get_world_size(group)
+    allrec = torch.empty((world,) + tuple(rec.shape), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(allrec, rec, group=group)
+    return merge_top2(allrec, ambiguity)

@@ -1,0 +1,129 @@
+"""Test-side bindings of the CHECKERS: the CPU oracle (oracle/libnm_oracle.so) and the
+reference's own CUDA build (oracle/_ref/libnmref.so).  Both export the same frame-level
+entry point, so one wrapper serves both.  Test infrastructure only."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "libnm_oracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libnmref.so")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def octave_dims(w, h, n_oct):
+    return [(w >> o, h >> o) for o in range(n_oct)]
+
+
+class FrameChecker:
+    """sift_frame / match on host arrays through `<prefix>_sift_frame`, `<prefix>_match`."""
+
+    def __init__(self, lib, prefix):
+        self.lib, self.prefix = lib, prefix
+        self._frame = getattr(lib, prefix + "_sift_frame")
+        self._frame.restype = C.c_int
+        self._match = getattr(lib, prefix + "_match")
+        self._match.restype = C.c_int
+
+    def sift_frame(self, image, peak=0.0, edge=-1.0, num_octaves=-1, capacity=65536, clear_grad=1,
+                   kp_cap=200000, want_levels=True, want_grad=False, orient_mode=None, orient_in=None):
+        """orient_mode: 0 = public-API orientation semantics (window clamp 10; the reference's
+        own kernel deadlocks on sm_70+, so the reference build refuses it), 1 = arithmetic of the
+        reference's kernel_orientations_naive (no clamp), 2 = injected orientations.
+        Default: 0 for the CPU oracle, 1 for the reference build."""
+        if orient_mode is None:
+            orient_mode = 0 if self.prefix == "orc" else 1
+        if orient_in is not None:
+            orient_in = np.ascontiguousarray(orient_in, dtype=np.float32)
+        h, w = image.shape
+        image = np.ascontiguousarray(image, dtype=np.float32)
+        cfg = np.array([peak, edge, num_octaves, capacity, clear_grad, orient_mode], dtype=np.float32)
+        desc = np.zeros((capacity, 128), np.float32)
+        x = np.zeros(capacity, np.float32)
+        y = np.zeros(capacity, np.float32)
+        n = C.c_int()
+        max_oct = 12
+        tot = sum((w >> o) * (h >> o) for o in range(max_oct))
+        levels = np.zeros(tot * 6, np.float32) if want_levels else None
+        grad = np.zeros(tot * 3 * 2, np.float32) if want_grad else None
+        kpts = np.zeros((kp_cap, 4), np.float32)
+        orient = np.zeros((kp_cap, 2), np.float32)
+        seg = np.zeros(max_oct * 3, np.int32)
+        n_oct = self._frame(_p(image), w, h, _p(cfg), _p(desc), _p(x), _p(y), C.byref(n), _p(levels), _p(kpts),
+                            _p(orient), _p(seg), kp_cap, _p(grad), _p(orient_in))
+        if n_oct < 0:
+            raise RuntimeError(f"{self.prefix}_sift_frame refused (code {n_oct}): orient_mode {orient_mode}")
+        out = {"n_oct": n_oct, "n": n.value, "desc": desc[: n.value], "x": x[: n.value], "y": y[: n.value],
+               "seg_counts": seg[: n_oct * 3].copy()}
+        nk = int(seg[: n_oct * 3].sum())
+        out["kpts"], out["orient"] = kpts[:nk], orient[:nk]
+        if want_levels:
+            lv, off = [], 0
+            for (ow, oh) in octave_dims(w, h, n_oct):
+                lv.append([levels[off + i * ow * oh: off + (i + 1) * ow * oh].reshape(oh, ow) for i in range(6)])
+                off += 6 * ow * oh
+            out["levels"] = lv
+        if want_grad:
+            gr, off = [], 0
+            for (ow, oh) in octave_dims(w, h, n_oct):
+                gr.append(grad[off: off + 6 * ow * oh].reshape(3, oh, ow, 2))
+                off += 6 * ow * oh
+            out["grad"] = gr
+        return out
+
+    def match(self, A, B, ambiguity=0.8, match_io=None, want_distance=False):
+        A = np.ascontiguousarray(A, np.float32)
+        B = np.ascontiguousarray(B, np.float32)
+        nA, nB = A.shape[0], B.shape[0]
+        m = np.full(nA, -1, np.int32) if match_io is None else np.ascontiguousarray(match_io, np.int32).copy()
+        if self.prefix == "orc":
+            self._match(_p(A), nA, _p(B), nB, C.c_float(ambiguity), _p(m))
+            if want_distance:
+                D = np.zeros((nA, nB), np.float32)
+                self.lib.orc_dist2(_p(A), nA, _p(B), nB, 128, _p(D))
+                return m, D
+            return m
+        D = np.zeros((nA, nB), np.float32) if want_distance else None
+        self._match(_p(A), nA, _p(B), nB, C.c_float(ambiguity), _p(m), _p(D))
+        return (m, D) if want_distance else m
+
+
+def load_oracle():
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(ROOT, "oracle", "nm_oracle.c")):
+        subprocess.check_call(["make", "-C", ROOT, "oracle/libnm_oracle.so"], stdout=subprocess.DEVNULL)
+    return FrameChecker(C.CDLL(ORACLE_SO), "orc")
+
+
+def load_reflib():
+    if not os.path.exists(REF_SO):
+        return None
+    return FrameChecker(C.CDLL(REF_SO), "nmref")
+
+
+# ---- comparison helpers shared by the CPU and GPU parity tests -------------------------
+def match_keypoints(kp_a, kp_b, tol=0.01):
+    """Greedy one-to-one association of float4 keypoints (x, y, sigma, level) by level and
+    position (<= tol px).  Returns index arrays (ia, ib)."""
+    ia, ib = [], []
+    used = np.zeros(len(kp_b), bool)
+    for i, k in enumerate(kp_a):
+        cand = np.where((kp_b[:, 3] == k[3]) & ~used & (np.abs(kp_b[:, 0] - k[0]) <= tol) & (np.abs(kp_b[:, 1] - k[1]) <= tol))[0]
+        if len(cand):
+            j = cand[np.argmin(np.abs(kp_b[cand, 0] - k[0]) + np.abs(kp_b[cand, 1] - k[1]))]
+            used[j] = True
+            ia.append(i)
+            ib.append(j)
+    return np.array(ia, int), np.array(ib, int)
+
+
+def ang_diff(a, b):
+    d = np.abs(a - b)
+    return np.minimum(d, np.abs(2 * np.pi - d))
