@@ -1,0 +1,44 @@
+"""Multi-GPU partitioning of the hot path (one process per GPU, torch.distributed).
+
+* SIFT detect+describe shards by FRAMES: each rank takes a contiguous range of the batch /
+  stream (frame_range); there is no data-path collective (weak scaling).
+* Brute-force matching against a large database shards the DATABASE rows: queries are
+  replicated, every rank scans its shard and emits one 16-byte record per query
+  (d1, i1_global, d2); the records are all-gathered (NCCL over NVLink/NVSwitch) and merged on
+  every rank.  The merged result is bit-identical to the single-GPU result.
+"""
+from __future__ import annotations
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous range [lo, hi) of shard `rank` out of `world` over n items; the first
+    n % world shards get one extra item."""
+    q, r = divmod(n, world)
+    lo = rank * q + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
+
+
+def frame_range(n_frames: int, world: int, rank: int, overlap: int = 0):
+    """Frames of a batch / stream owned by `rank`.  overlap = 1 for consecutive-frame matching
+    streams: every rank but the last also computes the first frame of the next range, so no
+    descriptors have to cross GPUs."""
+    lo, hi = shard_bounds(n_frames, world, rank)
+    return lo, min(n_frames, hi + (overlap if rank + 1 < world else 0))
+
+
+def match_sharded(A, B_shard, shard_offset: int, ambiguity: float = 0.8, group=None,
+                  top2=None, merge=None):
+    """Match replicated queries A against a row-sharded database.  `top2` / `merge` default to
+    the CUDA entry points (nm_match_top2_f32 / nm_match_merge_top2); the CPU gloo tests pass the
+    oracle's functions to exercise the same orchestration without a GPU."""
+    import torch
+    import torch.distributed as dist
+    from . import match as _m
+    top2 = top2 or _m.match_top2
+    merge = merge or _m.merge_top2
+    rec = top2(A, B_shard, shard_offset)
+    world = dist.get_world_size(group)
+    n = rec.shape[0]
+    allrec = torch.empty((world * n,) + tuple(rec.shape[1:]), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(allrec, rec.contiguous(), group=group)     # shard-major
+    return merge(allrec.view((world, n) + tuple(rec.shape[1:])), ambiguity)

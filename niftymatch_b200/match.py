@@ -51,23 +51,3 @@ def merge_top2(recs, ambiguity: float = 0.8, match_io=None):
     check(_lib.load().nm_match_merge_top2(C.c_void_p(recs.data_ptr()), n_shards, nA, ambiguity,
                                           C.c_void_p(match_io.data_ptr()), _stream_ptr()), "nm_match_merge_top2")
     return match_io
-
-
-def shard_bounds(n: int, world: int, rank: int):
-    """Contiguous row range [lo, hi) of shard `rank` (first n % world shards get one more row)."""
-    q, r = divmod(n, world)
-    lo = rank * q + min(rank, r)
-    return lo, lo + q + (1 if rank < r else 0)
-
-
-def match_sharded(A, B_shard, shard_offset: int, ambiguity: float = 0.8, group=None):
-    """Database sharded by rows over the ranks of `group`, queries replicated.  Each rank scans
-    its shard, the 16-byte/query records are all-gathered (NCCL over NVLink) and merged on
-    every rank; the result is bit-identical to match(A, concat(B_shards))."""
-    import torch
-    import torch.distributed as dist
-    rec = match_top2(A, B_shard, shard_offset)
-    world = dist.get_world_size(group)
-    allrec = torch.empty((world,) + tuple(rec.shape), dtype=rec.dtype, device=rec.device)
-    dist.all_gather_into_tensor(allrec, rec, group=group)
-    return merge_top2(allrec, ambiguity)

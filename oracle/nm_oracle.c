@@ -478,6 +478,49 @@ void orc_match_top2(const float* A, int nA, const float* B, int nB, float* d1, i
     }
 }
 
+/* --- sharded-database helpers (checker for the multi-GPU path; no reference equivalent) ---
+ * True per-row top-2 (d1, i1 + index_offset, d2) with +inf for missing entries, ties to
+ * the lowest index; rec4[a] = {d1, bits(i1), d2, 0}. */
+void orc_match_top2_true(const float* A, int nA, const float* B, int nB, int index_offset, float* rec4)
+{
+#pragma omp parallel for schedule(static)
+    for (int a = 0; a < nA; ++a) {
+        float m1 = INFINITY, m2 = INFINITY; int idx = -1;
+        for (int b = 0; b < nB; ++b) {
+            float cur = dist2(A + (size_t)a * 128, B + (size_t)b * 128, 128);
+            if (cur < m1) { m2 = m1; idx = b; m1 = cur; }
+            else if (cur < m2) m2 = cur;
+        }
+        int gi = idx < 0 ? -1 : idx + index_offset;
+        rec4[4 * a] = m1; memcpy(&rec4[4 * a + 1], &gi, 4); rec4[4 * a + 2] = m2; rec4[4 * a + 3] = 0.f;
+    }
+}
+
+/* Merge shard-major records and apply the reference's rule.  The sequential scan of
+ * match.cu:88-105 ends with min2 = (idx == 0) ? min(2139095040.0f, d2) : d2 where
+ * (d1, idx, d2) is the true top-2: the odd start value of min2 only survives while column
+ * 0 stays the minimum (the first displacement overwrites it with D[0]). */
+void orc_merge_top2(const float* recs4, int n_shards, int nA, float ambiguity, int* match_io)
+{
+    for (int a = 0; a < nA; ++a) {
+        float m1 = INFINITY, m2 = INFINITY; int mi = -1;
+        for (int s = 0; s < n_shards; ++s) {
+            const float* r = recs4 + 4 * ((size_t)s * nA + a);
+            float u1 = r[0], u2 = r[2]; int j1; memcpy(&j1, &r[1], 4);
+            if (j1 < 0) continue;
+            if (mi < 0 || u1 < m1 || (u1 == m1 && j1 < mi)) {
+                float t = m1; m1 = u1; u1 = t;
+                t = m2; m2 = u2; u2 = t;
+                mi = j1;
+            }
+            if (u1 < m2) m2 = u1;
+        }
+        if (mi < 0) continue;
+        float min2 = (mi == 0) ? fminf(2139095040.0f, m2) : m2;
+        row_rule(m1, mi, min2, ambiguity, &match_io[a]);
+    }
+}
+
 /* compute_sift_matches semantics (match_io in/out). */
 void orc_match(const float* A, int nA, const float* B, int nB, float ambiguity, int* match_io)
 {

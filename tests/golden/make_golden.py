@@ -1,0 +1,108 @@
+"""Capture golden vectors from the REFERENCE'S OWN CUDA code (oracle/_ref/libnmref.so, built
+by oracle/build_ref.sh from /root/reference) on a B200.  Run on the GPU box:
+
+    python tests/golden/make_golden.py gpurun_out/golden
+
+and copy the .npz files into tests/golden/.  The fixtures pin the CPU oracle
+(tests/test_oracle_golden.py, no GPU needed) and the CUDA product (tests/test_gpu_*.py).
+
+What the reference can and cannot produce on sm_100: everything up to the collated
+keypoints, and the descriptors, run unmodified through its public API.  Its orientation
+kernel (kernel_orientations_optim) deadlocks on sm_70+ (divergent __syncthreads), so
+orientations are captured from the reference's other kernel (kernel_orientations_naive,
+same arithmetic, no 10-px window clamp), and descriptors are captured with injected
+orientations (the CPU oracle's public-API orientations), see oracle/ref_driver.cu.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from niftymatch_b200 import synth  # noqa: E402
+from tests._util import load_oracle, load_reflib  # noqa: E402
+
+
+def crafted_match_sets():
+    """Descriptor sets with the edge cases of the reference's scan (match.cu:88-116)."""
+    B = synth.descriptors(250, 2)
+    A = synth.descriptors(200, 1, planted_from=B)
+    # exact duplicates -> min1 = min2 = 0 -> entry left untouched (match.cu:107)
+    B[9] = B[5]
+    A[0] = B[5]
+    # min2 start value 2139095040.0f only survives when column 0 is the minimum
+    A[1] = 0; A[1, 1] = 1.0e6
+    B[0] = A[1]; B[0, 0] = 42426.0            # d1 = 1.8e9 at index 0
+    B[11] = A[1]; B[11, 0] = 54772.0          # d2 = 3.0e9  -> ratio vs init = 0.84 -> -1
+    A[2] = 0; A[2, 2] = 1.0e6
+    B[7] = A[2]; B[7, 0] = 42426.0            # d1 = 1.8e9 at index 7
+    B[3] = A[2]; B[3, 0] = 54772.0            # d2 = 3.0e9  -> ratio 0.6 -> match 7
+    # tie on the minimum: lowest index wins, min2 == min1 -> ratio 1 -> -1
+    B[21] = B[20]
+    A[3] = B[20] + 1.0
+    m0 = np.full(200, 77, np.int32)           # sentinel initial values
+    return A.astype(np.float32), B.astype(np.float32), m0
+
+
+def main(outdir):
+    os.makedirs(outdir, exist_ok=True)
+    ref, orc = load_reflib(), load_oracle()
+    assert ref is not None, "oracle/_ref/libnmref.so missing"
+    # ---- parameters and taps ----
+    par = {}
+    for (w, h) in [(256, 192), (640, 480), (1920, 1080), (3840, 2160)]:
+        no, sk, s0, sd, bs = C.c_int(), C.c_float(), C.c_float(), C.c_float(), C.c_float()
+        sg = (C.c_float * 5)()
+        ref.lib.nmref_params(w, h, C.byref(no), C.byref(sk), C.byref(s0), C.byref(sd), C.byref(bs), sg)
+        par[f"params_{w}x{h}"] = np.array([no.value, sk.value, s0.value, sd.value, bs.value] + list(sg), np.float64)
+    t = (C.c_float * 96)()
+    for which in range(-1, 5):
+        r = ref.lib.nmref_taps(640, 480, which, t)
+        par[f"taps_{which}"] = np.array(t[: 2 * r + 1], np.float32)
+    np.savez_compressed(os.path.join(outdir, "params_taps.npz"), **par)
+    # ---- SIFT frames ----
+    for (w, h, seed) in [(256, 192, synth.SEED_BASE), (384, 256, synth.SEED_BASE + 3)]:
+        img = synth.scene(w, h, seed)
+        out = {"image": img}
+        for peak in (0.0, 2.0):
+            tag = f"p{int(peak)}"
+            r = ref.sift_frame(img, peak=peak, want_grad=True, orient_mode=1)
+            c = orc.sift_frame(img, peak=peak, orient_mode=0)
+            assert np.array_equal(r["seg_counts"], c["seg_counts"]), "oracle/reference keypoint counts differ"
+            ri = ref.sift_frame(img, peak=peak, want_levels=False, orient_mode=2, orient_in=c["orient"])
+            out[f"{tag}_seg_counts"] = r["seg_counts"]
+            out[f"{tag}_kpts"] = r["kpts"]
+            out[f"{tag}_orient_naive"] = r["orient"]
+            out[f"{tag}_orient_in"] = c["orient"]
+            out[f"{tag}_desc"] = ri["desc"]
+            out[f"{tag}_x"] = ri["x"]
+            out[f"{tag}_y"] = ri["y"]
+            if peak == 0.0:
+                for o in range(r["n_oct"]):
+                    out[f"level5_oct{o}"] = r["levels"][o][5]
+                    out[f"level3_oct{o}"] = r["levels"][o][3]
+                last = r["n_oct"] - 1
+                for l in range(6):
+                    out[f"level{l}_oct{last}"] = r["levels"][last][l]
+                out[f"grad_oct{last}"] = r["grad"][last]
+            print(w, h, peak, "n =", r["n"], r["seg_counts"])
+        np.savez_compressed(os.path.join(outdir, f"sift_{w}x{h}.npz"), **out)
+    # ---- matcher ----
+    A, B, m0 = crafted_match_sets()
+    m, D = ref.match(A, B, 0.8, match_io=m0, want_distance=True)
+    print("match: matched", int((m >= 0).sum()), "untouched", int((m == 77).sum()), "rows 0..3:", m[:4])
+    np.savez_compressed(os.path.join(outdir, "match_200x250.npz"), A=A, B=B, m0=m0, m=m, D=D)
+    # convolution with a width that is not a multiple of 16 and an odd radius / generic taps
+    img = synth.scene(208, 144, synth.SEED_BASE + 9)
+    taps = np.array(par["taps_2"], np.float32)
+    res = np.zeros_like(img)
+    ref.lib.nmref_convolve(res.ctypes.data_as(C.c_void_p), img.ctypes.data_as(C.c_void_p), 208, 144,
+                           taps.ctypes.data_as(C.c_void_p), (len(taps) - 1) // 2)
+    np.savez_compressed(os.path.join(outdir, "convolve_208x144.npz"), image=img, taps=taps, result=res)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"))

