@@ -19,7 +19,7 @@ build/obj/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(LIB): $(OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcuda
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
 
 oracle/libnm_oracle.so: oracle/nm_oracle.c
 	gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC -Wall -o $@ $< -lm

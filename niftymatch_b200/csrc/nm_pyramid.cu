@@ -15,7 +15,16 @@
 // shared-memory port, is the limiter.  Each output accumulates k = -R..R in the
 // reference's order with explicit fmaf, so the result is bitwise the reference's.
 // Algorithmic traffic: 8 B/pixel/level (one read, one write).
+//
+// The input window is fetched by TMA (cp.async.bulk.tensor.3d, one elected thread, mbarrier
+// completion): the hardware zero-fills everything outside the (w, h) tensor, which is
+// exactly the reference's zero padding, and no thread spends issue slots or scoreboard
+// stalls on the load -- two resident CTAs per SM overlap one CTA's load with the other's
+// FMA phases.  Sources that TMA cannot describe (unaligned pointer or pitch) take the same
+// kernel with plain loads.
 #include "nm_pyramid.cuh"
+#include <mutex>
+#include <cstring>
 
 namespace {
 
@@ -24,54 +33,105 @@ constexpr int kTH = 64;           // tile height (outputs)
 constexpr int kThreads = 256;
 constexpr int kRowPitch = kTW + 4;   // 132 == 4 (mod 32): conflict-free float4 per-row access
 
+// TMA needs a 16-byte aligned start in the innermost dimension, so the staged window starts
+// at x0 - RA with RA = R rounded up to a multiple of 4 (x0 is a multiple of 128).
+__host__ __device__ constexpr int radius_aligned(int R) { return (R + 3) / 4 * 4; }
 __host__ __device__ constexpr int in_pitch(int R)
 {
-    // >= kTW + 2R + 3 (float4 over-read), multiple of 4, == 4 (mod 32)
-    int p = kTW + 2 * R + 3;
+    // >= kTW + RA + R + 3 (float4 over-read), multiple of 4, == 4 (mod 32)
+    int p = kTW + radius_aligned(R) + R + 3;
     p = (p + 3) / 4 * 4;
     while (p % 32 != 4) p += 4;
     return p;
 }
 __host__ __device__ constexpr int blur_smem_bytes(int R)
 {
-    return ((kTH + 2 * R) * in_pitch(R) + (kTH + 2 * R) * kRowPitch) * (int)sizeof(float);
+    // staged window + row-pass tile + mbarrier, plus slack for the manual 128-byte alignment
+    return ((kTH + 2 * R) * in_pitch(R) + (kTH + 2 * R) * kRowPitch) * (int)sizeof(float) + 16 + 128;
 }
 
-template <int R>
-__global__ void __launch_bounds__(kThreads, 2) blur_tile_kernel(const NmBlurArgs a)
+// ---- mbarrier / TMA PTX -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE_%=;\n"
+        "bra LAB_WAIT_%=;\n"
+        "LAB_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <int R, bool TMA>
+__global__ void __launch_bounds__(kThreads, 2) blur_tile_kernel(const NmBlurArgs a, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int IH = kTH + 2 * R;          // rows staged
-    constexpr int IW = kTW + 2 * R;          // columns staged
+    constexpr int RA = radius_aligned(R);    // staged column 0 is image column x0 - RA
+    constexpr int SH = RA - R;               // first column a row-pass window really needs
+    constexpr int IW = kTW + RA + R;         // columns staged
     constexpr int IP = in_pitch(R);
     constexpr int NT = 2 * R + 1;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     float* s_in = smem;
     float* s_row = smem + IH * IP;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_row + IH * kRowPitch);
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH, f = blockIdx.z;
-    const float* __restrict__ src = a.src + (long long)f * a.src_fstride;
     float* __restrict__ dst = a.dst + (long long)f * a.dst_fstride;
 
+    if (TMA) {
+        // ---- stage the input window by TMA; out-of-tensor elements arrive as +0 -------
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(bar, IH * IP * (uint32_t)sizeof(float));
+            tma_load_3d(s_in, &tmap, bar, x0 - RA, y0 - R, f);
+        }
+    }
     float t[NT];
 #pragma unroll
     for (int k = 0; k < NT; ++k) t[k] = __ldg(a.taps + k);
-
-    // ---- stage the input window, zero fill outside the image -------------------
-    for (int i = tid; i < IH * IP; i += kThreads) {
-        const int r = i / IP, c = i - r * IP;
-        const int gy = y0 - R + r, gx = x0 - R + c;
-        float v = 0.f;
-        if (c < IW && gy >= 0 && gy < a.h && gx >= 0 && gx < a.w)
-            v = __ldg(src + (long long)gy * a.src_pitch + gx);
-        s_in[i] = v;
+    if (TMA) {
+        __syncthreads();                       // barrier initialised before anyone polls it
+        mbar_wait(bar, 0);
+    } else {
+        // ---- plain loads, zero fill outside the image ---------------------------------
+        const float* __restrict__ src = a.src + (long long)f * a.src_fstride;
+        for (int i = tid; i < IH * IP; i += kThreads) {
+            const int r = i / IP, c = i - r * IP;
+            const int gy = y0 - R + r, gx = x0 - RA + c;
+            float v = 0.f;
+            if (c < IW && gy >= 0 && gy < a.h && gx >= 0 && gx < a.w)
+                v = __ldg(src + (long long)gy * a.src_pitch + gx);
+            s_in[i] = v;
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- row pass: 8 outputs per item, lanes walk rows (pitch == 4 mod 32) -----
     {
         constexpr int P = 8;
-        constexpr int NV = (P + 2 * R + 3) / 4;      // float4 loads per item
+        constexpr int NV = (SH + P + 2 * R + 3) / 4; // float4 loads per item
         for (int it = tid; it < IH * (kTW / P); it += kThreads) {
             const int xs = it / IH, r = it - xs * IH;
             float wv[NV * 4];
@@ -87,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 2) blur_tile_kernel(const NmBlurArgs
 #pragma unroll
             for (int kk = 0; kk < NT; ++kk)
 #pragma unroll
-                for (int j = 0; j < P; ++j) acc[j] = __fmaf_rn(wv[j + kk], t[2 * R - kk], acc[j]);
+                for (int j = 0; j < P; ++j) acc[j] = __fmaf_rn(wv[SH + j + kk], t[2 * R - kk], acc[j]);
             float4* o4 = reinterpret_cast<float4*>(s_row + r * kRowPitch + xs * P);
             o4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
             o4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
@@ -163,19 +223,45 @@ __global__ void blur_cols_generic(const NmBlurArgs a)
 }
 
 template <int R>
-int launch_tile(const NmBlurArgs& a, cudaStream_t stream)
+int launch_tile(const NmBlurArgs& a, cudaStream_t stream, const NmBlurTma* tma)
 {
     static bool configured = false;
     constexpr int smem = blur_smem_bytes(R);
     if (!configured) {
-        NM_CUDA_TRY(cudaFuncSetAttribute(blur_tile_kernel<R>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        NM_CUDA_TRY(cudaFuncSetAttribute(blur_tile_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        NM_CUDA_TRY(cudaFuncSetAttribute(blur_tile_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     dim3 grid(nm_div_up(a.w, kTW), nm_div_up(a.h, kTH), a.batch);
-    blur_tile_kernel<R><<<grid, kThreads, smem, stream>>>(a);
+    if (tma && tma->valid) {
+        blur_tile_kernel<R, true><<<grid, kThreads, smem, stream>>>(a, tma->map);
+    } else {
+        CUtensorMap dummy;
+        memset(&dummy, 0, sizeof(dummy));
+        blur_tile_kernel<R, false><<<grid, kThreads, smem, stream>>>(a, dummy);
+    }
     NM_LAUNCH_CHECK();
     return NM_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encoder()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    });
+    return fn;
 }
 
 __global__ void downsample2_kernel(float* __restrict__ dst, int dw, int dh, int dpitch,
@@ -208,11 +294,30 @@ __global__ void gradient_kernel(const float* __restrict__ src, float2* __restric
 
 } // namespace
 
-int nm_blur_launch(const NmBlurArgs& a, cudaStream_t stream)
+bool nm_blur_make_tma(NmBlurTma* t, const float* src, int w, int h, int pitch, long long fstride,
+                      int batch, int radius)
+{
+    t->valid = false;
+    if (radius < 1 || radius > 16 || w <= 0 || h <= 0 || batch <= 0) return false;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) || (pitch & 3) || (batch > 1 && (fstride & 3))) return false;
+    EncodeTiledFn enc = get_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)(batch > 1 ? fstride : (long long)pitch * h) * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)in_pitch(radius), (cuuint32_t)(kTH + 2 * radius), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&t->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(src), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    t->valid = (r == CUDA_SUCCESS);
+    return t->valid;
+}
+
+int nm_blur_launch(const NmBlurArgs& a, cudaStream_t stream, const NmBlurTma* tma)
 {
     if (a.w <= 0 || a.h <= 0 || a.batch <= 0 || a.radius < 0 || a.radius > 45) return NM_ERR_INVALID;
     switch (a.radius) {
-#define NM_CASE(R) case R: return launch_tile<R>(a, stream);
+#define NM_CASE(R) case R: return launch_tile<R>(a, stream, tma);
         NM_CASE(1) NM_CASE(2) NM_CASE(3) NM_CASE(4) NM_CASE(5) NM_CASE(6) NM_CASE(7) NM_CASE(8)
         NM_CASE(9) NM_CASE(10) NM_CASE(11) NM_CASE(12) NM_CASE(13) NM_CASE(14) NM_CASE(15) NM_CASE(16)
 #undef NM_CASE
@@ -249,10 +354,9 @@ extern "C" int nm_blur_f32(float* result, const float* image, float* buffer, int
     NmBlurArgs a{};
     a.src = image; a.dst = result; a.taps = taps_dev; a.dst2 = nullptr; a.scratch = buffer;
     a.w = width; a.h = height; a.src_pitch = width; a.dst_pitch = width; a.batch = 1; a.radius = radius;
-    if (radius == 0) {   // degenerate: single tap applied twice
-        if (!buffer) return NM_ERR_INVALID;
-    }
-    return nm_blur_launch(a, (cudaStream_t)stream);
+    NmBlurTma tma;
+    nm_blur_make_tma(&tma, image, width, height, width, 0, 1, radius);
+    return nm_blur_launch(a, (cudaStream_t)stream, &tma);
 }
 
 extern "C" int nm_downsample2_f32(float* result, int rw, int rh, const float* source, int sw, int sh,

@@ -1,6 +1,7 @@
 // nm_pyramid.cuh -- internal interface of the Gaussian scale-space kernels.
 #pragma once
 #include "nm_common.cuh"
+#include <cuda.h>      // CUtensorMap (type only; the encoder is fetched at run time)
 
 struct NmBlurArgs {
     const float* src;       // [batch][h][src_pitch]
@@ -12,8 +13,21 @@ struct NmBlurArgs {
     int          w, h, src_pitch, dst_pitch, dst2_pitch, batch, radius;
 };
 
+// TMA descriptor of a blur source: 3-D tensor (x: w, y: h, frame: batch) with the row pitch
+// and frame stride of NmBlurArgs, box = the kernel's staged window.  Encoding costs a few
+// microseconds on the host, so the batched driver caches one per (octave, level).
+struct NmBlurTma {
+    CUtensorMap map;
+    bool        valid;
+};
+// Returns false when the source cannot be described to TMA (pointer / pitch not 16-byte
+// aligned, radius outside the tiled kernel's range): the caller then uses the plain-load
+// kernel, which computes the same values.
+bool nm_blur_make_tma(NmBlurTma* t, const float* src, int w, int h, int pitch, long long fstride,
+                      int batch, int radius);
+
 // Fused separable blur (rows then columns, zero padding, reference order of operations).
-int nm_blur_launch(const NmBlurArgs& a, cudaStream_t stream);
+int nm_blur_launch(const NmBlurArgs& a, cudaStream_t stream, const NmBlurTma* tma = nullptr);
 
 // dst[y][x] = src[2y][2x]
 int nm_downsample_launch(float* dst, int dw, int dh, int dpitch, long long dfstride,

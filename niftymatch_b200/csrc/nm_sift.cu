@@ -16,6 +16,8 @@ struct nm_sift_ctx {
     nm_sift_params P;
     int B, capacity, n_oct;
     NmOctaveTable tab;
+    NmBlurTma tma[NM_MAX_OCTAVES][5];   // source level i of octave o, box for radius radii[i+1]
+    int tma_batch;           // batch the cached maps were encoded for
     float* taps[6];          // 0: base kernel, 1..5: level kernels (device)
     int    radii[6];
     int *seg_raw, *seg_cnt, *seg_off, *counts, *meta;
@@ -137,7 +139,7 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
     nm_sift_ctx* c = new (std::nothrow) nm_sift_ctx();
     if (!c) return NM_ERR_ALLOC;
     c->P = P; c->B = max_batch; c->capacity = capacity; c->n_oct = P.num_octaves;
-    c->scratch = nullptr; c->exact_desc = 0; c->last_launches = 0; c->timing = 0;
+    c->scratch = nullptr; c->exact_desc = 0; c->last_launches = 0; c->timing = 0; c->tma_batch = 0;
     for (int i = 0; i < 6; ++i) c->ev[i] = nullptr;
     int rc = NM_OK;
     // Gaussian kernels
@@ -196,6 +198,16 @@ extern "C" int nm_sift_run(nm_sift_ctx* c, const float* frames_dev, int n_frames
     const nm_sift_params& P = c->P;
     int launches = 0, rc;
     NmDetectParams dp{P.peak_threshold, P.edge_threshold, P.sigma_0, P.num_dog_levels};
+    if (c->tma_batch != n_frames) {
+        // (re-)encode the TMA descriptors of the internal levels for this batch size
+        for (int o = 0; o < c->n_oct; ++o) {
+            const NmOctave& oc = c->tab.o[o];
+            for (int i = 0; i < 5; ++i)
+                nm_blur_make_tma(&c->tma[o][i], oc.levels + i * oc.level_elems, oc.w, oc.h, oc.pitch,
+                                 6 * oc.level_elems, n_frames, c->radii[i + 1]);
+        }
+        c->tma_batch = n_frames;
+    }
     if (c->timing) cudaEventRecord(c->ev[0], st);
     // ---- pyramid ---------------------------------------------------------------
     for (int o = 0; o < c->n_oct; ++o) {
@@ -206,7 +218,9 @@ extern "C" int nm_sift_run(nm_sift_ctx* c, const float* frames_dev, int n_frames
             a.src = frames_dev; a.src_pitch = P.width; a.src_fstride = (long long)P.width * P.height;
             a.dst = oc.levels; a.dst_pitch = oc.pitch; a.dst_fstride = fstride;
             a.taps = c->taps[0]; a.radius = c->radii[0]; a.w = oc.w; a.h = oc.h; a.batch = n_frames;
-            if ((rc = nm_blur_launch(a, st)) != NM_OK) return rc;
+            NmBlurTma base;
+            nm_blur_make_tma(&base, frames_dev, P.width, P.height, P.width, (long long)P.width * P.height, n_frames, c->radii[0]);
+            if ((rc = nm_blur_launch(a, st, &base)) != NM_OK) return rc;
             ++launches;
         }
         for (int i = 0; i < 5; ++i) {
@@ -219,7 +233,7 @@ extern "C" int nm_sift_run(nm_sift_ctx* c, const float* frames_dev, int n_frames
                 const NmOctave& nx = c->tab.o[o + 1];
                 a.dst2 = nx.levels; a.dst2_pitch = nx.pitch; a.dst2_fstride = 6 * nx.level_elems;
             }
-            if ((rc = nm_blur_launch(a, st)) != NM_OK) return rc;
+            if ((rc = nm_blur_launch(a, st, &c->tma[o][i])) != NM_OK) return rc;
             ++launches;
         }
     }
