@@ -153,6 +153,12 @@ int nm_match_merge_top2(const float* recs4, int n_shards, int nA, float ambiguit
 int nm_match_set_engine(int engine);
 int nm_match_get_engine(void);
 
+/* Diagnostics of the tensor-core engine: records like nm_match_top2_f32 (index_offset 0), and
+ * *fallback_rows = number of query rows whose exactness certificate failed and that were
+ * re-scanned by the exact fp32 engine (host int; the call synchronises the stream). */
+int nm_match_tc_probe(const float* A, int nA, const float* B, int nB, float* rec4,
+                      int* fallback_rows, nm_stream_t stream);
+
 /* ------------------------------------------------------------------------ */
 /* Batched SIFT detect+describe: the client loop of the reference             */
 /* (compute_dog/_gradients/_keypoints/_orientations/_descriptors,             */

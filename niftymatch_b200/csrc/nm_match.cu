@@ -42,23 +42,36 @@ __device__ __forceinline__ void rec_merge(float& t1, int& i1, float& t2, float u
     (void)j1; (void)u2;
 }
 
-template <bool WRITE_D>
+// ROWS = false: query rows are 0..nA-1, one row tile per blockIdx.x.
+// ROWS = true : query rows are row_list[0 .. *row_count) (device-side count, e.g. the rows the
+//               tensor-core engine could not certify); blocks stride over the listed row tiles
+//               and records are written by LIST POSITION (part[split * nA + k]).
+template <bool WRITE_D, bool ROWS>
 __global__ void __launch_bounds__(256) scan_exact_kernel(const float* __restrict__ A, long long a_sa,
                                                          long long a_sk, int nA, const float* __restrict__ B,
                                                          int nB, int dim, int index_offset, int b_tiles_per_split,
                                                          float4* __restrict__ part, float* __restrict__ D,
-                                                         long long d_sa, long long d_sb)
+                                                         long long d_sa, long long d_sb,
+                                                         const int* __restrict__ row_list,
+                                                         const int* __restrict__ row_count)
 {
     __shared__ __align__(16) float As[MK][MP];
     __shared__ __align__(16) float Bs[MK][MP];
     __shared__ float4 s_rec[MT][17];
+    __shared__ int s_rows[MT];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int a0 = blockIdx.x * MT;
     const int split = blockIdx.y;
     const int n_btiles = (nB + MT - 1) / MT;
     const int bt_beg = split * b_tiles_per_split;
     const int bt_end = min(bt_beg + b_tiles_per_split, n_btiles);
+    const int n_rows = ROWS ? min(*row_count, nA) : nA;
 
+  for (int a0 = blockIdx.x * MT; a0 < n_rows; a0 += gridDim.x * MT) {
+    if (ROWS) {
+        __syncthreads();
+        if (tid < MT) s_rows[tid] = a0 + tid < n_rows ? row_list[a0 + tid] : -1;
+        __syncthreads();
+    }
     float t1[4], t2[4]; int i1[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { t1[i] = INFINITY; t2[i] = INFINITY; i1[i] = 0x7fffffff; }
@@ -78,7 +91,8 @@ __global__ void __launch_bounds__(256) scan_exact_kernel(const float* __restrict
                 const int k = idx & (MK - 1), r = idx >> 5;
                 float va = 0.f, vb = 0.f;
                 if (k0 + k < dim) {
-                    if (a0 + r < nA) va = __ldg(A + (long long)(a0 + r) * a_sa + (long long)(k0 + k) * a_sk);
+                    const int ar = ROWS ? s_rows[r] : (a0 + r < nA ? a0 + r : -1);
+                    if (ar >= 0) va = __ldg(A + (long long)ar * a_sa + (long long)(k0 + k) * a_sk);
                     if (b0 + r < nB) vb = __ldg(B + (long long)(b0 + r) * dim + (k0 + k));
                 }
                 As[k][r] = va; Bs[k][r] = vb;
@@ -125,10 +139,29 @@ __global__ void __launch_bounds__(256) scan_exact_kernel(const float* __restrict
             const float4 q = s_rec[tid][k];
             rec_merge(m1, mi, m2, q.x, __float_as_int(q.y), q.z);
         }
-        if (a < nA) {
+        if (a < n_rows) {
             if (mi != 0x7fffffff) mi += index_offset; else mi = -1;
             part[(long long)split * nA + a] = make_float4(m1, __int_as_float(mi), m2, 0.f);
         }
+    }
+    __syncthreads();                                              // s_rec reused by the next row tile
+  }
+}
+
+// Merge of the per-split records of a row list: out_rec[row_list[k]] for k < *row_count.
+__global__ void merge_rows_kernel(const float4* __restrict__ part, int n_splits, int nA, const int* __restrict__ row_list,
+                                  const int* __restrict__ row_count, float4* __restrict__ out_rec)
+{
+    const int n_rows = min(*row_count, nA);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_rows; k += gridDim.x * blockDim.x) {
+        float m1 = INFINITY, m2 = INFINITY; int mi = 0x7fffffff;
+        for (int s = 0; s < n_splits; ++s) {
+            const float4 q = part[(long long)s * nA + k];
+            int qi = __float_as_int(q.y);
+            if (qi < 0) qi = 0x7fffffff;
+            rec_merge(m1, mi, m2, q.x, qi, q.z);
+        }
+        out_rec[row_list[k]] = make_float4(m1, __int_as_float(mi == 0x7fffffff ? -1 : mi), m2, 0.f);
     }
 }
 
@@ -208,9 +241,9 @@ int nm_match_scan_exact(const float* A, long long a_sa, long long a_sk, int nA, 
     if (splits > 1) NM_CUDA_TRY(cudaMallocAsync(&part, sizeof(float4) * (size_t)splits * nA, stream));
     dim3 grid(a_tiles, splits);
     if (D)
-        scan_exact_kernel<true><<<grid, 256, 0, stream>>>(A, a_sa, a_sk, nA, B, nB, dim, index_offset, per, part, D, d_sa, d_sb);
+        scan_exact_kernel<true, false><<<grid, 256, 0, stream>>>(A, a_sa, a_sk, nA, B, nB, dim, index_offset, per, part, D, d_sa, d_sb, nullptr, nullptr);
     else
-        scan_exact_kernel<false><<<grid, 256, 0, stream>>>(A, a_sa, a_sk, nA, B, nB, dim, index_offset, per, part, nullptr, 0, 0);
+        scan_exact_kernel<false, false><<<grid, 256, 0, stream>>>(A, a_sa, a_sk, nA, B, nB, dim, index_offset, per, part, nullptr, 0, 0, nullptr, nullptr);
     cudaError_t e = cudaGetLastError();
     if (splits > 1) {
         if (e == cudaSuccess) {
@@ -222,6 +255,31 @@ int nm_match_scan_exact(const float* A, long long a_sa, long long a_sk, int nA, 
     return nm_cuda_err(e);
 }
 
+// Exact records for the rows row_list[0 .. *row_count) only (count lives on the device, no host
+// synchronisation): the database is cut into ~1024-row splits so that even a handful of rows
+// spreads over the machine; a fixed-size grid strides over the listed row tiles.
+int nm_match_scan_exact_rows(const float* A, int nA, const float* B, int nB, int dim, int index_offset,
+                             const int* row_list, const int* row_count, float4* rec4, cudaStream_t stream)
+{
+    if (nA <= 0 || nB <= 0 || dim <= 0 || !row_list || !row_count) return NM_ERR_INVALID;
+    const int b_tiles = nm_div_up(nB, MT);
+    int splits = min(b_tiles, max(1, nm_div_up(nB, 1024)));
+    const int per = nm_div_up(b_tiles, splits);
+    splits = nm_div_up(b_tiles, per);
+    const int row_blocks = min(nm_div_up(nA, MT), 64);
+    float4* part = nullptr;
+    NM_CUDA_TRY(cudaMallocAsync(&part, sizeof(float4) * (size_t)splits * nA, stream));
+    scan_exact_kernel<false, true><<<dim3(row_blocks, splits), 256, 0, stream>>>(
+        A, dim, 1, nA, B, nB, dim, index_offset, per, part, nullptr, 0, 0, row_list, row_count);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        merge_rows_kernel<<<min(nm_div_up(nA, 256), 64), 256, 0, stream>>>(part, splits, nA, row_list, row_count, rec4);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(part, stream);
+    return nm_cuda_err(e);
+}
+
 int nm_match_finalize(const float4* recs, int n_shards, int nA, float ambiguity, int* match_io, cudaStream_t stream)
 {
     merge_kernel<<<nm_div_up(nA, 256), 256, 0, stream>>>(recs, n_shards, nA, nullptr, 1, ambiguity, match_io);
@@ -229,10 +287,14 @@ int nm_match_finalize(const float4* recs, int n_shards, int nA, float ambiguity,
     return NM_OK;
 }
 
-static int pick_engine()
+// Auto policy: both engines return the same exact records, so the choice is purely a matter of
+// speed -- the tensor-core engine pays ~6 extra small launches (pack, rerank, fallback) and wins
+// once there are a few million pairs to scan.
+static int pick_engine(long long pairs = -1)
 {
     if (g_engine >= 0) return g_engine;
-    return nm_match_tc_available() ? 1 : 0;
+    if (!nm_match_tc_available()) return 0;
+    return (pairs < 0 || pairs >= (1ll << 22)) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -252,7 +314,7 @@ extern "C" int nm_match_top2_f32(const float* A, int nA, const float* B, int nB,
 {
     if (!A || !rec4 || nA <= 0 || nB < 0 || (nB > 0 && !B)) return NM_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    if (pick_engine() == 1 && nB > 0)
+    if (nB > 0 && pick_engine((long long)nA * nB) == 1)
         return nm_match_scan_tc(A, nA, B, nB, index_offset, reinterpret_cast<float4*>(rec4), st);
     return nm_match_scan_exact(A, 128, 1, nA, B, nB, 128, index_offset, reinterpret_cast<float4*>(rec4), nullptr, 0, 0, st);
 }
@@ -272,7 +334,7 @@ extern "C" int nm_match_f32(const float* A, int nA, const float* B, int nB, floa
     float4* rec = nullptr;
     NM_CUDA_TRY(cudaMallocAsync(&rec, sizeof(float4) * (size_t)nA, st));
     int rc;
-    if (distance || pick_engine() == 0)
+    if (distance || pick_engine((long long)nA * nB) == 0)
         rc = nm_match_scan_exact(A, 128, 1, nA, B, nB, 128, 0, rec, distance, nB, 1, st);
     else
         rc = nm_match_scan_tc(A, nA, B, nB, 0, rec, st);

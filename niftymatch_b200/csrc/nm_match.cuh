@@ -13,6 +13,10 @@ int nm_match_scan_exact(const float* A, long long a_sa, long long a_sk, int nA, 
                         int dim, int index_offset, float4* rec4, float* D, long long d_sa, long long d_sb,
                         cudaStream_t stream);
 
+// The same exact scan restricted to the query rows row_list[0 .. *row_count) (both on the device).
+int nm_match_scan_exact_rows(const float* A, int nA, const float* B, int nB, int dim, int index_offset,
+                             const int* row_list, const int* row_count, float4* rec4, cudaStream_t stream);
+
 // Tensor-core candidate search + exact re-rank (nm_match_tc.cu).  Same record contract.
 int nm_match_scan_tc(const float* A, int nA, const float* B, int nB, int index_offset, float4* rec4,
                      cudaStream_t stream);
