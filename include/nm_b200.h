@@ -155,9 +155,13 @@ int nm_match_get_engine(void);
 
 /* Diagnostics of the tensor-core engine: records like nm_match_top2_f32 (index_offset 0), and
  * *fallback_rows = number of query rows whose exactness certificate failed and that were
- * re-scanned by the exact fp32 engine (host int; the call synchronises the stream). */
+ * re-scanned by the exact fp32 engine (host int; the call synchronises the stream).
+ * Optional HOST outputs (may be NULL): the candidate lists of the tensor-core scan,
+ * cand_scores/cand_index [n_lists][nA][4] (room for 8 lists), *n_lists, and the power-of-two
+ * *scale applied before the fp16 rounding. */
 int nm_match_tc_probe(const float* A, int nA, const float* B, int nB, float* rec4,
-                      int* fallback_rows, nm_stream_t stream);
+                      int* fallback_rows, float* cand_scores_host, int* cand_index_host,
+                      int* n_lists, float* scale, nm_stream_t stream);
 
 /* ------------------------------------------------------------------------ */
 /* Batched SIFT detect+describe: the client loop of the reference             */

@@ -37,6 +37,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -48,8 +49,9 @@ constexpr int TC_KSTRIDE = TC_TROWS * 16;           // bytes between consecutive
 constexpr int TC_ROWBLK = 2 * TC_TROWS;             // query rows per CTA
 constexpr int TC_NST = 4;                           // B stages in shared memory
 constexpr int TC_K = 4;                             // candidates kept per (row, split)
-constexpr int TC_MAX_SPLITS = 8;                    // 8 x 4 = 32 candidates = one warp in rerank
-constexpr int TC_THREADS = 320;                     // warp 0 copy, warp 1 mma, warps 2..9 epilogue
+constexpr int TC_MAX_SPLITS = 4;                    // 4 splits x 2 column halves x 4 = 32 candidates = one warp in rerank
+constexpr int TC_EPI_WARPS = 16;                    // 2 row halves x 4 lane quadrants x 2 column halves
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0 copy, warp 1 mma, warps 2..17 epilogue
 constexpr float TC_AUG_C = 256.f;
 constexpr float TC_PAD_H0 = -60000.f;               // padded database rows: score -1.536e7 < any real score
 constexpr int TC_SMEM_BYTES = (2 + TC_NST) * TC_TILE_BYTES + 256;
@@ -126,6 +128,14 @@ __device__ __forceinline__ void tc_ld64(uint32_t taddr, float (&v)[64])
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8])
+{
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 bytes stored
@@ -150,7 +160,8 @@ __host__ __device__ constexpr uint32_t tc_idesc(int M, int N)
 // ---------------------------------------------------------------------------------------
 // 1. pack
 // ---------------------------------------------------------------------------------------
-// hdr[0] = bits of max |x| over A and B; hdr[1] = bits of max |b|^2 (unscaled) over B.
+// hdr[0] = bits of max |x| over A and B; hdr[1] = bits of max |b|^2 (unscaled) over B;
+// hdr[2] = bits of max |b^ - s b|^2 over B (the squared fp16 rounding displacement, scaled units).
 __global__ void __launch_bounds__(256) tc_absmax_kernel(const float* __restrict__ X, long long n, unsigned* __restrict__ hdr)
 {
     float m = 0.f;
@@ -179,7 +190,7 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ 
     const float scale = tc_scale_from_max(hdr[0]);
     const int tile = blockIdx.x, rr = threadIdx.x >> 4, kc = threadIdx.x & 15;
     uint8_t* tout = out + (size_t)tile * TC_TILE_BYTES;
-    float bmax2 = 0.f;
+    float bmax2 = 0.f, emax2 = 0.f;
     for (int pass = 0; pass < TC_TROWS / 16; ++pass) {
         const int row = pass * 16 + rr;
         const long long g = (long long)tile * TC_TROWS + row;
@@ -190,18 +201,22 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ 
             v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
         }
         __half h[8];
-        float nh = 0.f, nx = 0.f;
+        float nh = 0.f, nx = 0.f, ne = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            h[i] = __float2half_rn(v[i] * scale);
+            const float xs = v[i] * scale;                    // exact (power-of-two scale)
+            h[i] = __float2half_rn(xs);
             const float f = __half2float(h[i]);
+            const float er = f - xs;                          // exact (Sterbenz / h = 0)
             nh = fmaf(f, f, nh);
             nx = fmaf(v[i], v[i], nx);
+            ne = fmaf(er, er, ne);
         }
 #pragma unroll
         for (int d = 8; d > 0; d >>= 1) {
             nh += __shfl_xor_sync(0xffffffffu, nh, d);
             nx += __shfl_xor_sync(0xffffffffu, nx, d);
+            ne += __shfl_xor_sync(0xffffffffu, ne, d);
         }
         *reinterpret_cast<uint4*>(tout + kc * TC_KSTRIDE + row * 16) = *reinterpret_cast<const uint4*>(h);
         if (kc < 2) {
@@ -227,9 +242,12 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ 
             }
             *reinterpret_cast<uint4*>(tout + (16 + kc) * TC_KSTRIDE + row * 16) = *reinterpret_cast<const uint4*>(a);
         }
-        if (IS_DB && g < n) bmax2 = fmaxf(bmax2, nx);
+        if (IS_DB && g < n) { bmax2 = fmaxf(bmax2, nx); emax2 = fmaxf(emax2, ne); }
     }
-    if (IS_DB && kc == 0 && bmax2 > 0.f) atomicMax(hdr + 1, __float_as_uint(bmax2));
+    if (IS_DB && kc == 0) {
+        if (bmax2 > 0.f) atomicMax(hdr + 1, __float_as_uint(bmax2));
+        if (emax2 > 0.f) atomicMax(hdr + 2, __float_as_uint(emax2));
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -238,8 +256,8 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ 
 struct TcScanArgs {
     const uint8_t* a_pack;      // [ceil(nA/256)*2] tiles
     const uint8_t* b_pack;      // [n_btiles] tiles
-    float4*        cand_s;      // [n_splits][nA] 4 best scores, descending
-    int4*          cand_i;      // [n_splits][nA] their database rows
+    float4*        cand_s;      // [2 * n_splits][nA] 4 best scores, descending (list = split * 2 + column half)
+    int4*          cand_i;      // [2 * n_splits][nA] their database rows
     int            nA, n_btiles, tiles_per_split;
     uint32_t       lbo, sbo;    // descriptor strides in bytes (k-chunk stride, 8-row-group stride)
 };
@@ -248,7 +266,8 @@ struct TcScanArgs {
     do {                                                                                           \
         const float v_ = (val);                                                                    \
         if (v_ > s3) {                                                                             \
-            const int j_ = (idx);                                                                  \
+            const int j_ = (idx); /* NB: callers must not use the names v_ / j_ in val / idx */    \
+                                                                            \
             if (v_ > s2) {                                                                         \
                 s3 = s2; i3 = i2;                                                                  \
                 if (v_ > s1) {                                                                     \
@@ -257,6 +276,30 @@ struct TcScanArgs {
                     else { s1 = v_; i1 = j_; }                                                     \
                 } else { s2 = v_; i2 = j_; }                                                       \
             } else { s3 = v_; i3 = j_; }                                                           \
+        }                                                                                          \
+    } while (0)
+
+// 64 scores of one row (registers v, TMEM address ta): 8 group maxima by FMNMX3 chains; the
+// groups in which ANY lane of the warp beats its row's 4th-best score (warp-wide OR of the
+// per-lane group masks) are re-read from TMEM at a run-time column address and walked element
+// by element.  Re-reading instead of indexing registers keeps the insertion code to one copy
+// per call site: an earlier version that unrolled the insertion over all 64 registers was
+// 80 KB of SASS and stalled on instruction fetch (ncu: stalled_no_instruction 9.5 per issue).
+#define TC_GMAX(v, j)                                                                              \
+    fmaxf(fmaxf(fmaxf(fmaxf(v[8 * (j)], v[8 * (j) + 1]), v[8 * (j) + 2]), fmaxf(v[8 * (j) + 3], v[8 * (j) + 4])),  \
+          fmaxf(fmaxf(v[8 * (j) + 5], v[8 * (j) + 6]), v[8 * (j) + 7]))
+#define TC_CHUNK(v, ta, col0)                                                                      \
+    do {                                                                                           \
+        unsigned mask_ = 0;                                                                        \
+        _Pragma("unroll") for (int j = 0; j < 8; ++j) mask_ |= (TC_GMAX(v, j) > s3 ? 1u : 0u) << j; \
+        unsigned um_ = __reduce_or_sync(0xffffffffu, mask_);                                       \
+        while (um_) {                                                                              \
+            const int grp_ = __ffs(um_) - 1;                                                       \
+            um_ &= um_ - 1;                                                                        \
+            float w_[8];                                                                           \
+            tc_ld8((ta) + 8 * grp_, w_);                                                           \
+            tc_wait_ld();                                                                          \
+            _Pragma("unroll") for (int e = 0; e < 8; ++e) TC_INSERT(w_[e], (col0) + 8 * grp_ + e); \
         }                                                                                          \
     } while (0)
 
@@ -282,7 +325,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const TcScanArgs
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_NST; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         mbar_init(a_full, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -337,61 +380,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const TcScanArgs
     } else {
         // ---- epilogue warps: running 4 best scores of one query row per thread ------------
         const int q = warp & 3;                 // TMEM lane quadrant this warp may read
-        const int half = (warp - 2) >> 2;       // which 128-row half of the CTA's rows
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int e4 = (warp - 2) >> 2;         // 0..3
+        const int half = e4 & 1;                // which 128-row half of the CTA's rows
+        const int ch = e4 >> 1;                 // which 64-column half of every B tile
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128 + ch * 64);
         float s0 = -FLT_MAX, s1 = -FLT_MAX, s2 = -FLT_MAX, s3 = -FLT_MAX;
         int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
         for (int i = 0; i < nt; ++i) {
             const int as = i & 1;
             mbar_wait(acc_full + as, (i >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = lane_addr + (uint32_t)((as * 2 + half) * 128);
-            const int gcol = (t0 + i) * TC_TROWS;
-            float va[64], vb[64];
+            const uint32_t taddr = lane_addr + (uint32_t)(as * 256);
+            const int gcol = (t0 + i) * TC_TROWS + ch * 64;
+            float va[64];
             tc_ld64(taddr, va);
             tc_wait_ld();
-            tc_ld64(taddr + 64, vb);
-            {
-                float m0 = va[0], m1 = va[1], m2 = va[2], m3 = va[3];
-#pragma unroll
-                for (int e = 4; e < 64; e += 8) {
-                    m0 = fmaxf(fmaxf(m0, va[e]), va[e + 1]);
-                    m1 = fmaxf(fmaxf(m1, va[e + 2]), va[e + 3]);
-                    m2 = fmaxf(fmaxf(m2, va[e + 4]), va[e + 5]);
-                    m3 = fmaxf(fmaxf(m3, va[e + 6]), va[e + 7]);
-                }
-                m0 = fmaxf(fmaxf(m0, va[60]), va[61]);
-                m1 = fmaxf(fmaxf(m1, va[62]), va[63]);
-                if (fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > s3) {
-#pragma unroll
-                    for (int e = 0; e < 64; ++e) TC_INSERT(va[e], gcol + e);
-                }
-            }
-            tc_wait_ld();
+            TC_CHUNK(va, taddr, gcol);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + as);   // TMEM stage drained into registers
-            {
-                float m0 = vb[0], m1 = vb[1], m2 = vb[2], m3 = vb[3];
-#pragma unroll
-                for (int e = 4; e < 64; e += 8) {
-                    m0 = fmaxf(fmaxf(m0, vb[e]), vb[e + 1]);
-                    m1 = fmaxf(fmaxf(m1, vb[e + 2]), vb[e + 3]);
-                    m2 = fmaxf(fmaxf(m2, vb[e + 4]), vb[e + 5]);
-                    m3 = fmaxf(fmaxf(m3, vb[e + 6]), vb[e + 7]);
-                }
-                m0 = fmaxf(fmaxf(m0, vb[60]), vb[61]);
-                m1 = fmaxf(fmaxf(m1, vb[62]), vb[63]);
-                if (fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > s3) {
-#pragma unroll
-                    for (int e = 0; e < 64; ++e) TC_INSERT(vb[e], gcol + 64 + e);
-                }
-            }
+            if (lane == 0) mbar_arrive(acc_empty + as);   // this warp is done with the TMEM stage
         }
         const int row = rb * TC_ROWBLK + half * TC_TROWS + q * 32 + lane;
         if (row < p.nA) {
-            p.cand_s[(size_t)split * p.nA + row] = make_float4(s0, s1, s2, s3);
-            p.cand_i[(size_t)split * p.nA + row] = make_int4(i0, i1, i2, i3);
+            p.cand_s[(size_t)(split * 2 + ch) * p.nA + row] = make_float4(s0, s1, s2, s3);
+            p.cand_i[(size_t)(split * 2 + ch) * p.nA + row] = make_int4(i0, i1, i2, i3);
         }
     }
     tc_fence_before();
@@ -416,7 +428,7 @@ __device__ __forceinline__ void rec_merge_lex(float& t1, int& i1, float& t2, flo
 }
 
 __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict__ A, int nA, const float* __restrict__ B,
-                                                        int nB, int n_splits, const float4* __restrict__ cand_s,
+                                                        int nB, int n_lists, const float4* __restrict__ cand_s,
                                                         const int4* __restrict__ cand_i, const unsigned* __restrict__ hdr,
                                                         int index_offset, float4* __restrict__ rec4,
                                                         int* __restrict__ fb_list, int* __restrict__ fb_count)
@@ -429,19 +441,21 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict_
     *reinterpret_cast<float4*>(&s_a[wid][lane * 4]) = av;
     // norms of the row: exact-ish |a| and the fp16-rounded |a^| (scaled units), in double
     const float scale = tc_scale_from_max(hdr[0]);
-    double na2 = 0.0, nh2 = 0.0;
+    double ne2 = 0.0, nh2 = 0.0;
     {
         const float x[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            na2 += (double)x[i] * (double)x[i];
-            const double hf = (double)__half2float(__float2half_rn(x[i] * scale));
+            const float xs = x[i] * scale;
+            const double hf = (double)__half2float(__float2half_rn(xs));
+            const double er = hf - (double)xs;
             nh2 += hf * hf;
+            ne2 += er * er;
         }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
-        na2 += __shfl_xor_sync(0xffffffffu, na2, d);
+        ne2 += __shfl_xor_sync(0xffffffffu, ne2, d);
         nh2 += __shfl_xor_sync(0xffffffffu, nh2, d);
     }
     __syncwarp();
@@ -449,7 +463,7 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict_
     const int sp = lane >> 2, k = lane & 3;
     int idx = -1;
     float thr = -FLT_MAX;                                         // 4th-best score of the lane's split
-    if (sp < n_splits) {
+    if (sp < n_lists) {
         const int4 ci = cand_i[(size_t)sp * nA + a];
         const float4 cs = cand_s[(size_t)sp * nA + a];
         idx = k == 0 ? ci.x : k == 1 ? ci.y : k == 2 ? ci.z : ci.w;
@@ -473,6 +487,7 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict_
         dist = acc;
         jdx = idx;
     }
+    const int n_valid = __popc(__ballot_sync(0xffffffffu, jdx != 0x7fffffff));
     float t1 = dist, t2 = INFINITY;
     int i1 = jdx;
 #pragma unroll
@@ -486,15 +501,17 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict_
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) thr = fmaxf(thr, __shfl_xor_sync(0xffffffffu, thr, d));
     if (lane == 0) {
-        // Scaled units: score S = a^.b^ - |b^|^2/2 (+- eta/2), so |a^-b^|^2 >= |a^|^2 - 2 thr - eta for
-        // every non-candidate; rounding to fp16 moved a and b by at most 2^-11 of their norms (plus the
-        // subnormal floor), so sqrt(true d) * scale >= sqrt(that) - delta.
+        // Scaled units (s = the power-of-two scale): the accumulator holds S = a^.b^ - |b^|^2/2 up to an
+        // accumulation error <= eta/2, so every non-candidate has |a^-b^|^2 >= |a^|^2 - 2 thr - eta.
+        // Rounding to fp16 displaced a by |a^ - s a| (measured here) and any b by at most
+        // max_j |b^_j - s b_j| (measured by the pack kernel), so by the triangle inequality
+        // s * sqrt(true d) >= sqrt(|a^-b^|^2) - delta.
         const double sc = (double)scale;
-        const double bmax = sqrt((double)__uint_as_float(hdr[1])) * (1.0 + 1e-6);
-        const double eta = ldexp(nh2 + bmax * bmax * sc * sc, -16);
-        const double delta = ldexp((sqrt(na2) + bmax) * sc, -11) * (1.0 + 1e-6) + 1e-5;
+        const double bmax2 = (double)__uint_as_float(hdr[1]) * sc * sc * (1.0 + 1e-5);
+        const double eta = ldexp(nh2 + bmax2, -17);    // measured: see tests (accumulation error < 2^-20 (|a^|^2+|b^|^2))
+        const double delta = (sqrt(ne2) + sqrt((double)__uint_as_float(hdr[2]))) * (1.0 + 1e-5) + 1e-7;
         bool certified;
-        if (thr <= -FLT_MAX) {
+        if (thr <= -FLT_MAX || n_valid >= nB) {
             certified = true;                                     // nothing was ever rejected: all columns are candidates
         } else {
             const double dh = nh2 - 2.0 * (double)thr - eta;
@@ -530,6 +547,15 @@ bool nm_match_tc_available()
                   smem >= TC_SMEM_BYTES;
         if (ok) ok = cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
         if (!ok) cudaGetLastError();
+        if (ok) {
+            // the engine allocates its workspace stream-ordered per call: keep freed blocks in the
+            // default pool instead of returning them to the driver at every synchronisation
+            cudaMemPool_t pool;
+            unsigned long long keep = ~0ull;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess ||
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess)
+                cudaGetLastError();
+        }
         // bring-up aid: NM_TC_DESC="lbo,sbo" overrides the descriptor strides (bytes)
         if (const char* env = getenv("NM_TC_DESC")) {
             unsigned l = 0, b = 0;
@@ -563,8 +589,16 @@ static int tc_pick_splits(int n_rowblocks, int n_btiles, int n_sms)
 
 // Common driver.  fb_rows_host != nullptr (diagnostics): the number of uncertified rows is copied
 // back (one stream synchronisation); otherwise nothing synchronises.
+struct TcProbeOut {
+    int*   fb_rows;       // host: rows that failed the certificate
+    float* cand_scores;   // host or null: [n_lists][nA][4]
+    int*   cand_index;    // host or null: [n_lists][nA][4]
+    int*   n_lists;       // host
+    float* scale;         // host: the power-of-two scale used
+};
+
 static int tc_run(const float* A, int nA, const float* B, int nB, int index_offset, float4* rec4, cudaStream_t stream,
-                  int* fb_rows_host)
+                  const TcProbeOut* probe)
 {
     if (!A || !B || !rec4 || nA <= 0 || nB <= 0) return NM_ERR_INVALID;
     if (!nm_match_tc_available()) return NM_ERR_UNSUPPORTED;
@@ -583,8 +617,9 @@ static int tc_run(const float* A, int nA, const float* B, int nB, int index_offs
     const size_t off_cnt = 16;
     const size_t off_list = 32;
     const size_t off_cs = (off_list + sizeof(int) * (size_t)nA + 255) & ~size_t(255);
-    const size_t off_ci = off_cs + sizeof(float4) * (size_t)n_splits * nA;
-    const size_t off_ap = (off_ci + sizeof(int4) * (size_t)n_splits * nA + 255) & ~size_t(255);
+    const int n_lists = 2 * n_splits;
+    const size_t off_ci = off_cs + sizeof(float4) * (size_t)n_lists * nA;
+    const size_t off_ap = (off_ci + sizeof(int4) * (size_t)n_lists * nA + 255) & ~size_t(255);
     const size_t off_bp = off_ap + (size_t)n_atiles * TC_TILE_BYTES;
     const size_t total = off_bp + (size_t)n_btiles * TC_TILE_BYTES;
     uint8_t* ws = nullptr;
@@ -608,13 +643,26 @@ static int tc_run(const float* A, int nA, const float* B, int nB, int index_offs
         tc_pack_kernel<true><<<n_btiles, 256, 0, stream>>>(B, nB, hdr, b_pack);
         TcScanArgs sa{a_pack, b_pack, cand_s, cand_i, nA, n_btiles, tiles_per_split, g_lbo, g_sbo};
         tc_scan_kernel<<<dim3(n_rowblocks, n_splits), TC_THREADS, TC_SMEM_BYTES, stream>>>(sa);
-        tc_rerank_kernel<<<nm_div_up(nA, 8), 256, 0, stream>>>(A, nA, B, nB, n_splits, cand_s, cand_i, hdr, index_offset, rec4,
+        tc_rerank_kernel<<<nm_div_up(nA, 8), 256, 0, stream>>>(A, nA, B, nB, n_lists, cand_s, cand_i, hdr, index_offset, rec4,
                                                                fb_list, fb_count);
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess && fb_rows_host) {
-        e = cudaMemcpyAsync(fb_rows_host, fb_count, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && probe) {
+        unsigned hdr_host[4] = {0, 0, 0, 0};
+        e = cudaMemcpyAsync(probe->fb_rows, fb_count, sizeof(int), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hdr_host, hdr, sizeof(hdr_host), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess && probe->cand_scores)
+            e = cudaMemcpyAsync(probe->cand_scores, cand_s, sizeof(float4) * (size_t)n_lists * nA, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess && probe->cand_index)
+            e = cudaMemcpyAsync(probe->cand_index, cand_i, sizeof(int4) * (size_t)n_lists * nA, cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (probe->n_lists) *probe->n_lists = n_lists;
+        if (probe->scale) {
+            float mx; memcpy(&mx, &hdr_host[0], 4);
+            int ex = 0;
+            if (mx > 0.f) frexpf(mx, &ex);
+            *probe->scale = mx > 0.f ? ldexpf(1.f, 8 - ex) : 1.f;
+        }
     }
     int rc = nm_cuda_err(e);
     // rows whose certificate failed: exact fp32 engine on the listed rows (usually none)
@@ -631,8 +679,10 @@ int nm_match_scan_tc(const float* A, int nA, const float* B, int nB, int index_o
 // Diagnostic entry (tests, benchmarks): the tensor-core engine's records plus the number of rows
 // whose certificate failed and that were re-scanned by the exact engine.
 extern "C" int nm_match_tc_probe(const float* A, int nA, const float* B, int nB, float* rec4, int* fallback_rows,
+                                 float* cand_scores_host, int* cand_index_host, int* n_lists, float* scale,
                                  nm_stream_t stream)
 {
     if (!fallback_rows) return NM_ERR_INVALID;
-    return tc_run(A, nA, B, nB, 0, reinterpret_cast<float4*>(rec4), (cudaStream_t)stream, fallback_rows);
+    TcProbeOut po{fallback_rows, cand_scores_host, cand_index_host, n_lists, scale};
+    return tc_run(A, nA, B, nB, 0, reinterpret_cast<float4*>(rec4), (cudaStream_t)stream, &po);
 }

@@ -20,9 +20,43 @@ def probe(A, B):
     rec = torch.empty((A.shape[0], 4), dtype=torch.float32, device="cuda")
     fb = C.c_int(-1)
     rc = lib.nm_match_tc_probe(C.c_void_p(A.data_ptr()), A.shape[0], C.c_void_p(B.data_ptr()), B.shape[0],
-                               C.c_void_p(rec.data_ptr()), C.byref(fb), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                               C.c_void_p(rec.data_ptr()), C.byref(fb), None, None, None, None,
+                               C.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     return rc, rec, fb.value
+
+
+def accumulation_error(nA=3000, nB=7000):
+    """max |S_tensor - S_exact| / (|a^|^2 + |b^|^2) over the candidates the scan kept."""
+    Bh = synth.descriptors(nB, 12)
+    Ah = synth.descriptors(nA, 11, planted_from=Bh)
+    A, B = torch.from_numpy(Ah).cuda(), torch.from_numpy(Bh).cuda()
+    rec = torch.empty((nA, 4), dtype=torch.float32, device="cuda")
+    fb, nl, sc = C.c_int(-1), C.c_int(0), C.c_float(0)
+    cs = np.zeros((8, nA, 4), np.float32)
+    ci = np.zeros((8, nA, 4), np.int32)
+    rc = lib.nm_match_tc_probe(C.c_void_p(A.data_ptr()), nA, C.c_void_p(B.data_ptr()), nB, C.c_void_p(rec.data_ptr()),
+                               C.byref(fb), cs.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p), C.byref(nl),
+                               C.byref(sc), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, rc
+    n = nl.value
+    cs = cs.reshape(-1)[: n * nA * 4].reshape(n, nA, 4)
+    ci = ci.reshape(-1)[: n * nA * 4].reshape(n, nA, 4)
+    a16 = (Ah * sc.value).astype(np.float16).astype(np.float64)
+    b16 = (Bh * sc.value).astype(np.float16).astype(np.float64)
+    na2, nb2 = (a16 ** 2).sum(1), (b16 ** 2).sum(1)
+    worst = 0.0
+    for l in range(n):
+        for k in range(4):
+            idx = ci[l, :, k]
+            ok = (idx >= 0) & (idx < nB)
+            rows = np.nonzero(ok)[0]
+            j = idx[ok]
+            s_exact = (a16[rows] * b16[j]).sum(1) - 0.5 * nb2[j]
+            err = np.abs(cs[l, rows, k].astype(np.float64) - s_exact) / (na2[rows] + nb2[j])
+            worst = max(worst, float(err.max()))
+    print(f"accumulation error: lists={n} scale={sc.value} max |dS|/(|a|^2+|b|^2) = {worst:.3e} = 2^{np.log2(worst):.1f}", flush=True)
+    return worst
 
 
 def check(nA, nB, seed=0):
@@ -65,6 +99,7 @@ if __name__ == "__main__":
     for nA, nB in [(256, 128), (256, 512), (300, 1000), (1, 1), (5, 3), (1000, 37), (2048, 2048), (4096, 8192), (20000, 30000)]:
         ok &= check(nA, nB)
     print("ALL EQUAL" if ok else "MISMATCH")
+    accumulation_error()
     if ok and len(sys.argv) > 1:
         n = 100000
         Bh = synth.descriptors(n, 2)
