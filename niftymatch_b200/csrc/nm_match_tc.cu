@@ -50,6 +50,7 @@ constexpr int TC_ROWBLK = 2 * TC_TROWS;             // query rows per CTA
 constexpr int TC_NST = 4;                           // B stages in shared memory
 constexpr int TC_K = 4;                             // candidates kept per (row, split)
 constexpr int TC_MAX_SPLITS = 4;                    // 4 splits x 2 column halves x 4 = 32 candidates = one warp in rerank
+constexpr int TC_SEED_TILES = 16;                   // database tiles of the seed pass (2048 columns)
 constexpr int TC_EPI_WARPS = 16;                    // 2 row halves x 4 lane quadrants x 2 column halves
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0 copy, warp 1 mma, warps 2..17 epilogue
 constexpr float TC_AUG_C = 256.f;
@@ -258,7 +259,9 @@ struct TcScanArgs {
     const uint8_t* b_pack;      // [n_btiles] tiles
     float4*        cand_s;      // [2 * n_splits][nA] 4 best scores, descending (list = split * 2 + column half)
     int4*          cand_i;      // [2 * n_splits][nA] their database rows
-    int            nA, n_btiles, tiles_per_split;
+    const float4*  seed_s;      // [2][nA] lists of the seed pass (tiles [0, tile_first)), or null
+    const int4*    seed_i;
+    int            nA, tile_first, tile_end, tiles_per_split;   // split s scans tiles tile_first + s*tps ...
     uint32_t       lbo, sbo;    // descriptor strides in bytes (k-chunk stride, 8-row-group stride)
 };
 
@@ -319,8 +322,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const TcScanArgs
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rb = blockIdx.x, split = blockIdx.y;
-    const int t0 = split * p.tiles_per_split;
-    const int nt = min(p.tiles_per_split, p.n_btiles - t0);
+    const int t0 = p.tile_first + split * p.tiles_per_split;
+    const int nt = min(p.tiles_per_split, p.tile_end - t0);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_NST; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
@@ -386,6 +389,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const TcScanArgs
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128 + ch * 64);
         float s0 = -FLT_MAX, s1 = -FLT_MAX, s2 = -FLT_MAX, s3 = -FLT_MAX;
         int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+        const int row = rb * TC_ROWBLK + half * TC_TROWS + q * 32 + lane;
+        if (p.seed_s != nullptr && row < p.nA) {
+            // start from the row's 4 best of the seed pass (merge of its two lists): the insertion
+            // rate of a running top-k falls like k/n, so a few thousand seed columns remove most
+            // of the (warp-divergent) insertions of the main scan
+            const float4 a4 = p.seed_s[row], b4 = p.seed_s[p.nA + row];
+            const int4 ai = p.seed_i[row], bi = p.seed_i[p.nA + row];
+            s0 = a4.x; s1 = a4.y; s2 = a4.z; s3 = a4.w;
+            i0 = ai.x; i1 = ai.y; i2 = ai.z; i3 = ai.w;
+            TC_INSERT(b4.x, bi.x); TC_INSERT(b4.y, bi.y); TC_INSERT(b4.z, bi.z); TC_INSERT(b4.w, bi.w);
+        }
         for (int i = 0; i < nt; ++i) {
             const int as = i & 1;
             mbar_wait(acc_full + as, (i >> 1) & 1);
@@ -400,7 +414,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const TcScanArgs
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + as);   // this warp is done with the TMEM stage
         }
-        const int row = rb * TC_ROWBLK + half * TC_TROWS + q * 32 + lane;
         if (row < p.nA) {
             p.cand_s[(size_t)(split * 2 + ch) * p.nA + row] = make_float4(s0, s1, s2, s3);
             p.cand_i[(size_t)(split * 2 + ch) * p.nA + row] = make_int4(i0, i1, i2, i3);
@@ -468,6 +481,17 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict_
         const float4 cs = cand_s[(size_t)sp * nA + a];
         idx = k == 0 ? ci.x : k == 1 ? ci.y : k == 2 ? ci.z : ci.w;
         thr = cs.w;
+    }
+    // the seed candidates start every list of the row: keep one copy (lowest lane)
+    {
+        const bool valid = idx >= 0 && idx < nB;
+        bool dup = false;
+#pragma unroll
+        for (int d = 1; d < 32; ++d) {
+            const int o = __shfl_sync(0xffffffffu, idx, (lane + 32 - d) & 31);      // lane - d (cyclic)
+            dup |= (d <= lane) && (o == idx);
+        }
+        if (!valid || dup) idx = -1;
     }
     float dist = INFINITY;
     int jdx = 0x7fffffff;
@@ -610,8 +634,12 @@ static int tc_run(const float* A, int nA, const float* B, int nB, int index_offs
     const int n_rowblocks = nm_div_up(nA, TC_ROWBLK);
     const int n_atiles = n_rowblocks * 2;
     const int n_btiles = nm_div_up(nB, TC_TROWS);
-    const int n_splits = tc_pick_splits(n_rowblocks, n_btiles, n_sms);
-    const int tiles_per_split = nm_div_up(n_btiles, n_splits);
+    // seed pass: the first TC_SEED_TILES tiles are scanned first, for all rows; their 4 best per row
+    // start every list of the main scan (which then skips those tiles)
+    const int seed_tiles = n_btiles >= 4 * TC_SEED_TILES ? TC_SEED_TILES : 0;
+    const int main_tiles = n_btiles - seed_tiles;
+    const int n_splits = tc_pick_splits(n_rowblocks, main_tiles, n_sms);
+    const int tiles_per_split = nm_div_up(main_tiles, n_splits);
 
     // one stream-ordered workspace: header | fallback count | fallback list | candidates | packed A | packed B
     const size_t off_cnt = 16;
@@ -619,7 +647,9 @@ static int tc_run(const float* A, int nA, const float* B, int nB, int index_offs
     const size_t off_cs = (off_list + sizeof(int) * (size_t)nA + 255) & ~size_t(255);
     const int n_lists = 2 * n_splits;
     const size_t off_ci = off_cs + sizeof(float4) * (size_t)n_lists * nA;
-    const size_t off_ap = (off_ci + sizeof(int4) * (size_t)n_lists * nA + 255) & ~size_t(255);
+    const size_t off_ss = off_ci + sizeof(int4) * (size_t)n_lists * nA;
+    const size_t off_si = off_ss + sizeof(float4) * 2 * (size_t)nA;
+    const size_t off_ap = (off_si + sizeof(int4) * 2 * (size_t)nA + 255) & ~size_t(255);
     const size_t off_bp = off_ap + (size_t)n_atiles * TC_TILE_BYTES;
     const size_t total = off_bp + (size_t)n_btiles * TC_TILE_BYTES;
     uint8_t* ws = nullptr;
@@ -629,6 +659,8 @@ static int tc_run(const float* A, int nA, const float* B, int nB, int index_offs
     int* fb_list = reinterpret_cast<int*>(ws + off_list);
     float4* cand_s = reinterpret_cast<float4*>(ws + off_cs);
     int4* cand_i = reinterpret_cast<int4*>(ws + off_ci);
+    float4* seed_s = reinterpret_cast<float4*>(ws + off_ss);
+    int4* seed_i = reinterpret_cast<int4*>(ws + off_si);
     uint8_t* a_pack = ws + off_ap;
     uint8_t* b_pack = ws + off_bp;
 
@@ -641,7 +673,12 @@ static int tc_run(const float* A, int nA, const float* B, int nB, int index_offs
         tc_absmax_kernel<<<gb, 256, 0, stream>>>(B, eb, hdr);
         tc_pack_kernel<false><<<n_atiles, 256, 0, stream>>>(A, nA, hdr, a_pack);
         tc_pack_kernel<true><<<n_btiles, 256, 0, stream>>>(B, nB, hdr, b_pack);
-        TcScanArgs sa{a_pack, b_pack, cand_s, cand_i, nA, n_btiles, tiles_per_split, g_lbo, g_sbo};
+        if (seed_tiles > 0) {
+            TcScanArgs ss{a_pack, b_pack, seed_s, seed_i, nullptr, nullptr, nA, 0, seed_tiles, seed_tiles, g_lbo, g_sbo};
+            tc_scan_kernel<<<dim3(n_rowblocks, 1), TC_THREADS, TC_SMEM_BYTES, stream>>>(ss);
+        }
+        TcScanArgs sa{a_pack, b_pack, cand_s, cand_i, seed_tiles > 0 ? seed_s : nullptr, seed_tiles > 0 ? seed_i : nullptr,
+                      nA, seed_tiles, n_btiles, tiles_per_split, g_lbo, g_sbo};
         tc_scan_kernel<<<dim3(n_rowblocks, n_splits), TC_THREADS, TC_SMEM_BYTES, stream>>>(sa);
         tc_rerank_kernel<<<nm_div_up(nA, 8), 256, 0, stream>>>(A, nA, B, nB, n_lists, cand_s, cand_i, hdr, index_offset, rec4,
                                                                fb_list, fb_count);
