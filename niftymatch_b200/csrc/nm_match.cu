@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(256) scan_exact_kernel(const float* __restrict
                                                          float4* __restrict__ part, float* __restrict__ D,
                                                          long long d_sa, long long d_sb,
                                                          const int* __restrict__ row_list,
-                                                         const int* __restrict__ row_count)
+                                                         const int* __restrict__ row_count,
+                                                         unsigned long long* __restrict__ key1,
+                                                         unsigned* __restrict__ key2)
 {
     __shared__ __align__(16) float As[MK][MP];
     __shared__ __align__(16) float Bs[MK][MP];
@@ -141,27 +143,36 @@ __global__ void __launch_bounds__(256) scan_exact_kernel(const float* __restrict
         }
         if (a < n_rows) {
             if (mi != 0x7fffffff) mi += index_offset; else mi = -1;
-            part[(long long)split * nA + a] = make_float4(m1, __int_as_float(mi), m2, 0.f);
+            if (!ROWS) {
+                part[(long long)split * nA + a] = make_float4(m1, __int_as_float(mi), m2, 0.f);
+            } else if (mi >= 0) {
+                // lock-free merge over the splits (distances are >= 0, so their bit patterns order like
+                // the values): key1 = (d1, index) minimum = best column, lowest index on ties; key2 = the
+                // minimum over every other value seen (each split's d2 and every displaced d1)
+                const unsigned long long mine = ((unsigned long long)__float_as_uint(m1) << 32) | (unsigned)mi;
+                const unsigned long long old = atomicMin(key1 + a, mine);
+                const unsigned long long loser = old > mine ? old : mine;
+                atomicMin(key2 + a, min((unsigned)(loser >> 32), __float_as_uint(m2)));
+            }
         }
     }
     __syncthreads();                                              // s_rec reused by the next row tile
   }
 }
 
-// Merge of the per-split records of a row list: out_rec[row_list[k]] for k < *row_count.
-__global__ void merge_rows_kernel(const float4* __restrict__ part, int n_splits, int nA, const int* __restrict__ row_list,
-                                  const int* __restrict__ row_count, float4* __restrict__ out_rec)
+// Records of a row list from the merged keys: out_rec[row_list[k]] for k < *row_count.
+__global__ void finish_rows_kernel(const unsigned long long* __restrict__ key1, const unsigned* __restrict__ key2, int nA,
+                                   const int* __restrict__ row_list, const int* __restrict__ row_count,
+                                   float4* __restrict__ out_rec)
 {
     const int n_rows = min(*row_count, nA);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_rows; k += gridDim.x * blockDim.x) {
-        float m1 = INFINITY, m2 = INFINITY; int mi = 0x7fffffff;
-        for (int s = 0; s < n_splits; ++s) {
-            const float4 q = part[(long long)s * nA + k];
-            int qi = __float_as_int(q.y);
-            if (qi < 0) qi = 0x7fffffff;
-            rec_merge(m1, mi, m2, q.x, qi, q.z);
-        }
-        out_rec[row_list[k]] = make_float4(m1, __int_as_float(mi == 0x7fffffff ? -1 : mi), m2, 0.f);
+        const unsigned long long k1 = key1[k];
+        const unsigned k2 = key2[k];
+        const bool any = k1 != ~0ull;
+        out_rec[row_list[k]] = make_float4(any ? __uint_as_float((unsigned)(k1 >> 32)) : INFINITY,
+                                           __int_as_float(any ? (int)(unsigned)k1 : -1),
+                                           k2 != ~0u ? __uint_as_float(k2) : INFINITY, 0.f);
     }
 }
 
@@ -241,9 +252,9 @@ int nm_match_scan_exact(const float* A, long long a_sa, long long a_sk, int nA, 
     if (splits > 1) NM_CUDA_TRY(cudaMallocAsync(&part, sizeof(float4) * (size_t)splits * nA, stream));
     dim3 grid(a_tiles, splits);
     if (D)
-        scan_exact_kernel<true, false><<<grid, 256, 0, stream>>>(A, a_sa, a_sk, nA, B, nB, dim, index_offset, per, part, D, d_sa, d_sb, nullptr, nullptr);
+        scan_exact_kernel<true, false><<<grid, 256, 0, stream>>>(A, a_sa, a_sk, nA, B, nB, dim, index_offset, per, part, D, d_sa, d_sb, nullptr, nullptr, nullptr, nullptr);
     else
-        scan_exact_kernel<false, false><<<grid, 256, 0, stream>>>(A, a_sa, a_sk, nA, B, nB, dim, index_offset, per, part, nullptr, 0, 0, nullptr, nullptr);
+        scan_exact_kernel<false, false><<<grid, 256, 0, stream>>>(A, a_sa, a_sk, nA, B, nB, dim, index_offset, per, part, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr);
     cudaError_t e = cudaGetLastError();
     if (splits > 1) {
         if (e == cudaSuccess) {
@@ -256,27 +267,33 @@ int nm_match_scan_exact(const float* A, long long a_sa, long long a_sk, int nA, 
 }
 
 // Exact records for the rows row_list[0 .. *row_count) only (count lives on the device, no host
-// synchronisation): the database is cut into ~1024-row splits so that even a handful of rows
-// spreads over the machine; a fixed-size grid strides over the listed row tiles.
+// synchronisation).  The database is cut into 256-column splits so that even a handful of rows
+// spreads over the whole machine; a fixed-size grid strides over the listed row tiles and the
+// splits merge lock-free into two key arrays (no per-split scratch).
 int nm_match_scan_exact_rows(const float* A, int nA, const float* B, int nB, int dim, int index_offset,
                              const int* row_list, const int* row_count, float4* rec4, cudaStream_t stream)
 {
     if (nA <= 0 || nB <= 0 || dim <= 0 || !row_list || !row_count) return NM_ERR_INVALID;
     const int b_tiles = nm_div_up(nB, MT);
-    int splits = min(b_tiles, max(1, nm_div_up(nB, 1024)));
-    const int per = nm_div_up(b_tiles, splits);
-    splits = nm_div_up(b_tiles, per);
-    const int row_blocks = min(nm_div_up(nA, MT), 64);
-    float4* part = nullptr;
-    NM_CUDA_TRY(cudaMallocAsync(&part, sizeof(float4) * (size_t)splits * nA, stream));
-    scan_exact_kernel<false, true><<<dim3(row_blocks, splits), 256, 0, stream>>>(
-        A, dim, 1, nA, B, nB, dim, index_offset, per, part, nullptr, 0, 0, row_list, row_count);
-    cudaError_t e = cudaGetLastError();
+    const int per = 4;                                            // 4 x 64 database rows per block
+    const int splits = nm_div_up(b_tiles, per);
+    if (splits > 65535) return NM_ERR_OVERFLOW;
+    const int row_blocks = min(nm_div_up(nA, MT), 32);
+    unsigned char* keys = nullptr;
+    NM_CUDA_TRY(cudaMallocAsync(&keys, 12 * (size_t)nA, stream));
+    unsigned long long* key1 = reinterpret_cast<unsigned long long*>(keys);
+    unsigned* key2 = reinterpret_cast<unsigned*>(keys + 8 * (size_t)nA);
+    cudaError_t e = cudaMemsetAsync(keys, 0xff, 12 * (size_t)nA, stream);
     if (e == cudaSuccess) {
-        merge_rows_kernel<<<min(nm_div_up(nA, 256), 64), 256, 0, stream>>>(part, splits, nA, row_list, row_count, rec4);
+        scan_exact_kernel<false, true><<<dim3(row_blocks, splits), 256, 0, stream>>>(
+            A, dim, 1, nA, B, nB, dim, index_offset, per, nullptr, nullptr, 0, 0, row_list, row_count, key1, key2);
         e = cudaGetLastError();
     }
-    cudaFreeAsync(part, stream);
+    if (e == cudaSuccess) {
+        finish_rows_kernel<<<min(nm_div_up(nA, 256), 64), 256, 0, stream>>>(key1, key2, nA, row_list, row_count, rec4);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(keys, stream);
     return nm_cuda_err(e);
 }
 

@@ -50,6 +50,7 @@ constexpr int TC_ROWBLK = 2 * TC_TROWS;             // query rows per CTA
 constexpr int TC_NST = 4;                           // B stages in shared memory
 constexpr int TC_K = 4;                             // candidates kept per (row, split)
 constexpr int TC_MAX_SPLITS = 4;                    // 4 splits x 2 column halves x 4 = 32 candidates = one warp in rerank
+constexpr int TC_RERANK = 16;                       // candidates per row evaluated exactly
 constexpr int TC_SEED_TILES = 16;                   // database tiles of the seed pass (2048 columns)
 constexpr int TC_EPI_WARPS = 16;                    // 2 row halves x 4 lane quadrants x 2 column halves
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0 copy, warp 1 mma, warps 2..17 epilogue
@@ -482,16 +483,36 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict_
         idx = k == 0 ? ci.x : k == 1 ? ci.y : k == 2 ? ci.z : ci.w;
         thr = cs.w;
     }
-    // the seed candidates start every list of the row: keep one copy (lowest lane)
+    // The seed candidates start every list of the row: keep one copy (lowest lane).  Then only the
+    // TC_RERANK best candidates by tensor-core score are evaluated exactly (the gather of 512-byte
+    // database rows is what this kernel costs); the others become non-candidates, bounded by the
+    // best score among them.
+    float sc_own = -FLT_MAX;
+    if (sp < n_lists) {
+        const float4 cs = cand_s[(size_t)sp * nA + a];
+        sc_own = k == 0 ? cs.x : k == 1 ? cs.y : k == 2 ? cs.z : cs.w;
+    }
     {
         const bool valid = idx >= 0 && idx < nB;
         bool dup = false;
+        int rank = 0;
 #pragma unroll
         for (int d = 1; d < 32; ++d) {
-            const int o = __shfl_sync(0xffffffffu, idx, (lane + 32 - d) & 31);      // lane - d (cyclic)
+            const int src = (lane + 32 - d) & 31;                                   // lane - d (cyclic)
+            const int o = __shfl_sync(0xffffffffu, idx, src);
             dup |= (d <= lane) && (o == idx);
         }
-        if (!valid || dup) idx = -1;
+        if (!valid || dup) { idx = -1; sc_own = -FLT_MAX; }
+#pragma unroll
+        for (int d = 1; d < 32; ++d) {
+            const int src = (lane + 32 - d) & 31;
+            const float os = __shfl_sync(0xffffffffu, sc_own, src);
+            rank += (os > sc_own || (os == sc_own && src < lane)) ? 1 : 0;
+        }
+        // best score among the pruned candidates (rank == TC_RERANK), if any
+        const float cut = (rank == TC_RERANK && idx >= 0) ? sc_own : -FLT_MAX;
+        if (rank >= TC_RERANK) idx = -1;
+        thr = fmaxf(thr, cut);
     }
     float dist = INFINITY;
     int jdx = 0x7fffffff;
