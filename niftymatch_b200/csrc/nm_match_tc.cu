@@ -317,9 +317,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const TcScanArgs
     uint64_t* full = bars;                      // [TC_NST]  B stage filled (tx bytes)
     uint64_t* empty = bars + TC_NST;            // [TC_NST]  B stage consumed (tcgen05.commit)
     uint64_t* a_full = bars + 2 * TC_NST;       // A tiles resident
-    uint64_t* acc_full = a_full + 1;            // [2] accumulator stage written (tcgen05.commit)
-    uint64_t* acc_empty = acc_full + 2;         // [2] accumulator stage drained (8 epilogue warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    // Accumulator hand-off is per (stage, 128-row half): the epilogue of a half starts as soon as its
+    // 9 MMAs are done and has until that half is issued again two tiles later (1.5 tile times instead of
+    // 1) -- the slowest of the 8 warps of a half sets the pace, and the insertion path makes that slow.
+    uint64_t* acc_full = a_full + 1;            // [2][2] accumulator (stage, half) written (tcgen05.commit)
+    uint64_t* acc_empty = acc_full + 4;         // [2][2] accumulator (stage, half) drained (8 epilogue warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rb = blockIdx.x, split = blockIdx.y;
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const TcScanArgs
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_NST; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         mbar_init(a_full, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, TC_EPI_WARPS); }
+        for (int i = 0; i < 4; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, TC_EPI_WARPS / 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -363,21 +366,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const TcScanArgs
             mbar_wait(a_full, 0);
             for (int i = 0; i < nt; ++i) {
                 const int st = i % TC_NST, as = i & 1;
-                if (i >= 2) mbar_wait(acc_empty + as, ((i >> 1) - 1) & 1);
                 mbar_wait(full + st, (i / TC_NST) & 1);
-                tc_fence_after();
                 const uint64_t bdesc = bdesc0 + (uint64_t)((st * TC_TILE_BYTES) >> 4);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
+                    if (i >= 2) mbar_wait(acc_empty + as * 2 + h, ((i >> 1) - 1) & 1);
+                    tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)((as * 2 + h) * 128);
 #pragma unroll
                     for (int kk = 0; kk < TC_KAUG / 16; ++kk) {
                         const uint64_t koff = (uint64_t)((kk * 2 * TC_KSTRIDE) >> 4);
                         tc_mma_f16(d, adesc0 + (uint64_t)((h * TC_TILE_BYTES) >> 4) + koff, bdesc + koff, idesc, kk > 0 ? 1u : 0u);
                     }
+                    tc_commit(acc_full + as * 2 + h);   // accumulators of this half complete
                 }
                 tc_commit(empty + st);          // B stage reusable once these MMAs have read it
-                tc_commit(acc_full + as);       // accumulators of this tile complete
             }
         }
         __syncwarp();
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const TcScanArgs
         }
         for (int i = 0; i < nt; ++i) {
             const int as = i & 1;
-            mbar_wait(acc_full + as, (i >> 1) & 1);
+            mbar_wait(acc_full + as * 2 + half, (i >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = lane_addr + (uint32_t)(as * 256);
             const int gcol = (t0 + i) * TC_TROWS + ch * 64;
@@ -413,7 +416,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const TcScanArgs
             TC_CHUNK(va, taddr, gcol);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + as);   // this warp is done with the TMEM stage
+            if (lane == 0) mbar_arrive(acc_empty + as * 2 + half);   // this warp is done with the TMEM half-stage
         }
         if (row < p.nA) {
             p.cand_s[(size_t)(split * 2 + ch) * p.nA + row] = make_float4(s0, s1, s2, s3);
