@@ -101,6 +101,9 @@ __global__ void __launch_bounds__(256) scan_exact_kernel(const float* __restrict
             }
             __syncthreads();
             const int kmax = min(MK, dim - k0);
+            // row-list mode: the last listed tile is usually almost empty (a handful of uncertified
+            // rows); threads whose 4 rows are all padding skip the arithmetic
+            if (!ROWS || a0 + ty * 4 < n_rows)
             for (int k = 0; k < kmax; ++k) {
                 const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
                 const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);

@@ -497,18 +497,13 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict_
     }
     {
         const bool valid = idx >= 0 && idx < nB;
-        bool dup = false;
+        // lanes holding the same database row: keep the lowest one
+        const unsigned same = __match_any_sync(0xffffffffu, idx);
+        if (!valid || (__ffs(same) - 1) != lane) { idx = -1; sc_own = -FLT_MAX; }
         int rank = 0;
 #pragma unroll
         for (int d = 1; d < 32; ++d) {
             const int src = (lane + 32 - d) & 31;                                   // lane - d (cyclic)
-            const int o = __shfl_sync(0xffffffffu, idx, src);
-            dup |= (d <= lane) && (o == idx);
-        }
-        if (!valid || dup) { idx = -1; sc_own = -FLT_MAX; }
-#pragma unroll
-        for (int d = 1; d < 32; ++d) {
-            const int src = (lane + 32 - d) & 31;
             const float os = __shfl_sync(0xffffffffu, sc_own, src);
             rank += (os > sc_own || (os == sc_own && src < lane)) ? 1 : 0;
         }
