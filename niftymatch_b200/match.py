@@ -51,3 +51,26 @@ def merge_top2(recs, ambiguity: float = 0.8, match_io=None):
     check(_lib.load().nm_match_merge_top2(C.c_void_p(recs.data_ptr()), n_shards, nA, ambiguity,
                                           C.c_void_p(match_io.data_ptr()), _stream_ptr()), "nm_match_merge_top2")
     return match_io
+
+
+def tc_probe(A, B, want_candidates: bool = False):
+    """Diagnostics of the tensor-core engine (nm_match_tc_probe): exact records (nA,4), the number
+    of rows whose exactness certificate failed (re-scanned by the exact engine), and optionally
+    the candidate lists of the tcgen05 scan with the power-of-two scale that was applied."""
+    import numpy as np
+    import torch
+    nA, nB = A.shape[0], B.shape[0]
+    rec = torch.empty((nA, 4), dtype=torch.float32, device=A.device)
+    fb, nl, sc = C.c_int(-1), C.c_int(0), C.c_float(0)
+    cs = np.zeros((8, nA, 4), np.float32) if want_candidates else None
+    ci = np.zeros((8, nA, 4), np.int32) if want_candidates else None
+    check(_lib.load().nm_match_tc_probe(C.c_void_p(A.data_ptr()), nA, C.c_void_p(B.data_ptr()), nB, C.c_void_p(rec.data_ptr()),
+                                        C.byref(fb), cs.ctypes.data_as(C.c_void_p) if want_candidates else None,
+                                        ci.ctypes.data_as(C.c_void_p) if want_candidates else None, C.byref(nl), C.byref(sc),
+                                        _stream_ptr()), "nm_match_tc_probe")
+    out = {"rec": rec, "fallback_rows": fb.value, "n_lists": nl.value, "scale": sc.value}
+    if want_candidates:
+        n = nl.value
+        out["cand_scores"] = cs.reshape(-1)[: n * nA * 4].reshape(n, nA, 4)
+        out["cand_index"] = ci.reshape(-1)[: n * nA * 4].reshape(n, nA, 4)
+    return out

@@ -121,3 +121,95 @@ def test_large_match_properties(nm, oracle):
     mo = oracle.match(np.ascontiguousarray(A[sub]), B, 0.8)
     assert np.array_equal(m[sub], mo)
     assert (m >= 0).sum() > 0.15 * n
+
+
+# ---- tensor-core engine (tcgen05 candidate search + exact re-rank + certificate) ---------
+def _need_tc(nm):
+    try:
+        nm.set_engine(1)
+    except nm.NmError:
+        pytest.skip("tensor-core engine unavailable on this device")
+    nm.set_engine(-1)
+
+
+@pytest.mark.parametrize("nA,nB", [(1, 1), (7, 130), (256, 128), (300, 1000), (1000, 37), (4096, 8192), (9000, 20000)])
+def test_tc_records_bitwise_equal_exact_engine(nm, nA, nB):
+    """The tcgen05 engine must return the SAME records (d1, i1, d2 bit patterns) as the exact fp32
+    scan: candidates come from fp16 tensor-core scores, the values from the reference's fp32
+    arithmetic, and rows whose certificate fails are re-scanned exactly."""
+    _need_tc(nm)
+    B = synth.descriptors(nB, 300 + nB)
+    A = synth.descriptors(nA, 400 + nA, planted_from=B)
+    At, Bt = _cu(A), _cu(B)
+    nm.set_engine(0)
+    ref = nm.match_top2(At, Bt)
+    nm.set_engine(-1)
+    pr = nm.tc_probe(At, Bt)
+    assert torch.equal(pr["rec"].view(torch.int32), ref.view(torch.int32))
+    assert 0 <= pr["fallback_rows"] <= max(4, nA // 50), pr["fallback_rows"]
+
+
+def test_tc_engine_hard_cases(nm, oracle):
+    """Inputs built to stress the certificate: exact duplicates in the database (ties -> lowest
+    index), all-equal rows, a huge dynamic range, zero vectors.  Indices must equal the oracle's."""
+    _need_tc(nm)
+    rng = np.random.RandomState(5)
+    nB, nA = 3000, 700
+    B = synth.descriptors(nB, 77)
+    B[100:200] = B[0:100]                      # duplicates: ties must resolve to the lower index
+    B[500] = 0.0
+    B[501:520] = B[501]                        # 19 identical rows
+    B[600:700] *= 1e-4                         # tiny rows (fp16 subnormal range after scaling)
+    B[700:710] *= 50.0                         # large rows set the global scale
+    A = synth.descriptors(nA, 78, planted_from=B)
+    A[0:50] = B[100:150]                       # exact copies of duplicated rows: d1 = d2 = 0
+    A[50] = 0.0
+    A[51:60] = B[501] + rng.randn(9, 128).astype(np.float32) * 0.01
+    A[60:70] = B[600:610]
+    mo = oracle.match(A, B, 0.8)
+    nm.set_engine(1)
+    m = nm.match(_cu(A), _cu(B), 0.8).cpu().numpy()
+    nm.set_engine(0)
+    m0 = nm.match(_cu(A), _cu(B), 0.8).cpu().numpy()
+    nm.set_engine(-1)
+    assert np.array_equal(m0, mo)
+    assert np.array_equal(m, mo)
+
+
+def test_tc_accumulation_error_within_certificate_margin(nm):
+    """The certificate assumes |S_tensor - S_exact| <= 2^-18 (|a^|^2 + |b^|^2) for the fp32
+    accumulation of the fp16 products (eta / 2, nm_match_tc.cu).  Measure it on the candidates."""
+    _need_tc(nm)
+    nA, nB = 3000, 7000
+    Bh = synth.descriptors(nB, 12)
+    Ah = synth.descriptors(nA, 11, planted_from=Bh)
+    pr = nm.tc_probe(_cu(Ah), _cu(Bh), want_candidates=True)
+    sc = pr["scale"]
+    a16 = (Ah * sc).astype(np.float16).astype(np.float64)
+    b16 = (Bh * sc).astype(np.float16).astype(np.float64)
+    na2, nb2 = (a16 ** 2).sum(1), (b16 ** 2).sum(1)
+    worst = 0.0
+    for l in range(pr["n_lists"]):
+        for k in range(4):
+            idx = pr["cand_index"][l, :, k]
+            ok = (idx >= 0) & (idx < nB)
+            rows, j = np.nonzero(ok)[0], idx[ok]
+            s_exact = (a16[rows] * b16[j]).sum(1) - 0.5 * nb2[j]
+            err = np.abs(pr["cand_scores"][l, rows, k].astype(np.float64) - s_exact) / (na2[rows] + nb2[j])
+            worst = max(worst, float(err.max()))
+    assert worst < 2.0 ** -20, worst          # 4x below what the certificate budgets
+
+
+def test_tc_matches_exact_at_scale(nm):
+    """40k x 60k: match indices of the two engines must be identical."""
+    _need_tc(nm)
+    B = synth.descriptors(60000, 2)
+    A = synth.descriptors(40000, 1, planted_from=B)
+    At, Bt = _cu(A), _cu(B)
+    nm.set_engine(1)
+    m1 = nm.match(At, Bt, 0.8)
+    nm.set_engine(0)
+    m0 = nm.match(At, Bt, 0.8)
+    nm.set_engine(-1)
+    assert torch.equal(m0, m1)
+    assert int((m1 >= 0).sum()) > 5000
