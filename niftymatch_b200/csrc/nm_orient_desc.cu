@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
                                                                  float* __restrict__ desc, float* __restrict__ xo,
                                                                  float* __restrict__ yo, int num_dogs)
 {
-    extern __shared__ __align__(16) float s_h[];      // [DE_WARPS][128][32], swizzled
+    extern __shared__ __align__(16) float s_h[];      // [DE_WARPS][128 bins][32 lane-private copies]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int f = blockIdx.y;
     const int j = blockIdx.x * DE_WARPS + wid;
@@ -202,11 +202,28 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
     const float2* __restrict__ G = oc.grad + ((long long)f * 3 + g.level) * oc.level_elems +
                                    (long long)g.yi * oc.pitch + g.xi;
     const int total = chunks * 256;
-    for (int s = lane; s < total; s += 32) {
+    // The gradient samples come from HBM (the maps of a 64-frame batch are 4.5 GB, L2 hit rate 23 %)
+    // and only ~11 warps fit an SM next to the private histograms, so the load of iteration i+1 is
+    // issued before the arithmetic of iteration i (ncu: 53 % of the stall samples sat on the first
+    // use of the loaded value).
+    auto sample_pos = [&](int s, int& cx, int& cy) -> bool {
         const int c = s >> 8, ty = (s >> 4) & 15, tx = s & 15;
-        const int cx = xmin + tx + 16 * c, cy = ymin + ty + 16 * c;   // diagonal chunks only (:142-143)
-        if (cx > xmax || cy > ymax) continue;                         // :96
-        const float2 gv = __ldg(G + (long long)cy * oc.pitch + cx);
+        cx = xmin + tx + 16 * c; cy = ymin + ty + 16 * c;         // diagonal chunks only (:142-143)
+        return s < total && cx <= xmax && cy <= ymax;             // :96
+    };
+    int ncx, ncy, mcx, mcy;
+    bool nvalid = sample_pos(lane, ncx, ncy), mvalid = sample_pos(lane + 32, mcx, mcy);
+    float2 ngv = make_float2(0.f, 0.f), mgv = make_float2(0.f, 0.f);
+    if (nvalid) ngv = __ldg(G + (long long)ncy * oc.pitch + ncx);
+    if (mvalid) mgv = __ldg(G + (long long)mcy * oc.pitch + mcx);
+    for (int s = lane; s < total; s += 32) {
+        const int cx = ncx, cy = ncy;
+        const bool valid = nvalid;
+        const float2 gv = ngv;
+        ncx = mcx; ncy = mcy; nvalid = mvalid; ngv = mgv;          // two loads stay in flight
+        mvalid = sample_pos(s + 64, mcx, mcy);
+        if (mvalid) mgv = __ldg(G + (long long)mcy * oc.pitch + mcx);
+        if (!valid) continue;
         const float mod = gv.x;
         const float theta = nm_mod_2pi_f(__fsub_rn(gv.y, th0));       // :100
         const float dx = __fsub_rn((float)(g.xi + cx), g.x);          // :102-103
@@ -247,7 +264,7 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
                     for (int dbt = 0; dbt < 2; ++dbt) {
                         const float wt = __fmul_rn(wxy, fabsf(__fsub_rn(1.f - dbt, rbint)));
                         const int loc = (by + 2) * 32 + (bx + 2) * 8 + ((bint + dbt) & 7);   // :133
-                        float* p = hist + loc * 32 + ((lane + loc) & 31);
+                        float* p = hist + loc * 32 + lane;            // bank == lane: conflict free
                         *p = __fadd_rn(*p, wt);                       // :135
                     }
                 }
@@ -260,7 +277,7 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
         const int b = lane + 32 * q;
         float acc = 0.f;
 #pragma unroll 8
-        for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, hist[b * 32 + ((k + b) & 31)]);
+        for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, hist[b * 32 + ((k + lane) & 31)]);   // rotated: conflict free
         dout[b] = acc;
     }
     if (lane == 0) { xo[kidx] = kp.x; yo[kidx] = kp.y; }              // :76
