@@ -225,12 +225,12 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
         if (mvalid) mgv = __ldg(G + (long long)mcy * oc.pitch + mcx);
         if (!valid) continue;
         const float mod = gv.x;
-        const float theta = nm_mod_2pi_f(__fsub_rn(gv.y, th0));       // :100
         const float dx = __fsub_rn((float)(g.xi + cx), g.x);          // :102-103
         const float dy = __fsub_rn((float)(g.yi + cy), g.y);
         float nx, ny, nt, win, rbinx, rbiny;
         int binx, biny;
         if (EXACT) {
+            const float theta = nm_mod_2pi_f(__fsub_rn(gv.y, th0));                                       // :100
             nx = (float)__ddiv_rn(__fma_rn(ct0, (double)dx, __dmul_rn(st0, (double)dy)), (double)SBP);    // :104
             ny = (float)__ddiv_rn(__fma_rn(ct0, (double)dy, -__dmul_rn(st0, (double)dx)), (double)SBP);   // :105
             nt = (float)__ddiv_rn((double)__fmul_rn(8.0f, theta), NM_TWO_PI_D);                           // :107
@@ -242,10 +242,14 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
         } else {
             nx = __fmul_rn(__fmaf_rn(ct0f, dx, __fmul_rn(st0f, dy)), inv_sbp);
             ny = __fmul_rn(__fmaf_rn(ct0f, dy, -__fmul_rn(st0f, dx)), inv_sbp);
-            nt = __fmul_rn(theta, 1.2732395447351628f);               // 8 / (2 pi)
-            win = expf(__fmul_rn(__fmaf_rn(nx, nx, __fmul_rn(ny, ny)), 0.125f));
             const float fx = floorf(__fsub_rn(nx, 0.5f)), fy = floorf(__fsub_rn(ny, 0.5f));
             binx = (int)fx; biny = (int)fy;
+            // about a third of the window (corners outside the rotated 4x4 cell grid) lands in no
+            // bin (:122-125 rejects all four cells): skip before the exponential and the angle
+            if (binx < -3 || binx > 1 || biny < -3 || biny > 1) continue;
+            const float theta = nm_mod_2pi_f(__fsub_rn(gv.y, th0));   // :100
+            nt = __fmul_rn(theta, 1.2732395447351628f);               // 8 / (2 pi)
+            win = expf(__fmul_rn(__fmaf_rn(nx, nx, __fmul_rn(ny, ny)), 0.125f));
             rbinx = __fsub_rn(nx, __fadd_rn(fx, 0.5f));
             rbiny = __fsub_rn(ny, __fadd_rn(fy, 0.5f));
         }
