@@ -12,12 +12,20 @@
 #include <new>
 #include <vector>
 
+#define NM_MAX_CHUNKS 64
+#define NM_HOST_CHUNK 8       // frames per pipeline stage of nm_sift_run_host
+
 struct nm_sift_ctx {
     nm_sift_params P;
     int B, capacity, n_oct;
     NmOctaveTable tab;
-    NmBlurTma tma[NM_MAX_OCTAVES][5];   // source level i of octave o, box for radius radii[i+1]
-    int tma_batch;           // batch the cached maps were encoded for
+    struct TmaSet {          // TMA descriptors of the internal levels for frames [first, first + n)
+        int first, n;
+        NmBlurTma lvl[NM_MAX_OCTAVES][5];   // source level i of octave o, box for radius radii[i+1]
+    };
+    std::vector<TmaSet*> tma_sets;
+    cudaStream_t s_in, s_out;            // nm_sift_run_host: H2D / D2H copy streams
+    cudaEvent_t ev_in[NM_MAX_CHUNKS], ev_done[NM_MAX_CHUNKS], ev_out;
     float* taps[6];          // 0: base kernel, 1..5: level kernels (device)
     int    radii[6];
     int *seg_raw, *seg_cnt, *seg_off, *counts, *meta;
@@ -121,6 +129,14 @@ extern "C" int nm_sift_destroy(nm_sift_ctx* c)
     if (!c) return NM_OK;
     for (void* p : c->allocs) cudaFree(p);
     for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (auto* t : c->tma_sets) delete t;
+    for (int i = 0; i < NM_MAX_CHUNKS; ++i) {
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    }
+    if (c->ev_out) cudaEventDestroy(c->ev_out);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     delete c;
     return NM_OK;
 }
@@ -139,8 +155,10 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
     nm_sift_ctx* c = new (std::nothrow) nm_sift_ctx();
     if (!c) return NM_ERR_ALLOC;
     c->P = P; c->B = max_batch; c->capacity = capacity; c->n_oct = P.num_octaves;
-    c->scratch = nullptr; c->exact_desc = 0; c->last_launches = 0; c->timing = 0; c->tma_batch = 0;
+    c->scratch = nullptr; c->exact_desc = 0; c->last_launches = 0; c->timing = 0;
     for (int i = 0; i < 6; ++i) c->ev[i] = nullptr;
+    c->s_in = c->s_out = nullptr; c->ev_out = nullptr;
+    for (int i = 0; i < NM_MAX_CHUNKS; ++i) c->ev_in[i] = c->ev_done[i] = nullptr;
     int rc = NM_OK;
     // Gaussian kernels
     for (int i = 0; i < 6 && rc == NM_OK; ++i) {
@@ -186,40 +204,75 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
     }
     for (int i = 0; i < 6 && rc == NM_OK; ++i)
         if (cudaEventCreate(&c->ev[i]) != cudaSuccess) rc = NM_ERR_ALLOC;
+    if (rc == NM_OK && (cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+                        cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) != cudaSuccess ||
+                        cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess))
+        rc = NM_ERR_ALLOC;
+    for (int i = 0; i < NM_MAX_CHUNKS && rc == NM_OK; ++i)
+        if (cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming) != cudaSuccess)
+            rc = NM_ERR_ALLOC;
     if (rc != NM_OK) { nm_sift_destroy(c); return rc; }
     *out = c;
     return NM_OK;
 }
 
-extern "C" int nm_sift_run(nm_sift_ctx* c, const float* frames_dev, int n_frames, nm_stream_t stream)
+// Detect + describe for the frames [first, first + n) of the workspace (frames_dev = the first of
+// those n frames).  All kernels index frames by block, so a range is the same launch sequence on
+// pointers advanced to the range's first frame.
+static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, int n, cudaStream_t st, bool timing)
 {
-    if (!c || !frames_dev || n_frames <= 0 || n_frames > c->B) return NM_ERR_INVALID;
-    cudaStream_t st = (cudaStream_t)stream;
     const nm_sift_params& P = c->P;
     int launches = 0, rc;
     NmDetectParams dp{P.peak_threshold, P.edge_threshold, P.sigma_0, P.num_dog_levels};
-    if (c->tma_batch != n_frames) {
-        // (re-)encode the TMA descriptors of the internal levels for this batch size
-        for (int o = 0; o < c->n_oct; ++o) {
-            const NmOctave& oc = c->tab.o[o];
-            for (int i = 0; i < 5; ++i)
-                nm_blur_make_tma(&c->tma[o][i], oc.levels + i * oc.level_elems, oc.w, oc.h, oc.pitch,
-                                 6 * oc.level_elems, n_frames, c->radii[i + 1]);
-        }
-        c->tma_batch = n_frames;
+    // workspace views of the range
+    NmOctaveTable tab = c->tab;
+    for (int o = 0; o < c->n_oct; ++o) {
+        NmOctave& oc = tab.o[o];
+        const long long nwords = (long long)oc.h * oc.wpr;
+        oc.levels += (long long)first * 6 * oc.level_elems;
+        oc.grad += (long long)first * 3 * oc.level_elems;
+        oc.bitmap += (long long)first * 3 * nwords;
+        oc.wprefix += (long long)first * 3 * nwords;
     }
-    if (c->timing) cudaEventRecord(c->ev[0], st);
+    const long long S = (long long)c->n_oct * 3, cap = c->capacity;
+    int* seg_raw = c->seg_raw + first * S;
+    int* seg_cnt = c->seg_cnt + first * S;
+    int* seg_off = c->seg_off + first * S;
+    int* counts = c->counts + first;
+    int* meta = c->meta + first * cap;
+    float4* kpts = c->kpts + first * cap;
+    float2* orient = c->orient + first * cap;
+    float* desc = c->desc + first * cap * 128;
+    float* x = c->x + first * cap;
+    float* y = c->y + first * cap;
+    // cached TMA descriptors of the internal levels for this range
+    nm_sift_ctx::TmaSet* ts = nullptr;
+    for (auto* t : c->tma_sets) if (t->first == first && t->n == n) { ts = t; break; }
+    if (!ts) {
+        ts = new (std::nothrow) nm_sift_ctx::TmaSet();
+        if (!ts) return NM_ERR_ALLOC;
+        ts->first = first; ts->n = n;
+        for (int o = 0; o < c->n_oct; ++o) {
+            const NmOctave& oc = tab.o[o];
+            for (int i = 0; i < 5; ++i)
+                nm_blur_make_tma(&ts->lvl[o][i], oc.levels + i * oc.level_elems, oc.w, oc.h, oc.pitch,
+                                 6 * oc.level_elems, n, c->radii[i + 1]);
+        }
+        c->tma_sets.push_back(ts);
+    }
+    if (timing) cudaEventRecord(c->ev[0], st);
     // ---- pyramid ---------------------------------------------------------------
     for (int o = 0; o < c->n_oct; ++o) {
-        const NmOctave& oc = c->tab.o[o];
+        const NmOctave& oc = tab.o[o];
         const long long fstride = 6 * oc.level_elems;
         if (o == 0) {
             NmBlurArgs a{};
             a.src = frames_dev; a.src_pitch = P.width; a.src_fstride = (long long)P.width * P.height;
             a.dst = oc.levels; a.dst_pitch = oc.pitch; a.dst_fstride = fstride;
-            a.taps = c->taps[0]; a.radius = c->radii[0]; a.w = oc.w; a.h = oc.h; a.batch = n_frames;
+            a.taps = c->taps[0]; a.radius = c->radii[0]; a.w = oc.w; a.h = oc.h; a.batch = n;
             NmBlurTma base;
-            nm_blur_make_tma(&base, frames_dev, P.width, P.height, P.width, (long long)P.width * P.height, n_frames, c->radii[0]);
+            nm_blur_make_tma(&base, frames_dev, P.width, P.height, P.width, (long long)P.width * P.height, n, c->radii[0]);
             if ((rc = nm_blur_launch(a, st, &base)) != NM_OK) return rc;
             ++launches;
         }
@@ -227,65 +280,99 @@ extern "C" int nm_sift_run(nm_sift_ctx* c, const float* frames_dev, int n_frames
             NmBlurArgs a{};
             a.src = oc.levels + i * oc.level_elems; a.src_pitch = oc.pitch; a.src_fstride = fstride;
             a.dst = oc.levels + (i + 1) * oc.level_elems; a.dst_pitch = oc.pitch; a.dst_fstride = fstride;
-            a.taps = c->taps[i + 1]; a.radius = c->radii[i + 1]; a.w = oc.w; a.h = oc.h; a.batch = n_frames;
+            a.taps = c->taps[i + 1]; a.radius = c->radii[i + 1]; a.w = oc.w; a.h = oc.h; a.batch = n;
             if (i + 1 == P.num_dog_levels && o + 1 < c->n_oct) {
                 // level 3 (sigma doubled) decimated by 2 = next octave's level 0 (downsample.cu:15-16)
-                const NmOctave& nx = c->tab.o[o + 1];
+                const NmOctave& nx = tab.o[o + 1];
                 a.dst2 = nx.levels; a.dst2_pitch = nx.pitch; a.dst2_fstride = 6 * nx.level_elems;
             }
-            if ((rc = nm_blur_launch(a, st, &c->tma[o][i])) != NM_OK) return rc;
+            if ((rc = nm_blur_launch(a, st, &ts->lvl[o][i])) != NM_OK) return rc;
             ++launches;
         }
     }
-    if (c->timing) cudaEventRecord(c->ev[1], st);
+    if (timing) cudaEventRecord(c->ev[1], st);
     // ---- DoG + extrema + refinement + gradients ----------------------------------
     for (int o = 0; o < c->n_oct; ++o) {
-        if ((rc = nm_extrema_launch(c->tab.o[o], o, c->n_oct, dp, n_frames, st)) != NM_OK) return rc;
+        if ((rc = nm_extrema_launch(tab.o[o], o, c->n_oct, dp, n, st)) != NM_OK) return rc;
         ++launches;
     }
-    if (c->timing) cudaEventRecord(c->ev[2], st);
+    if (timing) cudaEventRecord(c->ev[2], st);
     // ---- ordered compaction --------------------------------------------------------
-    if ((rc = nm_rank_launch(c->tab, n_frames, c->seg_raw, st)) != NM_OK) return rc;
-    if ((rc = nm_plan_launch(c->seg_raw, c->seg_cnt, c->seg_off, c->counts, c->n_oct, n_frames, c->capacity, st)) != NM_OK) return rc;
+    if ((rc = nm_rank_launch(tab, n, seg_raw, st)) != NM_OK) return rc;
+    if ((rc = nm_plan_launch(seg_raw, seg_cnt, seg_off, counts, c->n_oct, n, c->capacity, st)) != NM_OK) return rc;
     launches += 2;
     for (int o = 0; o < c->n_oct; ++o) {
-        if ((rc = nm_emit_launch(c->tab.o[o], o, c->n_oct, dp, n_frames, c->seg_cnt, c->seg_off, c->capacity,
-                                 c->kpts, c->meta, st)) != NM_OK) return rc;
+        if ((rc = nm_emit_launch(tab.o[o], o, c->n_oct, dp, n, seg_cnt, seg_off, c->capacity, kpts, meta, st)) != NM_OK) return rc;
         ++launches;
     }
-    if (c->timing) cudaEventRecord(c->ev[3], st);
+    if (timing) cudaEventRecord(c->ev[3], st);
     // ---- orientation, descriptor -----------------------------------------------------
-    if ((rc = nm_orient_launch(c->tab, n_frames, c->capacity, c->counts, c->kpts, c->meta, c->orient, st)) != NM_OK) return rc;
+    if ((rc = nm_orient_launch(tab, n, c->capacity, counts, kpts, meta, orient, st)) != NM_OK) return rc;
     ++launches;
-    if (c->timing) cudaEventRecord(c->ev[4], st);
-    if ((rc = nm_describe_launch(c->tab, n_frames, c->capacity, c->counts, c->kpts, c->meta, c->orient, c->desc,
-                                 c->x, c->y, P.num_dog_levels, c->exact_desc, st)) != NM_OK) return rc;
+    if (timing) cudaEventRecord(c->ev[4], st);
+    if ((rc = nm_describe_launch(tab, n, c->capacity, counts, kpts, meta, orient, desc, x, y, P.num_dog_levels,
+                                 c->exact_desc, st)) != NM_OK) return rc;
     ++launches;
-    if (c->timing) cudaEventRecord(c->ev[5], st);
+    if (timing) cudaEventRecord(c->ev[5], st);
     c->last_launches = launches;
     return NM_OK;
 }
 
+extern "C" int nm_sift_run(nm_sift_ctx* c, const float* frames_dev, int n_frames, nm_stream_t stream)
+{
+    if (!c || !frames_dev || n_frames <= 0 || n_frames > c->B) return NM_ERR_INVALID;
+    return sift_run_range(c, frames_dev, 0, n_frames, (cudaStream_t)stream, c->timing != 0);
+}
+
+// End to end from host memory, software pipelined in chunks of NM_HOST_CHUNK frames: the H2D copy
+// of chunk k+1 (stream s_in), the kernels of chunk k (caller's stream) and the D2H copies of chunk
+// k-1 (stream s_out) overlap; the host only waits for a chunk's 4-byte counts before it sizes that
+// chunk's result copies.  Host buffers should be pinned for the copies to be asynchronous.
 extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_frames, int* counts_host,
                                 float* desc_host, float* x_host, float* y_host, nm_stream_t stream)
 {
     if (!c || !frames_host || !counts_host || n_frames <= 0 || n_frames > c->B) return NM_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t fpix = (size_t)c->P.width * c->P.height;
-    NM_CUDA_TRY(cudaMemcpyAsync(c->frames_stage, frames_host, fpix * n_frames * sizeof(float), cudaMemcpyHostToDevice, st));
-    int rc = nm_sift_run(c, c->frames_stage, n_frames, st);
-    if (rc != NM_OK) return rc;
-    NM_CUDA_TRY(cudaMemcpyAsync(counts_host, c->counts, sizeof(int) * n_frames, cudaMemcpyDeviceToHost, st));
-    NM_CUDA_TRY(cudaStreamSynchronize(st));
-    // copy only the filled part of every frame's slots
-    for (int f = 0; f < n_frames; ++f) {
-        const size_t n = (size_t)counts_host[f], off = (size_t)f * c->capacity;
-        if (n == 0) continue;
-        if (desc_host) NM_CUDA_TRY(cudaMemcpyAsync(desc_host + off * 128, c->desc + off * 128, n * 128 * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (x_host) NM_CUDA_TRY(cudaMemcpyAsync(x_host + off, c->x + off, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (y_host) NM_CUDA_TRY(cudaMemcpyAsync(y_host + off, c->y + off, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    const int n_chunks = nm_div_up(n_frames, NM_HOST_CHUNK);
+    if (n_chunks > NM_MAX_CHUNKS) return NM_ERR_INVALID;
+    int launches = 0;
+    auto drain = [&](int k) -> int {
+        // results of chunk k: wait for its counts, then copy the filled part of every frame
+        NM_CUDA_TRY(cudaEventSynchronize(c->ev_done[k]));
+        const int f0 = k * NM_HOST_CHUNK, f1 = f0 + NM_HOST_CHUNK < n_frames ? f0 + NM_HOST_CHUNK : n_frames;
+        for (int f = f0; f < f1; ++f) {
+            const size_t n = (size_t)counts_host[f], off = (size_t)f * c->capacity;
+            if (n == 0) continue;
+            if (desc_host) NM_CUDA_TRY(cudaMemcpyAsync(desc_host + off * 128, c->desc + off * 128, n * 128 * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
+            if (x_host) NM_CUDA_TRY(cudaMemcpyAsync(x_host + off, c->x + off, n * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
+            if (y_host) NM_CUDA_TRY(cudaMemcpyAsync(y_host + off, c->y + off, n * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
+        }
+        return NM_OK;
+    };
+    for (int k = 0; k < n_chunks; ++k) {        // the uploads do not depend on anything: queue them all
+        const int f0 = k * NM_HOST_CHUNK, n = f0 + NM_HOST_CHUNK < n_frames ? NM_HOST_CHUNK : n_frames - f0;
+        NM_CUDA_TRY(cudaMemcpyAsync(c->frames_stage + f0 * fpix, frames_host + f0 * fpix, fpix * n * sizeof(float),
+                                    cudaMemcpyHostToDevice, c->s_in));
+        NM_CUDA_TRY(cudaEventRecord(c->ev_in[k], c->s_in));
     }
+    for (int k = 0; k < n_chunks; ++k) {
+        const int f0 = k * NM_HOST_CHUNK, n = f0 + NM_HOST_CHUNK < n_frames ? NM_HOST_CHUNK : n_frames - f0;
+        NM_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_in[k], 0));
+        int rc = sift_run_range(c, c->frames_stage + f0 * fpix, f0, n, st, false);
+        if (rc != NM_OK) return rc;
+        launches += c->last_launches;
+        NM_CUDA_TRY(cudaMemcpyAsync(counts_host + f0, c->counts + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+        NM_CUDA_TRY(cudaEventRecord(c->ev_done[k], st));
+        if (k > 0 && (rc = drain(k - 1)) != NM_OK) return rc;
+    }
+    int rc = drain(n_chunks - 1);
+    if (rc != NM_OK) return rc;
+    // the caller's stream is complete when the result copies are
+    NM_CUDA_TRY(cudaEventRecord(c->ev_out, c->s_out));
+    NM_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_out, 0));
     NM_CUDA_TRY(cudaStreamSynchronize(st));
+    c->last_launches = launches;
     return NM_OK;
 }
 
