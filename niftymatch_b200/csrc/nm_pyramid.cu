@@ -80,6 +80,19 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
+// d = a * (t, t) + c on both halves: one FFMA2.
+__device__ __forceinline__ float2 nm_ffma2(float2 a, float t, float2 c)
+{
+    unsigned long long a64, b64, c64, d64;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a64) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(b64) : "f"(t));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c64) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d64) : "l"(a64), "l"(b64), "l"(c64));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(d64));
+    return d;
+}
+
 template <int R, bool TMA>
 __global__ void __launch_bounds__(kThreads, 2) blur_tile_kernel(const NmBlurArgs a, const __grid_constant__ CUtensorMap tmap)
 {
@@ -89,8 +102,10 @@ __global__ void __launch_bounds__(kThreads, 2) blur_tile_kernel(const NmBlurArgs
     constexpr int IW = kTW + RA + R;         // columns staged
     constexpr int IP = in_pitch(R);
     constexpr int NT = 2 * R + 1;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    // the kernel has no static shared memory, so the dynamic window starts at the 128-byte aligned
+    // base the attribute asks for (TMA destination alignment); no pointer arithmetic on the base,
+    // which would turn every LDS/STS below into a generic LD/ST
+    extern __shared__ __align__(128) float smem[];
     float* s_in = smem;
     float* s_row = smem + IH * IP;
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_row + IH * kRowPitch);
@@ -128,62 +143,75 @@ __global__ void __launch_bounds__(kThreads, 2) blur_tile_kernel(const NmBlurArgs
         __syncthreads();
     }
 
-    // ---- row pass: 8 outputs per item, lanes walk rows (pitch == 4 mod 32) -----
+    // Both passes issue their multiply-adds as FFMA2 (fma.rn.f32x2: two independent IEEE fp32 FMAs per
+    // instruction, a Blackwell addition): the kernel is FMA-issue bound (ncu, R = 13: FMA pipe 52 %,
+    // issue slots 64 % busy, DRAM at 27 %), and the paired form halves the FMA instruction count while
+    // every output still accumulates k = -R..R in the reference's order, so the result stays bitwise.
+    // ---- row pass: P outputs (P/2 pairs along x) per item, lanes walk rows (pitch == 4 mod 32) -----
     {
-        constexpr int P = 8;
+        constexpr int P = R > 10 ? 4 : 8;
         constexpr int NV = (SH + P + 2 * R + 3) / 4; // float4 loads per item
         for (int it = tid; it < IH * (kTW / P); it += kThreads) {
             const int xs = it / IH, r = it - xs * IH;
-            float wv[NV * 4];
+            float wv[NV * 4 + 1];
             const float4* p4 = reinterpret_cast<const float4*>(s_in + r * IP + xs * P);
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
                 const float4 q = p4[j];
                 wv[4 * j] = q.x; wv[4 * j + 1] = q.y; wv[4 * j + 2] = q.z; wv[4 * j + 3] = q.w;
             }
-            float acc[P];
+            wv[NV * 4] = 0.f;
+            float2 acc[P / 2];
 #pragma unroll
-            for (int j = 0; j < P; ++j) acc[j] = 0.f;
+            for (int j = 0; j < P / 2; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int kk = 0; kk < NT; ++kk)
 #pragma unroll
-                for (int j = 0; j < P; ++j) acc[j] = __fmaf_rn(wv[SH + j + kk], t[2 * R - kk], acc[j]);
-            float4* o4 = reinterpret_cast<float4*>(s_row + r * kRowPitch + xs * P);
-            o4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            o4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                for (int j = 0; j < P / 2; ++j)
+                    acc[j] = nm_ffma2(make_float2(wv[SH + 2 * j + kk], wv[SH + 2 * j + kk + 1]), t[2 * R - kk], acc[j]);
+            float2* o2 = reinterpret_cast<float2*>(s_row + r * kRowPitch + xs * P);
+#pragma unroll
+            for (int j = 0; j < P / 2; ++j) o2[j] = acc[j];
         }
     }
     __syncthreads();
 
-    // ---- column pass: 16 outputs per item, lanes walk columns ------------------
+    // ---- column pass: 2 adjacent columns x 8 rows per item, lanes walk column pairs (LDS.64) --------
     {
-        constexpr int P = 16;
-        for (int it = tid; it < kTW * (kTH / P); it += kThreads) {
-            const int ys = it / kTW, col = it - ys * kTW;
-            const int gx = x0 + col;
+        constexpr int P = 8;
+        for (int it = tid; it < (kTW / 2) * (kTH / P); it += kThreads) {
+            const int ys = it / (kTW / 2), cp = it - ys * (kTW / 2);
+            const int gx = x0 + 2 * cp;
             const int gy0 = y0 + ys * P;
             if (gx >= a.w || gy0 >= a.h) continue;
-            float wv[P + 2 * R];
-            const float* p = s_row + (ys * P) * kRowPitch + col;
+            float2 wv[P + 2 * R];
+            const float* p = s_row + (ys * P) * kRowPitch + 2 * cp;
 #pragma unroll
-            for (int j = 0; j < P + 2 * R; ++j) wv[j] = p[j * kRowPitch];
-            float acc[P];
+            for (int j = 0; j < P + 2 * R; ++j) wv[j] = *reinterpret_cast<const float2*>(p + j * kRowPitch);
+            float2 acc[P];
 #pragma unroll
-            for (int j = 0; j < P; ++j) acc[j] = 0.f;
+            for (int j = 0; j < P; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int kk = 0; kk < NT; ++kk)
 #pragma unroll
-                for (int j = 0; j < P; ++j) acc[j] = __fmaf_rn(wv[j + kk], t[2 * R - kk], acc[j]);
+                for (int j = 0; j < P; ++j) acc[j] = nm_ffma2(wv[j + kk], t[2 * R - kk], acc[j]);
             float* o = dst + (long long)gy0 * a.dst_pitch + gx;
+            const bool two = gx + 1 < a.w;
+            // gx is even: the pair is 8-byte aligned when the pitch is even and the image base is
+            const bool vec = two && !(a.dst_pitch & 1) && !(reinterpret_cast<uintptr_t>(dst) & 7);
 #pragma unroll
             for (int j = 0; j < P; ++j)
-                if (gy0 + j < a.h) o[(long long)j * a.dst_pitch] = acc[j];
-            if (a.dst2 != nullptr && (gx & 1) == 0 && (gx >> 1) < (a.w >> 1)) {
+                if (gy0 + j < a.h) {
+                    float* oj = o + (long long)j * a.dst_pitch;
+                    if (vec) *reinterpret_cast<float2*>(oj) = acc[j];
+                    else { oj[0] = acc[j].x; if (two) oj[1] = acc[j].y; }
+                }
+            if (a.dst2 != nullptr && (gx >> 1) < (a.w >> 1)) {
                 float* o2 = a.dst2 + (long long)f * a.dst2_fstride + (gx >> 1);
 #pragma unroll
                 for (int j = 0; j < P; j += 2) {
-                    const int hy = (gy0 + j) >> 1;       // gy0 is even (multiple of 16)
-                    if (hy < (a.h >> 1)) o2[(long long)hy * a.dst2_pitch] = acc[j];
+                    const int hy = (gy0 + j) >> 1;       // gy0 is even (multiple of 8)
+                    if (hy < (a.h >> 1)) o2[(long long)hy * a.dst2_pitch] = acc[j].x;
                 }
             }
         }
