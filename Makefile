@@ -27,7 +27,29 @@ oracle/libnm_oracle.so: oracle/nm_oracle.c
 ref:
 	bash oracle/build_ref.sh
 
+# Drop-in layer: the reference's header names, its three library names and its CMake package file,
+# laid out like the reference's install tree (<prefix>/include/nm, <prefix>/lib/nm).
+CPREFIX   := build/compat/prefix
+CFLAGS_C  := $(ARCH) -O2 -std=c++17 -Xcompiler -fPIC -w -I$(CPREFIX)/include/nm
+compat: $(LIB)
+	@mkdir -p $(CPREFIX)/include/nm $(CPREFIX)/lib/nm build/compat/obj
+	cp compat/include/nm/*.h compat/include/nm/nm_compat.hpp include/nm_b200.h compat/NiftyMatchConfig.cmake $(CPREFIX)/include/nm/
+	$(NVCC) $(CFLAGS_C) -c compat/src/compat_utils.cu -o build/compat/obj/compat_utils.o
+	$(NVCC) $(CFLAGS_C) -c compat/src/compat_kernels.cu -o build/compat/obj/compat_kernels.o
+	$(NVCC) $(CFLAGS_C) -c compat/src/compat_sift.cu -o build/compat/obj/compat_sift.o
+	rm -f $(CPREFIX)/lib/nm/*.a
+	ar rcs $(CPREFIX)/lib/nm/libgpuutils.a build/compat/obj/compat_utils.o
+	ar rcs $(CPREFIX)/lib/nm/libkernels.a build/compat/obj/compat_kernels.o
+	ar rcs $(CPREFIX)/lib/nm/libsift.a build/compat/obj/compat_sift.o
+	cp $(LIB) $(CPREFIX)/lib/nm/libnm_b200.so
+
+# The client loop that drives the REFERENCE in the parity tests (oracle/ref_driver.cu), compiled
+# unchanged against the drop-in tree: test artefact, entry points nmcompat_*.
+compat-client: compat
+	$(NVCC) $(CFLAGS_C) -DNM_COMPAT_BUILD -shared oracle/ref_driver.cu -o build/compat/libnmcompat.so \
+	    -L$(CPREFIX)/lib/nm -lsift -lkernels -lgpuutils -lnm_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/prefix/lib/nm'
+
 clean:
 	rm -rf build $(LIB) oracle/libnm_oracle.so
 
-.PHONY: all ref clean
+.PHONY: all ref clean compat compat-client

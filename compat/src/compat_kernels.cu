@@ -1,0 +1,113 @@
+// compat_kernels.cu -- libkernels.a of the drop-in layer: the reference's kernel launchers
+// (src/gpu/kernels/*.h) as thin wrappers over the C-ABI of libnm_b200 (include/nm_b200.h).
+// No kernel lives here: a wrapper checks nothing the C-ABI does not check, forwards the caller's
+// stream, and turns a non-zero status into the reference's RUNTIME_EXCEPTION.
+#include "nm_compat.hpp"
+#include "nm_b200.h"
+
+namespace {
+inline void nm_check(int rc, const char* what)
+{
+    if (rc != NM_OK) RUNTIME_EXCEPTION(std::string(what) + ": " + nm_strerror(rc));
+}
+} // namespace
+
+// convolution.h:20
+template <>
+void convolve<float>(float* result, const float* image, float* buffer, const int width, const int height,
+                     const float* kernel, const int kernel_radius, cudaStream_t stream)
+{
+    nm_check(nm_blur_f32(result, image, buffer, width, height, kernel, kernel_radius, stream), "convolve");
+}
+
+// downsample.h (float only: the uchar4 instantiation serves the out-of-scope colour path)
+template <>
+void downsample_by_2<float>(float* result, const int result_width, const int result_height, const float* source,
+                            const int source_width, const int source_height, cudaStream_t stream)
+{
+    nm_check(nm_downsample2_f32(result, result_width, result_height, source, source_width, source_height, stream),
+             "downsample_by_2");
+}
+
+// cudamath.h:18-45
+extern "C" int DivUp(int a, int b) { return (a + b - 1) / b; }
+extern "C" int DivDown(int a, int b) { return a / b; }
+extern "C" int AlignUp(int a, int b) { return DivUp(a, b) * b; }
+extern "C" int AlignDown(int a, int b) { return DivDown(a, b) * b; }
+
+template <>
+void subtract<float>(const float* A, const float* B, float* C, const int width, const int height, cudaStream_t stream)
+{
+    nm_check(nm_subtract_f32(A, B, C, width, height, stream), "subtract");
+}
+
+template <>
+void gradient<float>(const float* source, float2* result, const int width, const int height, cudaStream_t stream)
+{
+    nm_check(nm_gradient_f32(source, reinterpret_cast<float*>(result), width, height, stream), "gradient");
+}
+
+// keypoint.h:25, :52
+void find_keypoints(cudaTextureObject_t current, cudaTextureObject_t down, cudaTextureObject_t up, const int width,
+                    const int height, const float peak_threshold, const float edge_threshold, const float xper,
+                    const float sigma_0, const int num_dogs, const int dog, float4* result, cudaStream_t stream)
+{
+    nm_check(nm_keypoints_dense_tex(current, 0, down, up, width, height, peak_threshold, edge_threshold, xper, sigma_0,
+                                    num_dogs, dog, reinterpret_cast<float*>(result), stream),
+             "find_keypoints");
+}
+
+void find_keypoints(cudaTextureObject_t current, cudaTextureObject_t mask, cudaTextureObject_t down,
+                    cudaTextureObject_t up, const int width, const int height, const float peak_threshold,
+                    const float edge_threshold, const float xper, const float sigma_0, const int num_dogs,
+                    const int dog, float4* result, cudaStream_t stream)
+{
+    nm_check(nm_keypoints_dense_tex(current, mask, down, up, width, height, peak_threshold, edge_threshold, xper,
+                                    sigma_0, num_dogs, dog, reinterpret_cast<float*>(result), stream),
+             "find_keypoints (masked)");
+}
+
+// orientation.h:19 -- zero keypoints is a no-op here (the reference would launch an empty grid and abort)
+void detect_orientations(const float4* key_pts, const float2* grad, const int num_pts, const int octave_width,
+                         const int octave_height, float gauss_factor, const float xper, float2* result,
+                         cudaStream_t stream)
+{
+    if (num_pts <= 0) return;
+    nm_check(nm_orientations_f32(reinterpret_cast<const float*>(key_pts), reinterpret_cast<const float*>(grad), num_pts,
+                                 octave_width, octave_height, gauss_factor, xper, reinterpret_cast<float*>(result),
+                                 stream),
+             "detect_orientations");
+}
+
+// descriptor.h:25
+void compute_sift_descriptors(const float4* key_pts, const float2* orients, const float2* grad, const int num_pts,
+                              const int octave_width, const int octave_height, const int num_dogs, const float xper,
+                              float* desc, float* x, float* y, cudaStream_t stream)
+{
+    if (num_pts <= 0) return;
+    nm_check(nm_descriptors_f32(reinterpret_cast<const float*>(key_pts), reinterpret_cast<const float*>(orients),
+                                reinterpret_cast<const float*>(grad), num_pts, octave_width, octave_height, num_dogs,
+                                xper, desc, x, y, stream),
+             "compute_sift_descriptors");
+}
+
+// match.h:19, :41 and transpose.h:17
+template <>
+void compute_brute_force_distance<float>(const float* A, const int size_A, const float* B, const int size_B,
+                                         const int sift_vector_size, float* result, cudaStream_t stream)
+{
+    nm_check(nm_dist2_f32(A, size_A, B, size_B, sift_vector_size, result, stream), "compute_brute_force_distance");
+}
+
+template <>
+void get_sift_matches<float>(const float* distance, const int rows, const int cols, const int buffer_width, int* result,
+                             float ambiguity, cudaStream_t stream)
+{
+    nm_check(nm_set_matches_f32(distance, rows, cols, buffer_width, result, ambiguity, stream), "get_sift_matches");
+}
+
+template <>
+void transpose<float>(float* odata, const float* idata, int width, int height, cudaStream_t stream)
+{
+    nm_check(nm_transpose_f32(odata, idata, width, height, stream), "transpose");
+}

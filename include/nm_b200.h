@@ -88,6 +88,16 @@ int nm_keypoints_dense_f32(const float* dog_cur, const float* dog_down, const fl
                            float xper, float sigma_0, int num_dogs, int level,
                            float* result4, nm_stream_t stream);
 
+/* compute_keypoints_with_mask (gpu/sift/siftfunctions.cu:65-98) without the per-octave cudaArray
+ * copies: DoG images stay linear, only the caller's mask is a texture (sampled at
+ * ((x+.5)*xper, (y+.5)*xper), pixels with mask < 1 are skipped, keypoint.cu:214).
+ * tex_mask = 0 behaves like nm_keypoints_dense_f32. */
+int nm_keypoints_dense_masked_f32(const float* dog_cur, const float* dog_down, const float* dog_up,
+                                  unsigned long long tex_mask, int width, int height,
+                                  float peak_threshold, float edge_threshold, float xper,
+                                  float sigma_0, int num_dogs, int level, float* result4,
+                                  nm_stream_t stream);
+
 /* find_keypoints on cudaTextureObject_t handles, unmasked and masked
  * (gpu/kernels/keypoint.h:25,52).  mask = 0 selects the unmasked variant. */
 int nm_keypoints_dense_tex(unsigned long long tex_cur, unsigned long long tex_mask,

@@ -47,6 +47,7 @@ SIGNATURES = {
     "nm_subtract_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "nm_gradient_f32": (_i, [_vp, _vp, _i, _i, _vp]),
     "nm_keypoints_dense_f32": (_i, [_vp, _vp, _vp, _i, _i, _f, _f, _f, _f, _i, _i, _vp, _vp]),
+    "nm_keypoints_dense_masked_f32": (_i, [_vp, _vp, _vp, _ull, _i, _i, _f, _f, _f, _f, _i, _i, _vp, _vp]),
     "nm_keypoints_dense_tex": (_i, [_ull, _ull, _ull, _ull, _i, _i, _f, _f, _f, _f, _i, _i, _vp, _vp]),
     "nm_collate_f32": (_i, [_vp, _i, _vp, _vp, _vp]),
     "nm_orientations_f32": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp]),

@@ -197,12 +197,13 @@ struct LinearDogFetch {
 };
 
 __global__ void keypoints_dense_linear_kernel(const float* __restrict__ cur, const float* __restrict__ down,
-                                              const float* __restrict__ up, int w, int h,
+                                              const float* __restrict__ up, cudaTextureObject_t mask, int w, int h,
                                               NmDetectParams dp, float xper, int level, float4* __restrict__ result)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x < 1 || x > w - 2 || y < 1 || y > h - 2) return;       // keypoint.cu:191
+    if (mask != 0 && tex2D<float>(mask, (x + 0.5f) * xper, (y + 0.5f) * xper) < 1.f) return;   // keypoint.cu:214
     const long long i = (long long)y * w + x;
     LinearDogFetch ft{cur + i, down + i, up + i, w};
     if (!nm_is_extremum(ft, dp.peak)) return;
@@ -336,7 +337,22 @@ extern "C" int nm_keypoints_dense_f32(const float* dog_cur, const float* dog_dow
     NmDetectParams dp{peak_threshold, edge_threshold, sigma_0, num_dogs};
     dim3 block(32, 8), grid(nm_div_up(width, 32), nm_div_up(height, 8));
     keypoints_dense_linear_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
-        dog_cur, dog_down, dog_up, width, height, dp, xper, level, reinterpret_cast<float4*>(result4));
+        dog_cur, dog_down, dog_up, 0, width, height, dp, xper, level, reinterpret_cast<float4*>(result4));
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+extern "C" int nm_keypoints_dense_masked_f32(const float* dog_cur, const float* dog_down, const float* dog_up,
+                                             unsigned long long tex_mask, int width, int height,
+                                             float peak_threshold, float edge_threshold, float xper, float sigma_0,
+                                             int num_dogs, int level, float* result4, nm_stream_t stream)
+{
+    if (!dog_cur || !dog_down || !dog_up || !result4 || width <= 0 || height <= 0) return NM_ERR_INVALID;
+    NmDetectParams dp{peak_threshold, edge_threshold, sigma_0, num_dogs};
+    dim3 block(32, 8), grid(nm_div_up(width, 32), nm_div_up(height, 8));
+    keypoints_dense_linear_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+        dog_cur, dog_down, dog_up, (cudaTextureObject_t)tex_mask, width, height, dp, xper, level,
+        reinterpret_cast<float4*>(result4));
     NM_LAUNCH_CHECK();
     return NM_OK;
 }

@@ -26,7 +26,17 @@
 // (independent thread scheduling), B200 included -- observed on the GPU box, see
 // DESIGN.md.  The reference's other kernel, kernel_orientations_naive (:132-216), has the
 // same arithmetic without the 10-pixel window clamp and runs fine.
+//
+// -DNM_COMPAT_BUILD compiles this SAME client against the drop-in headers/libraries of this
+// repository (compat/, `make compat-client` -> build/compat/libnmcompat.so, entry points
+// nmcompat_*): proof that reference client code builds and runs unchanged on the new library.
+// In that build only the public API is used (orientation mode 0 works there: no deadlock).
+#ifndef NM_COMPAT_BUILD
 #include "orientation.cu"
+#define NMREF(name) nmref_##name
+#else
+#define NMREF(name) nmcompat_##name
+#endif
 
 #include <thrust/fill.h>
 #include <thrust/copy.h>
@@ -74,7 +84,9 @@ void orientations_step(PyramidData& py, const SiftParams& P, int o, int ow, int 
         float2* orient = thrust::raw_pointer_cast(py._orientations[i].data());
         float2* grad = thrust::raw_pointer_cast(py._grad.data());
         if (mode == 1) {
+#ifndef NM_COMPAT_BUILD
             kernel_orientations_naive<<<(n + 127) / 128, 128>>>(key_pts, grad, n, ow, oh, 1.5f, xper, orient);
+#endif
         } else if (mode == 2) {
             cudaMemcpy(orient, orient_in + 2 * (size_t)(*inject_off), n * sizeof(float2), cudaMemcpyHostToDevice);
             *inject_off += n;
@@ -173,7 +185,7 @@ void run_frame(const float* image_dev, int w, int h, const SiftParams& P, Pyrami
 extern "C" {
 
 // Parameter derivation of the reference (siftparams.h:30-51), for cross-checking ports.
-int nmref_params(int w, int h, int* num_octaves, float* sigma_k, float* sigma_0, float* sigma_d_0,
+int NMREF(params)(int w, int h, int* num_octaves, float* sigma_k, float* sigma_0, float* sigma_d_0,
                  float* base_smooth, float* sigmas5)
 {
     SiftParams P(w, h);
@@ -185,7 +197,7 @@ int nmref_params(int w, int h, int* num_octaves, float* sigma_k, float* sigma_0,
 
 // Gaussian taps as PyramidData builds them (pyramidata.cu:105-123).
 // which = -1: base kernel, 0..4: level kernels.  Returns the radius.
-int nmref_taps(int w, int h, int which, float* taps_out)
+int NMREF(taps)(int w, int h, int which, float* taps_out)
 {
     SiftParams P(w, h);
     PyramidData py(P);
@@ -195,7 +207,7 @@ int nmref_taps(int w, int h, int which, float* taps_out)
     return r;
 }
 
-int nmref_convolve(float* result_host, const float* image_host, int w, int h,
+int NMREF(convolve)(float* result_host, const float* image_host, int w, int h,
                    const float* taps_host, int radius)
 {
     thrust::device_vector<float> img(image_host, image_host + (size_t)w * h);
@@ -217,13 +229,17 @@ int nmref_convolve(float* result_host, const float* image_host, int w, int h,
 //   grad_out   : per octave, 3*ow*oh float2
 //   orient_in  : (orient_mode 2) float2 per keypoint in segment order, injected
 //   cfg6 = {peak, edge(<=0 default), num_octaves(<=0 default), capacity, clear_grad, orient_mode}
-int nmref_sift_frame(const float* image_host, int w, int h, const float* cfg6,
+int NMREF(sift_frame)(const float* image_host, int w, int h, const float* cfg6,
                      float* desc, float* x, float* y, int* num_items,
                      float* levels_out, float* kpts_out, float* orient_out, int* seg_counts,
                      int kp_cap, float* grad_out, const float* orient_in)
 {
     Cfg c = { cfg6[0], cfg6[1], (int)cfg6[2], (int)cfg6[3], (int)cfg6[4], (int)cfg6[5] };
+#ifndef NM_COMPAT_BUILD
     if (c.orient_mode == 0 && !std::getenv("NMREF_ALLOW_DEADLOCK")) return -1;
+#else
+    if (c.orient_mode == 1) return -3;     // the reference's non-public kernel does not exist here
+#endif
     if (c.orient_mode == 2 && !orient_in) return -2;
     SiftParams P = make_params(w, h, c);
     PyramidData py(P);
@@ -244,11 +260,15 @@ int nmref_sift_frame(const float* image_host, int w, int h, const float* cfg6,
 // Timing arm: frames resident on the device (frames_dev: n_frames * w*h floats).
 // Returns total milliseconds (cudaEvent) for `iters` passes over the batch, one
 // PyramidData / SiftData reused across frames as a client would.
-int nmref_sift_bench(const float* frames_dev, int n_frames, int w, int h, const float* cfg6,
+int NMREF(sift_bench)(const float* frames_dev, int n_frames, int w, int h, const float* cfg6,
                      int iters, float* ms_out, long long* total_items)
 {
     Cfg c = { cfg6[0], cfg6[1], (int)cfg6[2], (int)cfg6[3], (int)cfg6[4], (int)cfg6[5] };
+#ifndef NM_COMPAT_BUILD
     if (c.orient_mode != 1) return -1;     // only the runnable configuration can be timed
+#else
+    if (c.orient_mode != 0) return -1;
+#endif
     SiftParams P = make_params(w, h, c);
     PyramidData py(P);
     SiftData data(c.capacity > 0 ? c.capacity : MAX_DESCRIPTORS);
@@ -273,7 +293,7 @@ int nmref_sift_bench(const float* frames_dev, int n_frames, int w, int h, const 
 
 // compute_sift_matches on host data.  match_io is in/out (the reference leaves entries
 // untouched when min2 <= 0, match.cu:107).  dist_out may be null (nA*nB floats otherwise).
-int nmref_match(const float* A_host, int nA, const float* B_host, int nB, float ambiguity,
+int NMREF(match)(const float* A_host, int nA, const float* B_host, int nB, float ambiguity,
                 int* match_io, float* dist_out)
 {
     SiftData A(nA), B(nB);
@@ -290,7 +310,7 @@ int nmref_match(const float* A_host, int nA, const float* B_host, int nB, float 
 }
 
 // Timing arm for the matcher: descriptors resident on the device.
-int nmref_match_bench(const float* A_dev, int nA, const float* B_dev, int nB, float ambiguity,
+int NMREF(match_bench)(const float* A_dev, int nA, const float* B_dev, int nB, float ambiguity,
                       int iters, float* ms_out)
 {
     SiftData A(nA), B(nB);
