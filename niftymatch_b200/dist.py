@@ -33,9 +33,9 @@ def match_sharded(A, B_shard, shard_offset: int, ambiguity: float = 0.8, group=N
     oracle's functions to exercise the same orchestration without a GPU."""
     import torch
     import torch.distributed as dist
-    from . import match as _m
-    top2 = top2 or _m.match_top2
-    merge = merge or _m.merge_top2
+    from .match import match_top2 as _top2, merge_top2 as _merge   # (the package attribute `match` is the function)
+    top2 = top2 or _top2
+    merge = merge or _merge
     rec = top2(A, B_shard, shard_offset)
     world = dist.get_world_size(group)
     n = rec.shape[0]

@@ -213,3 +213,24 @@ def test_tc_matches_exact_at_scale(nm):
     nm.set_engine(-1)
     assert torch.equal(m0, m1)
     assert int((m1 >= 0).sum()) > 5000
+
+
+def test_match_sharded_default_path_single_rank_nccl(nm, oracle):
+    """match_sharded with its default CUDA entry points and a real NCCL all-gather (world size 1 here;
+    the N > 1 orchestration is covered by tests/test_dist_gloo.py and bench.py --gpus N)."""
+    import torch.distributed as dist
+    from niftymatch_b200.dist import match_sharded
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+        created = True
+    try:
+        B = synth.descriptors(1500, 41)
+        A = synth.descriptors(900, 42, planted_from=B)
+        m = match_sharded(_cu(A), _cu(B), 0, 0.8).cpu().numpy()
+        assert np.array_equal(m, oracle.match(A, B, 0.8))
+    finally:
+        if created:
+            dist.destroy_process_group()
