@@ -33,7 +33,7 @@ struct SmemDogFetch {
     __device__ __forceinline__ float up(int dx, int dy) const { return dog[l + 2][r + dy][c + dx]; }
 };
 
-__global__ void __launch_bounds__(256) extrema_grad_kernel(const NmOctave oc, const NmDetectParams dp)
+__global__ void __launch_bounds__(256, 4) extrema_grad_kernel(const NmOctave oc, const NmDetectParams dp)
 {
     __shared__ float s_dog[5][EX_TH + 2][EX_P];
     __shared__ float s_lev[3][EX_TH + 2][EX_P];
@@ -61,6 +61,54 @@ __global__ void __launch_bounds__(256) extrema_grad_kernel(const NmOctave oc, co
     float2* __restrict__ G = oc.grad + (long long)f * 3 * oc.level_elems;
     const long long bm_words = (long long)oc.h * oc.wpr;
     uint32_t* __restrict__ BM = oc.bitmap + (long long)f * 3 * bm_words;
+
+    // ---- 26-neighbour extremum test for the thread's 4 pixels x 3 levels, separably -----------
+    // 3-wide row maxima / minima of every DoG level (with and without the centre column) are shared
+    // by the vertically adjacent pixels of the thread, so a pixel costs ~46 FMNMX3 + 23 LDS instead of
+    // 78 + 81 (the kernel is issue bound: ncu 84 % issue slots busy).  Same comparisons as
+    // keypoint.cu:19-105: strict, against the max / min of the 26 neighbours.
+    unsigned extmask = 0;                      // bit l * 4 + i
+    {
+        const int c = lane + 1, rbase = threadIdx.y * (EX_TH / 8);      // tile row of the first pixel's upper neighbour
+        const float t = __fmul_rn(0.8f, dp.peak);
+        // levels are walked bottom-up with a 3-deep window of the 3x3 (centre included) maxima, so that
+        // detection level l = k - 2 is decided as soon as DoG level k is reduced (keeps ~50 values live)
+        float m9x[3][4], m9n[3][4];            // ring over k % 3
+        float m8x[4], m8n[4], cv[4];           // DoG level k - 1 (centre excluded) and its centre values
+        float p8x[4], p8n[4], pcv[4];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            float hx[6], hn[6], gxm[6], gnm[6], ctr[6];
+#pragma unroll
+            for (int rr = 0; rr < 6; ++rr) {
+                const float a = s_dog[k][rbase + rr][c - 1], b = s_dog[k][rbase + rr][c], d = s_dog[k][rbase + rr][c + 1];
+                hx[rr] = fmaxf(fmaxf(a, b), d);
+                hn[rr] = fminf(fminf(a, b), d);
+                gxm[rr] = fmaxf(a, d);
+                gnm[rr] = fminf(a, d);
+                ctr[rr] = b;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                m9x[k % 3][j] = fmaxf(fmaxf(hx[j], hx[j + 1]), hx[j + 2]);
+                m9n[k % 3][j] = fminf(fminf(hn[j], hn[j + 1]), hn[j + 2]);
+                p8x[j] = m8x[j]; p8n[j] = m8n[j]; pcv[j] = cv[j];          // those of DoG level k - 1
+                m8x[j] = fmaxf(fmaxf(hx[j], gxm[j + 1]), hx[j + 2]);
+                m8n[j] = fminf(fminf(hn[j], gnm[j + 1]), hn[j + 2]);
+                cv[j] = ctr[j + 1];
+            }
+            if (k >= 2) {
+                const int l = k - 2;           // down = k - 2, current = k - 1, up = k
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float mx = fmaxf(fmaxf(m9x[(k - 2) % 3][j], p8x[j]), m9x[k % 3][j]);
+                    const float mn = fminf(fminf(m9n[(k - 2) % 3][j], p8n[j]), m9n[k % 3][j]);
+                    const float c0 = pcv[j];
+                    if ((c0 <= t && c0 < mn) || (c0 >= t && c0 > mx)) extmask |= 1u << (l * 4 + j);   // keypoint.cu:195-196
+                }
+            }
+        }
+    }
 #pragma unroll 1
     for (int i = 0; i < EX_TH / 8; ++i) {
         const int ly = threadIdx.y * (EX_TH / 8) + i;
@@ -79,12 +127,10 @@ __global__ void __launch_bounds__(256) extrema_grad_kernel(const NmOctave oc, co
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
             bool acc = false;
-            if (interior) {
+            if (interior && ((extmask >> (l * 4 + i)) & 1u)) {
                 SmemDogFetch ft{s_dog, l, r, c};
-                if (nm_is_extremum(ft, dp.peak)) {
-                    float4 out;
-                    acc = nm_refine(ft, gx, gy, dp.peak, dp.edge, oc.xper, dp.sigma_0, dp.num_dogs, l, out);
-                }
+                float4 out;
+                acc = nm_refine(ft, gx, gy, dp.peak, dp.edge, oc.xper, dp.sigma_0, dp.num_dogs, l, out);
             }
             const unsigned m = __ballot_sync(0xffffffffu, acc);
             if (lane == 0) BM[l * bm_words + (long long)gy * oc.wpr + blockIdx.x] = m;
