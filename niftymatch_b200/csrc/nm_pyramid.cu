@@ -50,6 +50,13 @@ __host__ __device__ constexpr int blur_smem_bytes(int R)
     return ((kTH + 2 * R) * in_pitch(R) + (kTH + 2 * R) * kRowPitch) * (int)sizeof(float) + 16 + 128;
 }
 
+__host__ __device__ constexpr int blur_window_elems(int R) { return ((kTH + 2 * R) * in_pitch(R) + 31) / 32 * 32; }
+__host__ __device__ constexpr int blur_persist_smem_bytes(int R)
+{
+    // two staged windows (each padded to 128 bytes: TMA destination alignment) + row-pass tile + two mbarriers
+    return (2 * blur_window_elems(R) + (kTH + 2 * R) * kRowPitch) * (int)sizeof(float) + 32;
+}
+
 // ---- mbarrier / TMA PTX -------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
@@ -93,6 +100,147 @@ __device__ __forceinline__ float2 nm_ffma2(float2 a, float t, float2 c)
     return d;
 }
 
+// Both passes issue their multiply-adds as FFMA2 (fma.rn.f32x2: two independent IEEE fp32 FMAs per
+// instruction, a Blackwell addition): the kernel is FMA-issue bound (ncu, R = 13: FMA pipe 52 %,
+// issue slots 64 % busy, DRAM at 27 %), and the paired form halves the FMA instruction count while
+// every output still accumulates k = -R..R in the reference's order, so the result stays bitwise.
+
+// ---- row pass: P outputs (P/2 pairs along x) per item, lanes walk rows (pitch == 4 mod 32) -----
+template <int R, int NTHREADS>
+__device__ __forceinline__ void blur_row_pass(const float* __restrict__ s_in, float* __restrict__ s_row,
+                                              const float (&t)[2 * R + 1], int tid)
+{
+    constexpr int IH = kTH + 2 * R, SH = radius_aligned(R) - R, IP = in_pitch(R), NT = 2 * R + 1;
+    constexpr int P = R > 10 ? 4 : 8;
+    constexpr int NV = (SH + P + 2 * R + 3) / 4; // float4 loads per item
+    for (int it = tid; it < IH * (kTW / P); it += NTHREADS) {
+        const int xs = it / IH, r = it - xs * IH;
+        float wv[NV * 4 + 1];
+        const float4* p4 = reinterpret_cast<const float4*>(s_in + r * IP + xs * P);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const float4 q = p4[j];
+            wv[4 * j] = q.x; wv[4 * j + 1] = q.y; wv[4 * j + 2] = q.z; wv[4 * j + 3] = q.w;
+        }
+        wv[NV * 4] = 0.f;
+        float2 acc[P / 2];
+#pragma unroll
+        for (int j = 0; j < P / 2; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int kk = 0; kk < NT; ++kk)
+#pragma unroll
+            for (int j = 0; j < P / 2; ++j)
+                acc[j] = nm_ffma2(make_float2(wv[SH + 2 * j + kk], wv[SH + 2 * j + kk + 1]), t[2 * R - kk], acc[j]);
+        float2* o2 = reinterpret_cast<float2*>(s_row + r * kRowPitch + xs * P);
+#pragma unroll
+        for (int j = 0; j < P / 2; ++j) o2[j] = acc[j];
+    }
+}
+
+// ---- column pass: 2 adjacent columns x 8 rows per item, lanes walk column pairs (LDS.64) --------
+template <int R, int NTHREADS>
+__device__ __forceinline__ void blur_col_pass(const float* __restrict__ s_row, const NmBlurArgs& a,
+                                              const float (&t)[2 * R + 1], int tid, int x0, int y0, int f)
+{
+    constexpr int NT = 2 * R + 1;
+    constexpr int P = 8;
+    float* __restrict__ dst = a.dst + (long long)f * a.dst_fstride;
+    for (int it = tid; it < (kTW / 2) * (kTH / P); it += NTHREADS) {
+        const int ys = it / (kTW / 2), cp = it - ys * (kTW / 2);
+        const int gx = x0 + 2 * cp;
+        const int gy0 = y0 + ys * P;
+        if (gx >= a.w || gy0 >= a.h) continue;
+        float2 wv[P + 2 * R];
+        const float* p = s_row + (ys * P) * kRowPitch + 2 * cp;
+#pragma unroll
+        for (int j = 0; j < P + 2 * R; ++j) wv[j] = *reinterpret_cast<const float2*>(p + j * kRowPitch);
+        float2 acc[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int kk = 0; kk < NT; ++kk)
+#pragma unroll
+            for (int j = 0; j < P; ++j) acc[j] = nm_ffma2(wv[j + kk], t[2 * R - kk], acc[j]);
+        float* o = dst + (long long)gy0 * a.dst_pitch + gx;
+        const bool two = gx + 1 < a.w;
+        // gx is even: the pair is 8-byte aligned when the pitch is even and the image base is
+        const bool vec = two && !(a.dst_pitch & 1) && !(reinterpret_cast<uintptr_t>(dst) & 7);
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+            if (gy0 + j < a.h) {
+                float* oj = o + (long long)j * a.dst_pitch;
+                if (vec) *reinterpret_cast<float2*>(oj) = acc[j];
+                else { oj[0] = acc[j].x; if (two) oj[1] = acc[j].y; }
+            }
+        if (a.dst2 != nullptr && (gx >> 1) < (a.w >> 1)) {
+            float* o2 = a.dst2 + (long long)f * a.dst2_fstride + (gx >> 1);
+#pragma unroll
+            for (int j = 0; j < P; j += 2) {
+                const int hy = (gy0 + j) >> 1;       // gy0 is even (multiple of 8)
+                if (hy < (a.h >> 1)) o2[(long long)hy * a.dst2_pitch] = acc[j].x;
+            }
+        }
+    }
+}
+
+// Persistent variant for TMA-describable sources: one 512-thread CTA per SM walks the tiles of the
+// launch with TWO input windows in shared memory; the TMA load of the next tile is issued before the
+// passes of the current one, so no warp ever waits for global memory (with one tile per CTA the
+// load, row, column and store phases of the 2 resident CTAs left the issue slots ~50 % idle).
+constexpr int kPThreads = 512;
+template <int R>
+__global__ void __launch_bounds__(kPThreads, 1) blur_persist_kernel(const NmBlurArgs a, const __grid_constant__ CUtensorMap tmap,
+                                                                   int tiles_x, int tiles_y, int n_tiles)
+{
+    constexpr int IH = kTH + 2 * R, RA = radius_aligned(R), IP = in_pitch(R), NT = 2 * R + 1;
+    extern __shared__ __align__(128) float smem[];
+    float* s_in0 = smem;
+    float* s_in1 = smem + blur_window_elems(R);
+    float* s_row = smem + 2 * blur_window_elems(R);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_row + IH * kRowPitch);      // [2]
+    const int tid = threadIdx.x;
+    auto tile_pos = [&](int tile, int& x0, int& y0, int& f) {
+        const int tx = tile % tiles_x, r = tile / tiles_x;
+        x0 = tx * kTW; y0 = (r % tiles_y) * kTH; f = r / tiles_y;
+    };
+    int tile = blockIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (tile < n_tiles) {
+            int x0, y0, f;
+            tile_pos(tile, x0, y0, f);
+            mbar_expect_tx(bar, IH * IP * (uint32_t)sizeof(float));
+            tma_load_3d(s_in0, &tmap, bar, x0 - RA, y0 - R, f);
+        }
+    }
+    float t[NT];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) t[k] = __ldg(a.taps + k);
+    __syncthreads();                           // barriers initialised before anyone polls them
+    for (int k = 0; tile < n_tiles; ++k, tile += gridDim.x) {
+        const int b = k & 1;
+        float* s_in = b ? s_in1 : s_in0;
+        const int next = tile + gridDim.x;
+        if (tid == 0 && next < n_tiles) {
+            // the other window was last read by the row pass of the previous iteration, which every
+            // thread has left (two __syncthreads ago)
+            int x0, y0, f;
+            tile_pos(next, x0, y0, f);
+            mbar_expect_tx(bar + (b ^ 1), IH * IP * (uint32_t)sizeof(float));
+            tma_load_3d(b ? s_in0 : s_in1, &tmap, bar + (b ^ 1), x0 - RA, y0 - R, f);
+        }
+        int x0, y0, f;
+        tile_pos(tile, x0, y0, f);
+        mbar_wait(bar + b, (k >> 1) & 1);
+        blur_row_pass<R, kPThreads>(s_in, s_row, t, tid);
+        __syncthreads();
+        blur_col_pass<R, kPThreads>(s_row, a, t, tid, x0, y0, f);
+        __syncthreads();                       // s_row is rewritten by the next row pass
+    }
+}
+
 template <int R, bool TMA>
 __global__ void __launch_bounds__(kThreads, 2) blur_tile_kernel(const NmBlurArgs a, const __grid_constant__ CUtensorMap tmap)
 {
@@ -112,7 +260,6 @@ __global__ void __launch_bounds__(kThreads, 2) blur_tile_kernel(const NmBlurArgs
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH, f = blockIdx.z;
-    float* __restrict__ dst = a.dst + (long long)f * a.dst_fstride;
 
     if (TMA) {
         // ---- stage the input window by TMA; out-of-tensor elements arrive as +0 -------
@@ -143,79 +290,9 @@ __global__ void __launch_bounds__(kThreads, 2) blur_tile_kernel(const NmBlurArgs
         __syncthreads();
     }
 
-    // Both passes issue their multiply-adds as FFMA2 (fma.rn.f32x2: two independent IEEE fp32 FMAs per
-    // instruction, a Blackwell addition): the kernel is FMA-issue bound (ncu, R = 13: FMA pipe 52 %,
-    // issue slots 64 % busy, DRAM at 27 %), and the paired form halves the FMA instruction count while
-    // every output still accumulates k = -R..R in the reference's order, so the result stays bitwise.
-    // ---- row pass: P outputs (P/2 pairs along x) per item, lanes walk rows (pitch == 4 mod 32) -----
-    {
-        constexpr int P = R > 10 ? 4 : 8;
-        constexpr int NV = (SH + P + 2 * R + 3) / 4; // float4 loads per item
-        for (int it = tid; it < IH * (kTW / P); it += kThreads) {
-            const int xs = it / IH, r = it - xs * IH;
-            float wv[NV * 4 + 1];
-            const float4* p4 = reinterpret_cast<const float4*>(s_in + r * IP + xs * P);
-#pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                const float4 q = p4[j];
-                wv[4 * j] = q.x; wv[4 * j + 1] = q.y; wv[4 * j + 2] = q.z; wv[4 * j + 3] = q.w;
-            }
-            wv[NV * 4] = 0.f;
-            float2 acc[P / 2];
-#pragma unroll
-            for (int j = 0; j < P / 2; ++j) acc[j] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int kk = 0; kk < NT; ++kk)
-#pragma unroll
-                for (int j = 0; j < P / 2; ++j)
-                    acc[j] = nm_ffma2(make_float2(wv[SH + 2 * j + kk], wv[SH + 2 * j + kk + 1]), t[2 * R - kk], acc[j]);
-            float2* o2 = reinterpret_cast<float2*>(s_row + r * kRowPitch + xs * P);
-#pragma unroll
-            for (int j = 0; j < P / 2; ++j) o2[j] = acc[j];
-        }
-    }
+    blur_row_pass<R, kThreads>(s_in, s_row, t, tid);
     __syncthreads();
-
-    // ---- column pass: 2 adjacent columns x 8 rows per item, lanes walk column pairs (LDS.64) --------
-    {
-        constexpr int P = 8;
-        for (int it = tid; it < (kTW / 2) * (kTH / P); it += kThreads) {
-            const int ys = it / (kTW / 2), cp = it - ys * (kTW / 2);
-            const int gx = x0 + 2 * cp;
-            const int gy0 = y0 + ys * P;
-            if (gx >= a.w || gy0 >= a.h) continue;
-            float2 wv[P + 2 * R];
-            const float* p = s_row + (ys * P) * kRowPitch + 2 * cp;
-#pragma unroll
-            for (int j = 0; j < P + 2 * R; ++j) wv[j] = *reinterpret_cast<const float2*>(p + j * kRowPitch);
-            float2 acc[P];
-#pragma unroll
-            for (int j = 0; j < P; ++j) acc[j] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int kk = 0; kk < NT; ++kk)
-#pragma unroll
-                for (int j = 0; j < P; ++j) acc[j] = nm_ffma2(wv[j + kk], t[2 * R - kk], acc[j]);
-            float* o = dst + (long long)gy0 * a.dst_pitch + gx;
-            const bool two = gx + 1 < a.w;
-            // gx is even: the pair is 8-byte aligned when the pitch is even and the image base is
-            const bool vec = two && !(a.dst_pitch & 1) && !(reinterpret_cast<uintptr_t>(dst) & 7);
-#pragma unroll
-            for (int j = 0; j < P; ++j)
-                if (gy0 + j < a.h) {
-                    float* oj = o + (long long)j * a.dst_pitch;
-                    if (vec) *reinterpret_cast<float2*>(oj) = acc[j];
-                    else { oj[0] = acc[j].x; if (two) oj[1] = acc[j].y; }
-                }
-            if (a.dst2 != nullptr && (gx >> 1) < (a.w >> 1)) {
-                float* o2 = a.dst2 + (long long)f * a.dst2_fstride + (gx >> 1);
-#pragma unroll
-                for (int j = 0; j < P; j += 2) {
-                    const int hy = (gy0 + j) >> 1;       // gy0 is even (multiple of 8)
-                    if (hy < (a.h >> 1)) o2[(long long)hy * a.dst2_pitch] = acc[j].x;
-                }
-            }
-        }
-    }
+    blur_col_pass<R, kThreads>(s_row, a, t, tid, x0, y0, f);
 }
 
 // Generic radius (R > 16): two plain kernels through `scratch`, same arithmetic.
@@ -262,7 +339,24 @@ int launch_tile(const NmBlurArgs& a, cudaStream_t stream, const NmBlurTma* tma)
     }
     dim3 grid(nm_div_up(a.w, kTW), nm_div_up(a.h, kTH), a.batch);
     if (tma && tma->valid) {
-        blur_tile_kernel<R, true><<<grid, kThreads, smem, stream>>>(a, tma->map);
+        static int n_sms = 0;
+        constexpr int psmem = blur_persist_smem_bytes(R);
+        if (n_sms == 0) {
+            int dev = 0;
+            NM_CUDA_TRY(cudaGetDevice(&dev));
+            NM_CUDA_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        static bool pconfigured = false;
+        if (!pconfigured) {
+            NM_CUDA_TRY(cudaFuncSetAttribute(blur_persist_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem));
+            pconfigured = true;
+        }
+        const long long n_tiles = (long long)grid.x * grid.y * grid.z;
+        if (n_tiles >= 2LL * n_sms && n_tiles < (1LL << 31)) {
+            blur_persist_kernel<R><<<n_sms, kPThreads, psmem, stream>>>(a, tma->map, (int)grid.x, (int)grid.y, (int)n_tiles);
+        } else {
+            blur_tile_kernel<R, true><<<grid, kThreads, smem, stream>>>(a, tma->map);
+        }
     } else {
         CUtensorMap dummy;
         memset(&dummy, 0, sizeof(dummy));
