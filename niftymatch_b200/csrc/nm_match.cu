@@ -22,6 +22,8 @@
 namespace {
 
 constexpr int MT = 64;            // tile: 64 query rows x 64 database rows
+constexpr int FB_SMALL_MAX = 256; // row-list fallback: lists up to this length take the warp-per-row kernel
+constexpr int FB_CHUNK = 64;      // ... with one block per chunk of this many database rows
 constexpr int MK = 32;            // dims per staged chunk
 constexpr int MP = MT + 4;        // smem pitch
 
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(256) scan_exact_kernel(const float* __restrict
     const int bt_beg = split * b_tiles_per_split;
     const int bt_end = min(bt_beg + b_tiles_per_split, n_btiles);
     const int n_rows = ROWS ? min(*row_count, nA) : nA;
+    if (ROWS && n_rows <= FB_SMALL_MAX) return;        // short lists: scan_rows_small_kernel
 
   for (int a0 = blockIdx.x * MT; a0 < n_rows; a0 += gridDim.x * MT) {
     if (ROWS) {
@@ -161,6 +164,61 @@ __global__ void __launch_bounds__(256) scan_exact_kernel(const float* __restrict
     }
     __syncthreads();                                              // s_rec reused by the next row tile
   }
+}
+
+// Few listed rows (the usual case: a handful of uncertified rows out of 100 000): one block per
+// 64-column chunk of the database stages the chunk in shared memory ONCE and runs every listed row
+// against it (a warp per row, a lane per column, the reference's sequential fp32 arithmetic), so the
+// database is read once however many rows are listed; merged with the same keys as the tiled kernel.
+__global__ void __launch_bounds__(128) scan_rows_small_kernel(const float* __restrict__ A, const float* __restrict__ B, int nB,
+                                                              int index_offset, const int* __restrict__ row_list,
+                                                              const int* __restrict__ row_count, int nA,
+                                                              unsigned long long* __restrict__ key1,
+                                                              unsigned* __restrict__ key2)
+{
+    __shared__ float s_b[FB_CHUNK][129];               // pitch 129: lanes walk rows conflict free
+    __shared__ __align__(16) float s_a[4][128];
+    const int n_rows = min(*row_count, nA);
+    if (n_rows == 0 || n_rows > FB_SMALL_MAX) return;  // long lists: the tiled kernel
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = blockIdx.x * FB_CHUNK;
+    for (int e = threadIdx.x; e < FB_CHUNK * 32; e += 128) {
+        const int r = e >> 5, q = e & 31;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + r < nB) v = __ldg(reinterpret_cast<const float4*>(B + (size_t)(c0 + r) * 128) + q);
+        s_b[r][4 * q] = v.x; s_b[r][4 * q + 1] = v.y; s_b[r][4 * q + 2] = v.z; s_b[r][4 * q + 3] = v.w;
+    }
+    __syncthreads();
+    for (int k = wid; k < n_rows; k += 4) {
+        const int row = row_list[k];
+        __syncwarp();
+        *reinterpret_cast<float4*>(&s_a[wid][lane * 4]) = __ldg(reinterpret_cast<const float4*>(A + (size_t)row * 128) + lane);
+        __syncwarp();
+        float acc0 = 0.f, acc1 = 0.f;                  // columns c0 + lane and c0 + lane + 32
+#pragma unroll 8
+        for (int i = 0; i < 128; ++i) {
+            const float a = s_a[wid][i];
+            float t;
+            t = __fsub_rn(a, s_b[lane][i]); acc0 = __fmaf_rn(t, t, acc0);          // match.cu:39-40, i ascending
+            t = __fsub_rn(a, s_b[lane + 32][i]); acc1 = __fmaf_rn(t, t, acc1);
+        }
+        float t1 = INFINITY, t2 = INFINITY; int i1 = 0x7fffffff;
+        if (c0 + lane < nB) rec_update(t1, i1, t2, acc0, c0 + lane);
+        if (c0 + lane + 32 < nB) rec_update(t1, i1, t2, acc1, c0 + lane + 32);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const float u1 = __shfl_xor_sync(0xffffffffu, t1, d);
+            const int j1 = __shfl_xor_sync(0xffffffffu, i1, d);
+            const float u2 = __shfl_xor_sync(0xffffffffu, t2, d);
+            rec_merge(t1, i1, t2, u1, j1, u2);
+        }
+        if (lane == 0 && i1 != 0x7fffffff) {
+            const unsigned long long mine = ((unsigned long long)__float_as_uint(t1) << 32) | (unsigned)(i1 + index_offset);
+            const unsigned long long old = atomicMin(key1 + k, mine);
+            const unsigned long long loser = old > mine ? old : mine;
+            atomicMin(key2 + k, min((unsigned)(loser >> 32), __float_as_uint(t2)));
+        }
+    }
 }
 
 // Records of a row list from the merged keys: out_rec[row_list[k]] for k < *row_count.
@@ -287,6 +345,13 @@ int nm_match_scan_exact_rows(const float* A, int nA, const float* B, int nB, int
     unsigned long long* key1 = reinterpret_cast<unsigned long long*>(keys);
     unsigned* key2 = reinterpret_cast<unsigned*>(keys + 8 * (size_t)nA);
     cudaError_t e = cudaMemsetAsync(keys, 0xff, 12 * (size_t)nA, stream);
+    if (e == cudaSuccess) {
+        // both regimes are launched; each kernel looks at the device-side count and leaves if the
+        // list is not its size
+        scan_rows_small_kernel<<<nm_div_up(nB, FB_CHUNK), 128, 0, stream>>>(
+            A, B, nB, index_offset, row_list, row_count, nA, key1, key2);
+        e = cudaGetLastError();
+    }
     if (e == cudaSuccess) {
         scan_exact_kernel<false, true><<<dim3(row_blocks, splits), 256, 0, stream>>>(
             A, dim, 1, nA, B, nB, dim, index_offset, per, nullptr, nullptr, 0, 0, row_list, row_count, key1, key2);

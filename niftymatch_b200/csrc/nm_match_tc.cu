@@ -50,7 +50,7 @@ constexpr int TC_ROWBLK = 2 * TC_TROWS;             // query rows per CTA
 constexpr int TC_NST = 4;                           // B stages in shared memory
 constexpr int TC_K = 4;                             // candidates kept per (row, split)
 constexpr int TC_MAX_SPLITS = 4;                    // 4 splits x 2 column halves x 4 = 32 candidates = one warp in rerank
-constexpr int TC_RERANK = 16;                       // candidates per row evaluated exactly
+constexpr int TC_RERANK = 12;                       // candidates per row evaluated exactly
 constexpr int TC_SEED_TILES = 16;                   // database tiles of the seed pass (2048 columns)
 constexpr int TC_EPI_WARPS = 16;                    // 2 row halves x 4 lane quadrants x 2 column halves
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0 copy, warp 1 mma, warps 2..17 epilogue
