@@ -164,11 +164,20 @@ __host__ __device__ constexpr uint32_t tc_idesc(int M, int N)
 // ---------------------------------------------------------------------------------------
 // hdr[0] = bits of max |x| over A and B; hdr[1] = bits of max |b|^2 (unscaled) over B;
 // hdr[2] = bits of max |b^ - s b|^2 over B (the squared fp16 rounding displacement, scaled units).
-__global__ void __launch_bounds__(256) tc_absmax_kernel(const float* __restrict__ X, long long n, unsigned* __restrict__ hdr)
+// One launch for both operands: blocks [0, blocks_a) reduce A, the others B (float4 loads).
+__global__ void __launch_bounds__(256) tc_absmax_kernel(const float* __restrict__ XA, long long na4, int blocks_a,
+                                                        const float* __restrict__ XB, long long nb4, unsigned* __restrict__ hdr)
 {
+    const bool isA = (int)blockIdx.x < blocks_a;
+    const float4* __restrict__ X = reinterpret_cast<const float4*>(isA ? XA : XB);
+    const long long n4 = isA ? na4 : nb4;
+    const long long nblk = isA ? blocks_a : (long long)gridDim.x - blocks_a;
+    const long long blk = isA ? blockIdx.x : (long long)blockIdx.x - blocks_a;
     float m = 0.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        m = fmaxf(m, fabsf(__ldg(X + i)));
+    for (long long i = blk * blockDim.x + threadIdx.x; i < n4; i += nblk * blockDim.x) {
+        const float4 v = __ldg(X + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
     if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(hdr, __float_as_uint(m));
@@ -685,11 +694,10 @@ static int tc_run(const float* A, int nA, const float* B, int nB, int index_offs
 
     cudaError_t e = cudaMemsetAsync(ws, 0, 32, stream);
     if (e == cudaSuccess) {
-        const long long ea = (long long)nA * 128, eb = (long long)nB * 128;
-        const unsigned ga = (unsigned)(nm_div_up64(ea, 2048) < 2048 ? nm_div_up64(ea, 2048) : 2048);
-        const unsigned gb = (unsigned)(nm_div_up64(eb, 2048) < 2048 ? nm_div_up64(eb, 2048) : 2048);
-        tc_absmax_kernel<<<ga, 256, 0, stream>>>(A, ea, hdr);
-        tc_absmax_kernel<<<gb, 256, 0, stream>>>(B, eb, hdr);
+        const long long ea4 = (long long)nA * 32, eb4 = (long long)nB * 32;     // float4 elements
+        const int ga = (int)(nm_div_up64(ea4, 1024) < 1184 ? nm_div_up64(ea4, 1024) : 1184);
+        const int gb = (int)(nm_div_up64(eb4, 1024) < 1184 ? nm_div_up64(eb4, 1024) : 1184);
+        tc_absmax_kernel<<<ga + gb, 256, 0, stream>>>(A, ea4, ga, B, eb4, hdr);
         tc_pack_kernel<false><<<n_atiles, 256, 0, stream>>>(A, nA, hdr, a_pack);
         tc_pack_kernel<true><<<n_btiles, 256, 0, stream>>>(B, nB, hdr, b_pack);
         if (seed_tiles > 0) {
