@@ -107,6 +107,16 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    """Dense bf16/fp16 TFLOP/s: the burst figure (the matcher is timed alone)."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["bf16_tflops"]), "measured burst (MEASURED_PEAKS.json bf16_tflops)"
+    except Exception:
+        return 1590.0, "fallback (B200_PROFILING.md)"
+
+
 def traffic_from_profiles(kernel):
     """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
     try:
@@ -315,8 +325,16 @@ def main():
             m1.record(stream)
             barrier()
             mms = max_over_ranks(m0.elapsed_time(m1) / msteps)
-            match = {"metric": "match_gpairs_per_s", "value": nq * ndb / mms / 1e6, "unit": "Gpairs/s",
+            tpeak, tsrc = measured_tensor_peak()
+            gp = nq * ndb / mms / 1e6
+            match = {"metric": "match_gpairs_per_s", "value": gp, "unit": "Gpairs/s",
                      "ms_per_step": mms, "scaling": "strong", "engine": nm.get_engine(),
+                     "roofline": {"bound": "tensor", "achieved": gp * 256 / 1e3 / world, "peak": tpeak, "unit": "TFLOP/s",
+                                  "frac": gp * 256 / 1e3 / world / tpeak, "peak_source": tsrc,
+                                  "note": "256 flop per (query, database) pair = the 128-long -2a.b contraction "
+                                          "(SURVEY.md 8d); per GPU; whole nm_match_f32 call (pack, tcgen05 scan, "
+                                          "exact re-rank, fallback, merge), not the scan kernel alone",
+                                  "traffic": None},
                      "config": {"workload": "100k x 100k 128-D fp32 descriptors, k=2 ratio test "
                                             "(BASELINE.json configs[3]); database rows sharded over the ranks, "
                                             "NCCL all-gather of per-shard top-2 records + merge",

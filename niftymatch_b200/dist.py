@@ -42,3 +42,36 @@ def match_sharded(A, B_shard, shard_offset: int, ambiguity: float = 0.8, group=N
     allrec = torch.empty((world * n,) + tuple(rec.shape[1:]), dtype=rec.dtype, device=rec.device)
     dist.all_gather_into_tensor(allrec, rec.contiguous(), group=group)     # shard-major
     return merge(allrec.view((world, n) + tuple(rec.shape[1:])), ambiguity)
+
+
+def stream_pairs(n_frames: int, world: int, rank: int):
+    """Consecutive-frame pairs (t, t+1) owned by `rank` of a mosaicking stream (BASELINE.json
+    configs[4]): its contiguous frame range plus one overlap frame, so no descriptors cross GPUs."""
+    lo, hi = frame_range(n_frames, world, rank, overlap=1)
+    return lo, hi, [(t, t + 1) for t in range(lo, hi - 1)]
+
+
+def match_stream(sift_batch, frames, ambiguity: float = 0.8, world: int = 1, rank: int = 0, chunk: int = 16):
+    """SIFT detect+describe on this rank's frames of a stream and match every frame to its
+    successor.  frames: cuda float32 (n, h, w) holding the WHOLE stream (or at least this rank's
+    range).  Returns {t: match indices of frame t into frame t+1} for the pairs this rank owns."""
+    import torch
+    from .match import match as _match
+    n = frames.shape[0]
+    lo, hi, pairs = stream_pairs(n, world, rank)
+    out, prev = {}, None
+    for c0 in range(lo, hi, chunk):
+        c1 = min(hi, c0 + chunk)
+        sift_batch.run(frames[c0:c1].contiguous())
+        r = sift_batch.results()
+        counts = r["counts"][: c1 - c0].tolist()
+        descs = [r["desc"][i, : counts[i]].clone() for i in range(c1 - c0)]
+        for i, d in enumerate(descs):
+            t = c0 + i
+            if prev is not None and prev[0] == t - 1:
+                if prev[1].shape[0] and d.shape[0]:
+                    out[t - 1] = _match(prev[1], d, ambiguity)
+                else:
+                    out[t - 1] = torch.full((prev[1].shape[0],), -1, dtype=torch.int32, device=frames.device)
+            prev = (t, d)
+    return out

@@ -339,3 +339,50 @@ def test_run_host_end_to_end(nm, oracle):
         assert rel.max() <= DESC_REL_TOL
         assert np.array_equal(out["x"][f, :n].numpy(), c["x"])
     sb.close()
+
+
+def test_4k_six_octave_pyramid_and_extrema_vs_oracle(nm, oracle):
+    """BASELINE.json configs[2]: 3840x2160, octave count forced to 6 (the default would be 7):
+    Gaussian levels bitwise, keypoints bitwise, against the CPU oracle."""
+    img = synth.scene(3840, 2160, synth.SEED_BASE + 3)
+    c = oracle.sift_frame(img, peak=2.0, num_octaves=6, capacity=200000, want_levels=True, kp_cap=400000)
+    P = nm.SiftParams(3840, 2160)
+    P._num_octaves = 6
+    P._peak_threshold = 2.0
+    sb = nm.SiftBatch(P, 1, 65536)
+    sb.run(_cu(img[None]))
+    torch.cuda.synchronize()
+    r = sb.results()
+    n = int(r["counts"][0].item())
+    assert c["n_oct"] == 6 and n == min(c["n"], 65536) and n > 1000
+    for o in range(6):
+        for l in range(6):
+            assert np.array_equal(sb.level(0, o, l).cpu().numpy(), c["levels"][o][l]), (o, l)
+    assert np.array_equal(r["seg_counts"][0].cpu().numpy(), c["seg_counts"])
+    assert np.array_equal(r["kpts"][0, :n].cpu().numpy(), c["kpts"][:n])
+    sb.close()
+
+
+def test_stream_sharding_equals_single_run(nm):
+    """BASELINE.json configs[4] at small scale: a stream of consecutive frames, SIFT + match(t -> t+1),
+    sharded over 2 and 3 'ranks' (run one after the other here) with a one-frame overlap, must give
+    exactly the single-rank result for every pair."""
+    from niftymatch_b200.dist import match_stream
+    n, w, h = 7, 320, 240
+    frames = np.stack([synth.scene(w, h, synth.SEED_BASE + 9, shift=(0.75 * t, 0.5 * t)) for t in range(n)])
+    fr = _cu(frames)
+    P = nm.SiftParams(w, h)
+    sb = nm.SiftBatch(P, 4, 4096)
+    single = match_stream(sb, fr, 0.8, 1, 0, chunk=4)
+    assert sorted(single) == list(range(n - 1))
+    assert sum(int((m >= 0).sum()) for m in single.values()) > 50
+    for world in (2, 3):
+        merged = {}
+        for rank in range(world):
+            part = match_stream(sb, fr, 0.8, world, rank, chunk=3)
+            assert not (set(part) & set(merged))
+            merged.update(part)
+        assert sorted(merged) == list(range(n - 1))
+        for t in range(n - 1):
+            assert torch.equal(merged[t], single[t]), (world, t)
+    sb.close()

@@ -73,3 +73,16 @@ def test_early_return_rule(oracle):
 def test_empty_image(oracle):
     r = oracle.sift_frame(np.zeros((64, 64), np.float32), want_levels=False)
     assert r["n"] == 0 and r["seg_counts"].sum() == 0
+
+
+def test_stream_pairs_partition():
+    """Every consecutive pair of a stream is owned by exactly one rank (configs[4] sharding)."""
+    from niftymatch_b200.dist import stream_pairs
+    for n in (2, 7, 100, 10000):
+        for world in (1, 2, 4, 8):
+            seen = []
+            for r in range(world):
+                lo, hi, pairs = stream_pairs(n, world, r)
+                assert all(lo <= a and b < hi for a, b in pairs)
+                seen += pairs
+            assert sorted(seen) == [(t, t + 1) for t in range(n - 1)]
