@@ -159,6 +159,8 @@ __global__ void __launch_bounds__(OR_WARPS * 32) orient_kernel(const NmOctaveTab
 // ------------------------------- descriptor -----------------------------------
 constexpr int DE_WARPS = 4;
 constexpr int DE_BINS = 128;
+constexpr int DE_COPIES = 16;    // private histogram copies per warp (lanes l, l + 16 share one): 8 KB per keypoint
+                                 // in flight instead of 16 -> twice the resident warps (the kernel is latency bound)
 
 // EXACT = the reference's mixed double/float expression shapes (descriptor.cu:98-115, with
 // the DFMA contractions of its sm_100a SASS); !EXACT = the same formulas in fp32 (the bins
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
                                                                  float* __restrict__ desc, float* __restrict__ xo,
                                                                  float* __restrict__ yo, int num_dogs)
 {
-    extern __shared__ __align__(16) float s_h[];      // [DE_WARPS][128 bins][32 lane-private copies]
+    extern __shared__ __align__(16) float s_h[];      // [DE_WARPS][128 bins][DE_COPIES private copies]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int f = blockIdx.y;
     const int j = blockIdx.x * DE_WARPS + wid;
@@ -185,9 +187,10 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
     float* dout = desc + kidx * DE_BINS;
     if (g.xi < 0 || g.xi >= oc.w || g.yi < 0 || g.yi >= oc.h || g.level < 0 || g.level >= num_dogs)
         return;                                                   // :49 (slot left as is)
-    float* hist = s_h + wid * (DE_BINS * 32);
+    float* hist = s_h + wid * (DE_BINS * DE_COPIES);
 #pragma unroll 4
-    for (int b = 0; b < DE_BINS; ++b) hist[b * 32 + lane] = 0.f;
+    for (int b = 0; b < DE_BINS * DE_COPIES / 32; ++b) hist[b * 32 + lane] = 0.f;
+    __syncwarp();
 
     const float SBP = (float)__dadd_rn((double)__fmul_rn(3.0f, g.s), 1.e-07);            // :54
     const int W = (int)floor(__fma_rn(__dmul_rn(__dmul_rn((double)SBP, 1.4142135623730951), 5.0), 0.5, 0.5));  // :55
@@ -212,7 +215,8 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
         return s < total && cx <= xmax && cy <= ymax;             // :96
     };
     // one sample: rotate into the keypoint frame, weight, spread into the 2 x 2 x 2 neighbouring bins
-    auto process = [&](const int cx, const int cy, const float2 gv) {
+    auto process = [&](const int cx, const int cy, const float2 gv, const bool valid) {
+        bool act = valid;
         const float mod = gv.x;
         const float dx = __fsub_rn((float)(g.xi + cx), g.x);          // :102-103
         const float dy = __fsub_rn((float)(g.yi + cy), g.y);
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
             binx = (int)fx; biny = (int)fy;
             // about a third of the window (corners outside the rotated 4x4 cell grid) lands in no
             // bin (:122-125 rejects all four cells): skip before the exponential and the angle
-            if (binx < -3 || binx > 1 || biny < -3 || biny > 1) return;
+            act = act && !(binx < -3 || binx > 1 || biny < -3 || biny > 1);
             const float theta = nm_mod_2pi_f(__fsub_rn(gv.y, th0));   // :100
             nt = __fmul_rn(theta, 1.2732395447351628f);               // 8 / (2 pi)
             win = expf(__fmul_rn(__fmaf_rn(nx, nx, __fmul_rn(ny, ny)), 0.125f));
@@ -252,14 +256,18 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
         const int bx0 = binx + 2, by0 = biny + 2;
         const bool vx0 = (unsigned)bx0 < 4u, vx1 = (unsigned)(bx0 + 1) < 4u;       // :122-125
         const bool vy0 = (unsigned)by0 < 4u, vy1 = (unsigned)(by0 + 1) < 4u;
-        float* hp = hist + lane + (by0 * 32 + bx0 * 8) * 32;          // only dereferenced for valid cells
-        float* h0 = hp + (bint & 7) * 32;                             // :133 (bint + dbt) % 8
-        float* h1 = hp + ((bint + 1) & 7) * 32;
+        float* hp = hist + (lane & 15) + (by0 * 32 + bx0 * 8) * DE_COPIES;   // only dereferenced for valid cells
+        float* h0 = hp + (bint & 7) * DE_COPIES;                      // :133 (bint + dbt) % 8
+        float* h1 = hp + ((bint + 1) & 7) * DE_COPIES;
         const float ax0 = fabsf(__fsub_rn(1.f, rbinx)), ax1 = fabsf(__fsub_rn(0.f, rbinx));
         const float ay0 = fabsf(__fsub_rn(1.f, rbiny)), ay1 = fabsf(__fsub_rn(0.f, rbiny));
         const float at0 = fabsf(__fsub_rn(1.f, rbint)), at1 = fabsf(__fsub_rn(0.f, rbint));
         const float a0 = __fmul_rn(wm, ax0), a1 = __fmul_rn(wm, ax1);
-        constexpr int OX = 8 * 32, OY = 32 * 32;                      // next cell in x / y (floats)
+        constexpr int OX = 8 * DE_COPIES, OY = 32 * DE_COPIES;        // next cell in x / y (floats)
+        // lanes l and l + 16 share a private copy: the two half-warps update one after the other
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+        if (act && (lane >> 4) == ph) {
         if (vx0 && vy0) {
             const float w = __fmul_rn(a0, ay0);
             h0[0] = __fadd_rn(h0[0], __fmul_rn(w, at0)); h1[0] = __fadd_rn(h1[0], __fmul_rn(w, at1));   // :135
@@ -275,6 +283,9 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
         if (vx1 && vy1) {
             const float w = __fmul_rn(a1, ay1);
             h0[OX + OY] = __fadd_rn(h0[OX + OY], __fmul_rn(w, at0)); h1[OX + OY] = __fadd_rn(h1[OX + OY], __fmul_rn(w, at1));
+        }
+        }
+        __syncwarp();
         }
     };
     // DEPTH gradient loads stay in flight per lane (DRAM latency ~1 us against ~150 instructions per
@@ -297,7 +308,7 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
             const float2 gv = pg[d];
             pv[d] = sample_pos(s + 32 * (d + DEPTH), pcx[d], pcy[d]);
             if (pv[d]) pg[d] = __ldg(G + (long long)pcy[d] * oc.pitch + pcx[d]);
-            if (valid) process(cx, cy, gv);
+            process(cx, cy, gv, valid);
         }
     }
     __syncwarp();
@@ -307,7 +318,8 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
         const int b = lane + 32 * q;
         float acc = 0.f;
 #pragma unroll 8
-        for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, hist[b * 32 + ((k + lane) & 31)]);   // rotated: conflict free
+        for (int k = 0; k < DE_COPIES; ++k)
+            acc = __fadd_rn(acc, hist[b * DE_COPIES + ((k + (lane >> 1)) & (DE_COPIES - 1))]);   // rotated: conflict free
         dout[b] = acc;
     }
     if (lane == 0) { xo[kidx] = kp.x; yo[kidx] = kp.y; }              // :76
@@ -332,7 +344,7 @@ int nm_describe_launch(const NmOctaveTable& tab, int batch, int capacity, const 
                        float* x, float* y, int num_dogs, int exact, cudaStream_t stream)
 {
     static bool configured = false;
-    constexpr int smem = DE_WARPS * DE_BINS * 32 * (int)sizeof(float);
+    constexpr int smem = DE_WARPS * DE_BINS * DE_COPIES * (int)sizeof(float);
     if (!configured) {
         NM_CUDA_TRY(cudaFuncSetAttribute(describe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         NM_CUDA_TRY(cudaFuncSetAttribute(describe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
