@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
         const int bx0 = binx + 2, by0 = biny + 2;
         const bool vx0 = (unsigned)bx0 < 4u, vx1 = (unsigned)(bx0 + 1) < 4u;       // :122-125
         const bool vy0 = (unsigned)by0 < 4u, vy1 = (unsigned)(by0 + 1) < 4u;
-        float* hp = hist + (lane & 15) + (by0 * 32 + bx0 * 8) * DE_COPIES;   // only dereferenced for valid cells
+        float* hp = hist + (lane & (DE_COPIES - 1)) + (by0 * 32 + bx0 * 8) * DE_COPIES;   // only dereferenced for valid cells
         float* h0 = hp + (bint & 7) * DE_COPIES;                      // :133 (bint + dbt) % 8
         float* h1 = hp + ((bint + 1) & 7) * DE_COPIES;
         const float ax0 = fabsf(__fsub_rn(1.f, rbinx)), ax1 = fabsf(__fsub_rn(0.f, rbinx));
@@ -266,8 +266,8 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
         constexpr int OX = 8 * DE_COPIES, OY = 32 * DE_COPIES;        // next cell in x / y (floats)
         // lanes l and l + 16 share a private copy: the two half-warps update one after the other
 #pragma unroll
-        for (int ph = 0; ph < 2; ++ph) {
-        if (act && (lane >> 4) == ph) {
+        for (int ph = 0; ph < 32 / DE_COPIES; ++ph) {
+        if (act && (lane / DE_COPIES) == ph) {
         if (vx0 && vy0) {
             const float w = __fmul_rn(a0, ay0);
             h0[0] = __fadd_rn(h0[0], __fmul_rn(w, at0)); h1[0] = __fadd_rn(h1[0], __fmul_rn(w, at1));   // :135
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
         float acc = 0.f;
 #pragma unroll 8
         for (int k = 0; k < DE_COPIES; ++k)
-            acc = __fadd_rn(acc, hist[b * DE_COPIES + ((k + (lane >> 1)) & (DE_COPIES - 1))]);   // rotated: conflict free
+            acc = __fadd_rn(acc, hist[b * DE_COPIES + ((k + lane / (32 / DE_COPIES)) & (DE_COPIES - 1))]);   // rotated: conflict free
         dout[b] = acc;
     }
     if (lane == 0) { xo[kidx] = kp.x; yo[kidx] = kp.y; }              // :76

@@ -111,7 +111,7 @@ __device__ __forceinline__ void blur_row_pass(const float* __restrict__ s_in, fl
                                               const float (&t)[2 * R + 1], int tid)
 {
     constexpr int IH = kTH + 2 * R, SH = radius_aligned(R) - R, IP = in_pitch(R), NT = 2 * R + 1;
-    constexpr int P = R > 10 ? 4 : 8;
+    constexpr int P = 8;
     constexpr int NV = (SH + P + 2 * R + 3) / 4; // float4 loads per item
     for (int it = tid; it < IH * (kTW / P); it += NTHREADS) {
         const int xs = it / IH, r = it - xs * IH;
