@@ -50,7 +50,7 @@ constexpr int TC_ROWBLK = 2 * TC_TROWS;             // query rows per CTA
 constexpr int TC_NST = 4;                           // B stages in shared memory
 constexpr int TC_K = 4;                             // candidates kept per (row, split)
 constexpr int TC_MAX_SPLITS = 4;                    // 4 splits x 2 column halves x 4 = 32 candidates = one warp in rerank
-constexpr int TC_RERANK = 12;                       // candidates per row evaluated exactly
+constexpr int TC_RERANK = 10;                       // candidates per row evaluated exactly
 constexpr int TC_SEED_TILES = 16;                   // database tiles of the seed pass (2048 columns)
 constexpr int TC_EPI_WARPS = 16;                    // 2 row halves x 4 lane quadrants x 2 column halves
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0 copy, warp 1 mma, warps 2..17 epilogue
@@ -194,12 +194,17 @@ __device__ __forceinline__ float tc_scale_from_max(unsigned maxbits)
 }
 
 // One block per 128-row tile; 16 lanes per row (lane = 8-wide k chunk), 16 rows per pass.
-template <bool IS_DB>
-__global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ X, int n, unsigned* __restrict__ hdr,
-                                                      uint8_t* __restrict__ out)
+// Blocks [0, n_atiles) pack the queries, the others the database (one launch for both).
+__global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ XA, int nA, int n_atiles, uint8_t* __restrict__ outA,
+                                                      const float* __restrict__ XB, int nB, uint8_t* __restrict__ outB,
+                                                      unsigned* __restrict__ hdr)
 {
     const float scale = tc_scale_from_max(hdr[0]);
-    const int tile = blockIdx.x, rr = threadIdx.x >> 4, kc = threadIdx.x & 15;
+    const bool IS_DB = (int)blockIdx.x >= n_atiles;
+    const float* __restrict__ X = IS_DB ? XB : XA;
+    const int n = IS_DB ? nB : nA;
+    uint8_t* __restrict__ out = IS_DB ? outB : outA;
+    const int tile = IS_DB ? (int)blockIdx.x - n_atiles : (int)blockIdx.x, rr = threadIdx.x >> 4, kc = threadIdx.x & 15;
     uint8_t* tout = out + (size_t)tile * TC_TILE_BYTES;
     float bmax2 = 0.f, emax2 = 0.f;
     for (int pass = 0; pass < TC_TROWS / 16; ++pass) {
@@ -698,8 +703,7 @@ static int tc_run(const float* A, int nA, const float* B, int nB, int index_offs
         const int ga = (int)(nm_div_up64(ea4, 1024) < 1184 ? nm_div_up64(ea4, 1024) : 1184);
         const int gb = (int)(nm_div_up64(eb4, 1024) < 1184 ? nm_div_up64(eb4, 1024) : 1184);
         tc_absmax_kernel<<<ga + gb, 256, 0, stream>>>(A, ea4, ga, B, eb4, hdr);
-        tc_pack_kernel<false><<<n_atiles, 256, 0, stream>>>(A, nA, hdr, a_pack);
-        tc_pack_kernel<true><<<n_btiles, 256, 0, stream>>>(B, nB, hdr, b_pack);
+        tc_pack_kernel<<<n_atiles + n_btiles, 256, 0, stream>>>(A, nA, n_atiles, a_pack, B, nB, b_pack, hdr);
         if (seed_tiles > 0) {
             TcScanArgs ss{a_pack, b_pack, seed_s, seed_i, nullptr, nullptr, nA, 0, seed_tiles, seed_tiles, g_lbo, g_sbo};
             tc_scan_kernel<<<dim3(n_rowblocks, 1), TC_THREADS, TC_SMEM_BYTES, stream>>>(ss);
