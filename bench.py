@@ -219,8 +219,19 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # stdout must carry the one JSON line only: NCCL prints its version banner to stdout when the
+        # communicator is created, so file descriptor 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     import niftymatch_b200 as nm
     from niftymatch_b200 import synth
