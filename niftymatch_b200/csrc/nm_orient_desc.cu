@@ -18,7 +18,7 @@ namespace {
 
 constexpr int OR_WARPS = 8;      // warps per block, orientation
 constexpr int NBINS = 36;
-constexpr int OR_HP = 33;        // padded lane pitch of the private histograms
+constexpr int OR_HP = 32;        // lane pitch of the private histograms (bank == lane)
 
 struct KpGeom {
     float x, y, s;
@@ -69,18 +69,27 @@ __global__ void __launch_bounds__(OR_WARPS * 32) orient_kernel(const NmOctaveTab
         const int total = (nx > 0 && ny > 0) ? nx * ny : 0;
         const float den = __fmul_rn(sigma_w, __fadd_rn(sigma_w, sigma_w));  // 2*sigma_w*sigma_w
         const double lim = __dadd_rn((double)(W * W), 0.6);
+        // Window samples in raster order, 32 per step; (cx, cy) advance incrementally (no division per
+        // sample) and the gradient of the next step is requested before the arithmetic of this one.
+        int cx = xmin + lane % max(nx, 1), cy = ymin + lane / max(nx, 1);
+        const int adv_y = 32 / max(nx, 1), adv_x = 32 % max(nx, 1);
+        float2 ngv = make_float2(0.f, 0.f);
+        if (lane < total) ngv = __ldg(G + (long long)(g.yi + cy) * oc.pitch + (g.xi + cx));
         for (int s = lane; s < total; s += 32) {
-            const int cy = ymin + s / nx, cx = xmin + s % nx;
-            const float dx = __fsub_rn((float)(cx + g.xi), g.x);  // :52-53
-            const float dy = __fsub_rn((float)(cy + g.yi), g.y);
+            const int ccx = cx, ccy = cy;
+            const float2 gv = ngv;
+            cx += adv_x; cy += adv_y;
+            if (cx > xmax) { cx -= nx; ++cy; }
+            if (s + 32 < total) ngv = __ldg(G + (long long)(g.yi + cy) * oc.pitch + (g.xi + cx));
+            const float dx = __fsub_rn((float)(ccx + g.xi), g.x);  // :52-53
+            const float dy = __fsub_rn((float)(ccy + g.yi), g.y);
             const float r2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));         // :54
             if ((double)r2 < lim) {                               // :55
                 const float wgt = expf(__fdiv_rn(r2, den));       // :56 (positive exponent)
-                const float2 gv = __ldg(G + (long long)(g.yi + cy) * oc.pitch + (g.xi + cx));
                 int bin = (int)floorf((float)__ddiv_rn((double)__fmul_rn(36.0f, gv.y), NM_TWO_PI_D));  // :57
                 bin %= NBINS;
                 if (bin < 0) bin += NBINS;
-                float* p = priv + bin * OR_HP + lane;
+                float* p = priv + bin * OR_HP + lane;             // bank == lane: conflict free
                 *p = __fadd_rn(*p, __fmul_rn(gv.x, wgt));         // :58
             }
         }
@@ -90,7 +99,7 @@ __global__ void __launch_bounds__(OR_WARPS * 32) orient_kernel(const NmOctaveTab
             float acc = 0.f;
             const float* p = priv + b * OR_HP;
 #pragma unroll 8
-            for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, p[k]);
+            for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, p[(k + lane) & 31]);   // rotated: conflict free
             hist[b] = acc;
         }
         __syncwarp();
