@@ -139,31 +139,58 @@ __global__ void __launch_bounds__(256, 4) extrema_grad_kernel(const NmOctave oc,
 }
 
 // One block per (segment, frame): exclusive prefix of the word popcounts + segment total.
+// Coalesced: the block walks the bitmap in spans of 1024 words (4 consecutive words per thread, one
+// 16-byte load), scans the span with warp shuffles, and carries the running total across spans.
 __global__ void __launch_bounds__(256) rank_kernel(const NmOctaveTable tab, int* __restrict__ seg_raw)
 {
-    __shared__ int s_part[256];
-    const int s = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    __shared__ int s_warp[8];
+    __shared__ int s_carry;
+    const int s = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const NmOctave& oc = tab.o[s / 3];
     const int l = s % 3;
     const int nwords = oc.h * oc.wpr;
     const uint32_t* __restrict__ bm = oc.bitmap + ((long long)f * 3 + l) * nwords;
     int* __restrict__ wp = oc.wprefix + ((long long)f * 3 + l) * nwords;
-    const int chunk = (nwords + 255) / 256;
-    const int beg = tid * chunk, end = min(beg + chunk, nwords);
-    int sum = 0;
-    for (int i = beg; i < end; ++i) sum += __popc(bm[i]);
-    s_part[tid] = sum;
+    const bool vec = ((reinterpret_cast<uintptr_t>(bm) | reinterpret_cast<uintptr_t>(wp)) & 15) == 0;
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    // Hillis-Steele inclusive scan over 256 partials
-    for (int d = 1; d < 256; d <<= 1) {
-        int v = tid >= d ? s_part[tid - d] : 0;
+    for (int base = 0; base < nwords; base += 1024) {
+        const int i0 = base + tid * 4;
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+        if (vec && i0 + 3 < nwords) {
+            w = *reinterpret_cast<const uint4*>(bm + i0);
+        } else {
+            if (i0 < nwords) w.x = bm[i0];
+            if (i0 + 1 < nwords) w.y = bm[i0 + 1];
+            if (i0 + 2 < nwords) w.z = bm[i0 + 2];
+            if (i0 + 3 < nwords) w.w = bm[i0 + 3];
+        }
+        const int c0 = __popc(w.x), c1 = __popc(w.y), c2 = __popc(w.z), c3 = __popc(w.w);
+        const int mine = c0 + c1 + c2 + c3;
+        int incl = mine;                                   // inclusive scan over the warp
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) s_warp[wid] = incl;
         __syncthreads();
-        s_part[tid] += v;
+        int off = s_carry;
+        for (int k = 0; k < wid; ++k) off += s_warp[k];
+        const int e0 = off + incl - mine;
+        if (vec && i0 + 3 < nwords) {
+            *reinterpret_cast<int4*>(wp + i0) = make_int4(e0, e0 + c0, e0 + c0 + c1, e0 + c0 + c1 + c2);
+        } else {
+            if (i0 < nwords) wp[i0] = e0;
+            if (i0 + 1 < nwords) wp[i0 + 1] = e0 + c0;
+            if (i0 + 2 < nwords) wp[i0 + 2] = e0 + c0 + c1;
+            if (i0 + 3 < nwords) wp[i0 + 3] = e0 + c0 + c1 + c2;
+        }
+        __syncthreads();
+        if (tid == 255) s_carry = off + incl;
         __syncthreads();
     }
-    int run = s_part[tid] - sum;
-    for (int i = beg; i < end; ++i) { wp[i] = run; run += __popc(bm[i]); }
-    if (tid == 255) seg_raw[f * tab.n_oct * 3 + s] = s_part[255];
+    if (tid == 0) seg_raw[f * tab.n_oct * 3 + s] = s_carry;
 }
 
 // Early-return rule (siftfunctions.cu:145,160: the first empty level ends the octave),
