@@ -50,6 +50,7 @@ constexpr int TC_ROWBLK = 2 * TC_TROWS;             // query rows per CTA
 constexpr int TC_NST = 4;                           // B stages in shared memory
 constexpr int TC_K = 4;                             // candidates kept per (row, split)
 constexpr int TC_MAX_SPLITS = 4;                    // 4 splits x 2 column halves x 4 = 32 candidates = one warp in rerank
+constexpr int TC_RERANK1 = 4;                       // ... in the first round
 constexpr int TC_RERANK = 10;                       // candidates per row evaluated exactly
 constexpr int TC_SEED_TILES = 16;                   // database tiles of the seed pass (2048 columns)
 constexpr int TC_EPI_WARPS = 16;                    // 2 row halves x 4 lane quadrants x 2 column halves
@@ -505,6 +506,7 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict_
     // database rows is what this kernel costs); the others become non-candidates, bounded by the
     // best score among them.
     float sc_own = -FLT_MAX;
+    int my_rank = 32;
     if (sp < n_lists) {
         const float4 cs = cand_s[(size_t)sp * nA + a];
         sc_own = k == 0 ? cs.x : k == 1 ? cs.y : k == 2 ? cs.z : cs.w;
@@ -521,61 +523,71 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict_
             const float os = __shfl_sync(0xffffffffu, sc_own, src);
             rank += (os > sc_own || (os == sc_own && src < lane)) ? 1 : 0;
         }
-        // best score among the pruned candidates (rank == TC_RERANK), if any
-        const float cut = (rank == TC_RERANK && idx >= 0) ? sc_own : -FLT_MAX;
-        if (rank >= TC_RERANK) idx = -1;
-        thr = fmaxf(thr, cut);
+        my_rank = rank;
     }
-    float dist = INFINITY;
-    int jdx = 0x7fffffff;
-    if (idx >= 0 && idx < nB) {
-        const float4* __restrict__ bp = reinterpret_cast<const float4*>(B + (size_t)idx * 128);
+    // every non-candidate of list s has score <= thr_s  =>  all of them have score <= max_s thr_s
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) thr = fmaxf(thr, __shfl_xor_sync(0xffffffffu, thr, d));
+
+    // Scaled units (s = the power-of-two scale): the accumulator holds S = a^.b^ - |b^|^2/2 up to an
+    // accumulation error <= eta/2, so every column with score <= t has |a^-b^|^2 >= |a^|^2 - 2 t - eta.
+    // Rounding to fp16 displaced a by |a^ - s a| (measured here) and any b by at most
+    // max_j |b^_j - s b_j| (measured by the pack kernel), so by the triangle inequality
+    // s * sqrt(true d) >= sqrt(|a^-b^|^2) - delta.
+    const double sc = (double)scale;
+    const double bmax2 = (double)__uint_as_float(hdr[1]) * sc * sc * (1.0 + 1e-5);
+    const double eta = ldexp(nh2 + bmax2, -17);    // measured: see tests (accumulation error < 2^-20 (|a^|^2+|b^|^2))
+    const double delta = (sqrt(ne2) + sqrt((double)__uint_as_float(hdr[2]))) * (1.0 + 1e-5) + 1e-7;
+    auto lower_bound = [&](float t) -> double {    // on the true distance of every column with score <= t
+        if (t <= -FLT_MAX) return (double)INFINITY;
+        const double dh = nh2 - 2.0 * (double)t - eta;
+        const double root = (dh > 0.0 ? sqrt(dh) : 0.0) - delta;
+        return root > 0.0 ? (root / sc) * (root / sc) * (1.0 - 1e-6) : 0.0;
+    };
+    auto exact_distance = [&](int col) -> float {  // match.cu:36-42: i ascending, t = a - b, acc = fma(t, t, acc)
+        const float4* __restrict__ bp = reinterpret_cast<const float4*>(B + (size_t)col * 128);
         float acc = 0.f;
 #pragma unroll 8
         for (int i = 0; i < 32; ++i) {
             const float4 b4 = __ldg(bp + i);
             const float4 a4 = *reinterpret_cast<const float4*>(&s_a[wid][i * 4]);
             float t;
-            t = __fsub_rn(a4.x, b4.x); acc = __fmaf_rn(t, t, acc);   // match.cu:39-40, i ascending
+            t = __fsub_rn(a4.x, b4.x); acc = __fmaf_rn(t, t, acc);
             t = __fsub_rn(a4.y, b4.y); acc = __fmaf_rn(t, t, acc);
             t = __fsub_rn(a4.z, b4.z); acc = __fmaf_rn(t, t, acc);
             t = __fsub_rn(a4.w, b4.w); acc = __fmaf_rn(t, t, acc);
         }
-        dist = acc;
-        jdx = idx;
-    }
-    const int n_valid = __popc(__ballot_sync(0xffffffffu, jdx != 0x7fffffff));
-    float t1 = dist, t2 = INFINITY;
-    int i1 = jdx;
+        return acc;
+    };
+    // Two rounds: most rows are already certified by their TC_RERANK1 best-scoring candidates (the
+    // others are then bounded by the best score among them); only the rest gather TC_RERANK rows.
+    float t1 = INFINITY, t2 = INFINITY;
+    int i1 = 0x7fffffff;
+    int lo = 0;
+    bool certified = false;
+#pragma unroll 1
+    for (int round = 0; round < 2 && !certified; ++round) {
+        const int hi = round == 0 ? TC_RERANK1 : TC_RERANK;
+        float d1 = INFINITY, d2 = INFINITY;
+        int j1 = 0x7fffffff;
+        if (idx >= 0 && my_rank >= lo && my_rank < hi) { d1 = exact_distance(idx); j1 = idx; }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        const float u1 = __shfl_xor_sync(0xffffffffu, t1, d);
-        const int j1 = __shfl_xor_sync(0xffffffffu, i1, d);
-        const float u2 = __shfl_xor_sync(0xffffffffu, t2, d);
-        rec_merge_lex(t1, i1, t2, u1, j1, u2);
-    }
-    // every non-candidate of split s has score <= thr_s  =>  all of them have score <= max_s thr_s
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) thr = fmaxf(thr, __shfl_xor_sync(0xffffffffu, thr, d));
-    if (lane == 0) {
-        // Scaled units (s = the power-of-two scale): the accumulator holds S = a^.b^ - |b^|^2/2 up to an
-        // accumulation error <= eta/2, so every non-candidate has |a^-b^|^2 >= |a^|^2 - 2 thr - eta.
-        // Rounding to fp16 displaced a by |a^ - s a| (measured here) and any b by at most
-        // max_j |b^_j - s b_j| (measured by the pack kernel), so by the triangle inequality
-        // s * sqrt(true d) >= sqrt(|a^-b^|^2) - delta.
-        const double sc = (double)scale;
-        const double bmax2 = (double)__uint_as_float(hdr[1]) * sc * sc * (1.0 + 1e-5);
-        const double eta = ldexp(nh2 + bmax2, -17);    // measured: see tests (accumulation error < 2^-20 (|a^|^2+|b^|^2))
-        const double delta = (sqrt(ne2) + sqrt((double)__uint_as_float(hdr[2]))) * (1.0 + 1e-5) + 1e-7;
-        bool certified;
-        if (thr <= -FLT_MAX || n_valid >= nB) {
-            certified = true;                                     // nothing was ever rejected: all columns are candidates
-        } else {
-            const double dh = nh2 - 2.0 * (double)thr - eta;
-            const double root = (dh > 0.0 ? sqrt(dh) : 0.0) - delta;
-            const double lb = root > 0.0 ? (root / sc) * (root / sc) * (1.0 - 1e-6) : 0.0;
-            certified = (double)t2 < lb;
+        for (int d = 16; d > 0; d >>= 1) {
+            const float u1 = __shfl_xor_sync(0xffffffffu, d1, d);
+            const int k1 = __shfl_xor_sync(0xffffffffu, j1, d);
+            const float u2 = __shfl_xor_sync(0xffffffffu, d2, d);
+            rec_merge_lex(d1, j1, d2, u1, k1, u2);
         }
+        rec_merge_lex(t1, i1, t2, d1, j1, d2);
+        // best score among the candidates not evaluated so far (rank == hi), if any
+        float cut = (idx >= 0 && my_rank == hi) ? sc_own : -FLT_MAX;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cut = fmaxf(cut, __shfl_xor_sync(0xffffffffu, cut, d));
+        const int n_eval = __popc(__ballot_sync(0xffffffffu, idx >= 0 && my_rank < hi));
+        certified = n_eval >= nB || (double)t2 < lower_bound(fmaxf(thr, cut));     // warp uniform
+        lo = hi;
+    }
+    if (lane == 0) {
         if (certified) {
             rec4[a] = make_float4(t1, __int_as_float(i1 == 0x7fffffff ? -1 : i1 + index_offset), t2, 0.f);
         } else {
