@@ -8,6 +8,7 @@
 #include "nm_pyramid.cuh"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <cstdio>
 #include <new>
 #include <vector>
@@ -334,14 +335,33 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
     if (!c || !frames_host || !counts_host || n_frames <= 0 || n_frames > c->B) return NM_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t fpix = (size_t)c->P.width * c->P.height;
-    const int n_chunks = nm_div_up(n_frames, NM_HOST_CHUNK);
+    // Pipeline stages: the end-to-end time is (upload of the first stage) + (all kernels) + (download of
+    // the last stage), and every stage costs ~0.25 ms of under-filled launches, so the schedule is a small
+    // first and last stage around stages of up to 16 frames.  NM_HOST_CHUNK=<n> forces uniform stages.
+    static const int forced = [] {
+        const char* e = getenv("NM_HOST_CHUNK");
+        return e ? atoi(e) : 0;
+    }();
+    int bounds[NM_MAX_CHUNKS + 1];
+    int n_chunks = 0;
+    bounds[0] = 0;
+    if (forced > 0) {
+        for (int f = 0; f < n_frames && n_chunks < NM_MAX_CHUNKS; f += forced) bounds[++n_chunks] = f + forced < n_frames ? f + forced : n_frames;
+        if (bounds[n_chunks] != n_frames) return NM_ERR_INVALID;
+    } else if (n_frames <= 8) {
+        bounds[++n_chunks] = n_frames;
+    } else {
+        const int edge = 4, mid = n_frames - 2 * edge, m = nm_div_up(mid, 16);
+        bounds[++n_chunks] = edge;
+        for (int i = 1; i <= m; ++i) bounds[++n_chunks] = edge + (int)((long long)mid * i / m);
+        bounds[++n_chunks] = n_frames;
+    }
     if (n_chunks > NM_MAX_CHUNKS) return NM_ERR_INVALID;
     int launches = 0;
     auto drain = [&](int k) -> int {
         // results of chunk k: wait for its counts, then copy the filled part of every frame
         NM_CUDA_TRY(cudaEventSynchronize(c->ev_done[k]));
-        const int f0 = k * NM_HOST_CHUNK, f1 = f0 + NM_HOST_CHUNK < n_frames ? f0 + NM_HOST_CHUNK : n_frames;
-        for (int f = f0; f < f1; ++f) {
+        for (int f = bounds[k]; f < bounds[k + 1]; ++f) {
             const size_t n = (size_t)counts_host[f], off = (size_t)f * c->capacity;
             if (n == 0) continue;
             if (desc_host) NM_CUDA_TRY(cudaMemcpyAsync(desc_host + off * 128, c->desc + off * 128, n * 128 * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
@@ -351,13 +371,13 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
         return NM_OK;
     };
     for (int k = 0; k < n_chunks; ++k) {        // the uploads do not depend on anything: queue them all
-        const int f0 = k * NM_HOST_CHUNK, n = f0 + NM_HOST_CHUNK < n_frames ? NM_HOST_CHUNK : n_frames - f0;
+        const int f0 = bounds[k], n = bounds[k + 1] - bounds[k];
         NM_CUDA_TRY(cudaMemcpyAsync(c->frames_stage + f0 * fpix, frames_host + f0 * fpix, fpix * n * sizeof(float),
                                     cudaMemcpyHostToDevice, c->s_in));
         NM_CUDA_TRY(cudaEventRecord(c->ev_in[k], c->s_in));
     }
     for (int k = 0; k < n_chunks; ++k) {
-        const int f0 = k * NM_HOST_CHUNK, n = f0 + NM_HOST_CHUNK < n_frames ? NM_HOST_CHUNK : n_frames - f0;
+        const int f0 = bounds[k], n = bounds[k + 1] - bounds[k];
         NM_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_in[k], 0));
         int rc = sift_run_range(c, c->frames_stage + f0 * fpix, f0, n, st, false);
         if (rc != NM_OK) return rc;

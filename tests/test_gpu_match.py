@@ -234,3 +234,32 @@ def test_match_sharded_default_path_single_rank_nccl(nm, oracle):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_full_size_100k_engines_agree_and_planted_rows_match(nm):
+    """BASELINE.json configs[3] at full size on one GPU: 100k x 100k.  The tensor-core engine and the
+    exact fp32 engine must return identical indices, and every planted query (a database row plus
+    small noise) must match the row it was planted from."""
+    _need_tc(nm)
+    n = 100000
+    Bh = synth.descriptors(n, 2)
+    Ah = synth.descriptors(n, 1, planted_from=Bh)
+    At, Bt = _cu(Ah), _cu(Bh)
+    nm.set_engine(1)
+    m1 = nm.match(At, Bt, 0.8)
+    nm.set_engine(0)
+    m0 = nm.match(At, Bt, 0.8)
+    nm.set_engine(-1)
+    assert torch.equal(m0, m1)
+    # recover the planting (same construction as synth.descriptors)
+    k = int(n * 0.2)
+    rows = (synth.uniform(1, 14, k) * n).astype(np.int64)
+    src = (synth.uniform(1, 15, k) * n).astype(np.int64)
+    last = {}
+    for r, s_ in zip(rows, src):
+        last[int(r)] = int(s_)                      # later plantings overwrite earlier ones
+    mm = m1.cpu().numpy()
+    rr = np.fromiter(last.keys(), dtype=np.int64)
+    ss = np.fromiter(last.values(), dtype=np.int64)
+    hit = mm[rr] == ss
+    assert hit.mean() > 0.999, hit.mean()
