@@ -58,7 +58,9 @@ __global__ void __launch_bounds__(OR_WARPS * 32) orient_kernel(const NmOctaveTab
         const float sigma_w = __fmul_rn(1.5f, g.s);               // :26, gauss_factor = 1.5 (siftfunctions.cu:150)
         int W = max((int)floorf(__fmul_rn(3.0f, sigma_w)), 1);    // :27
         W = min(W, 10);                                           // :29-30 (22x22 block)
-        const float2* __restrict__ G = oc.grad + ((long long)f * 3 + g.level) * oc.level_elems;
+        const float2* __restrict__ G = oc.grad + ((long long)f * 3 + g.level) * oc.level_elems +
+                                       (long long)g.yi * oc.pitch + g.xi;      // at the keypoint; offsets below are 32-bit
+        const int pitch = oc.pitch;
         float* priv = s_priv[wid];
         float* hist = s_hist[wid];
 #pragma unroll
@@ -74,13 +76,13 @@ __global__ void __launch_bounds__(OR_WARPS * 32) orient_kernel(const NmOctaveTab
         int cx = xmin + lane % max(nx, 1), cy = ymin + lane / max(nx, 1);
         const int adv_y = 32 / max(nx, 1), adv_x = 32 % max(nx, 1);
         float2 ngv = make_float2(0.f, 0.f);
-        if (lane < total) ngv = __ldg(G + (long long)(g.yi + cy) * oc.pitch + (g.xi + cx));
+        if (lane < total) ngv = __ldg(G + (cy * pitch + cx));
         for (int s = lane; s < total; s += 32) {
             const int ccx = cx, ccy = cy;
             const float2 gv = ngv;
             cx += adv_x; cy += adv_y;
             if (cx > xmax) { cx -= nx; ++cy; }
-            if (s + 32 < total) ngv = __ldg(G + (long long)(g.yi + cy) * oc.pitch + (g.xi + cx));
+            if (s + 32 < total) ngv = __ldg(G + (cy * pitch + cx));
             const float dx = __fsub_rn((float)(ccx + g.xi), g.x);  // :52-53
             const float dy = __fsub_rn((float)(ccy + g.yi), g.y);
             const float r2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));         // :54
@@ -300,6 +302,7 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
     // DEPTH gradient loads stay in flight per lane (DRAM latency ~1 us against ~150 instructions per
     // sample and under 3 resident warps per scheduler)
     constexpr int DEPTH = 4;
+    const int dpitch = oc.pitch;               // offsets inside one level fit 32 bits
     int pcx[DEPTH], pcy[DEPTH];
     bool pv[DEPTH];
     float2 pg[DEPTH];
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
     for (int d = 0; d < DEPTH; ++d) {
         pv[d] = sample_pos(lane + 32 * d, pcx[d], pcy[d]);
         pg[d] = make_float2(0.f, 0.f);
-        if (pv[d]) pg[d] = __ldg(G + (long long)pcy[d] * oc.pitch + pcx[d]);
+        if (pv[d]) pg[d] = __ldg(G + (pcy[d] * dpitch + pcx[d]));
     }
     for (int s = lane; s < total; s += 32 * DEPTH) {
 #pragma unroll
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
             const bool valid = pv[d];
             const float2 gv = pg[d];
             pv[d] = sample_pos(s + 32 * (d + DEPTH), pcx[d], pcy[d]);
-            if (pv[d]) pg[d] = __ldg(G + (long long)pcy[d] * oc.pitch + pcx[d]);
+            if (pv[d]) pg[d] = __ldg(G + (pcy[d] * dpitch + pcx[d]));
             process(cx, cy, gv, valid);
         }
     }
