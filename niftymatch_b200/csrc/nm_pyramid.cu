@@ -25,12 +25,14 @@
 #include "nm_pyramid.cuh"
 #include <mutex>
 #include <cstring>
+#include <cstdlib>
 
 namespace {
 
 constexpr int kTW = 128;          // tile width  (outputs)
 constexpr int kTH = 64;           // tile height (outputs)
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;        // 2 CTAs per SM = 32 warps: 256-thread CTAs (16 warps) and a persistent
+                                   // 512-thread CTA with double-buffered TMA windows were both ~10 % slower
 constexpr int kRowPitch = kTW + 4;   // 132 == 4 (mod 32): conflict-free float4 per-row access
 
 // TMA needs a 16-byte aligned start in the innermost dimension, so the staged window starts
@@ -48,13 +50,6 @@ __host__ __device__ constexpr int blur_smem_bytes(int R)
 {
     // staged window + row-pass tile + mbarrier, plus slack for the manual 128-byte alignment
     return ((kTH + 2 * R) * in_pitch(R) + (kTH + 2 * R) * kRowPitch) * (int)sizeof(float) + 16 + 128;
-}
-
-__host__ __device__ constexpr int blur_window_elems(int R) { return ((kTH + 2 * R) * in_pitch(R) + 31) / 32 * 32; }
-__host__ __device__ constexpr int blur_persist_smem_bytes(int R)
-{
-    // two staged windows (each padded to 128 bytes: TMA destination alignment) + row-pass tile + two mbarriers
-    return (2 * blur_window_elems(R) + (kTH + 2 * R) * kRowPitch) * (int)sizeof(float) + 32;
 }
 
 // ---- mbarrier / TMA PTX -------------------------------------------------------------------
@@ -183,64 +178,6 @@ __device__ __forceinline__ void blur_col_pass(const float* __restrict__ s_row, c
     }
 }
 
-// Persistent variant for TMA-describable sources: one 512-thread CTA per SM walks the tiles of the
-// launch with TWO input windows in shared memory; the TMA load of the next tile is issued before the
-// passes of the current one, so no warp ever waits for global memory (with one tile per CTA the
-// load, row, column and store phases of the 2 resident CTAs left the issue slots ~50 % idle).
-constexpr int kPThreads = 512;
-template <int R>
-__global__ void __launch_bounds__(kPThreads, 1) blur_persist_kernel(const NmBlurArgs a, const __grid_constant__ CUtensorMap tmap,
-                                                                   int tiles_x, int tiles_y, int n_tiles)
-{
-    constexpr int IH = kTH + 2 * R, RA = radius_aligned(R), IP = in_pitch(R), NT = 2 * R + 1;
-    extern __shared__ __align__(128) float smem[];
-    float* s_in0 = smem;
-    float* s_in1 = smem + blur_window_elems(R);
-    float* s_row = smem + 2 * blur_window_elems(R);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_row + IH * kRowPitch);      // [2]
-    const int tid = threadIdx.x;
-    auto tile_pos = [&](int tile, int& x0, int& y0, int& f) {
-        const int tx = tile % tiles_x, r = tile / tiles_x;
-        x0 = tx * kTW; y0 = (r % tiles_y) * kTH; f = r / tiles_y;
-    };
-    int tile = blockIdx.x;
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_init(bar + 1, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (tile < n_tiles) {
-            int x0, y0, f;
-            tile_pos(tile, x0, y0, f);
-            mbar_expect_tx(bar, IH * IP * (uint32_t)sizeof(float));
-            tma_load_3d(s_in0, &tmap, bar, x0 - RA, y0 - R, f);
-        }
-    }
-    float t[NT];
-#pragma unroll
-    for (int k = 0; k < NT; ++k) t[k] = __ldg(a.taps + k);
-    __syncthreads();                           // barriers initialised before anyone polls them
-    for (int k = 0; tile < n_tiles; ++k, tile += gridDim.x) {
-        const int b = k & 1;
-        float* s_in = b ? s_in1 : s_in0;
-        const int next = tile + gridDim.x;
-        if (tid == 0 && next < n_tiles) {
-            // the other window was last read by the row pass of the previous iteration, which every
-            // thread has left (two __syncthreads ago)
-            int x0, y0, f;
-            tile_pos(next, x0, y0, f);
-            mbar_expect_tx(bar + (b ^ 1), IH * IP * (uint32_t)sizeof(float));
-            tma_load_3d(b ? s_in0 : s_in1, &tmap, bar + (b ^ 1), x0 - RA, y0 - R, f);
-        }
-        int x0, y0, f;
-        tile_pos(tile, x0, y0, f);
-        mbar_wait(bar + b, (k >> 1) & 1);
-        blur_row_pass<R, kPThreads>(s_in, s_row, t, tid);
-        __syncthreads();
-        blur_col_pass<R, kPThreads>(s_row, a, t, tid, x0, y0, f);
-        __syncthreads();                       // s_row is rewritten by the next row pass
-    }
-}
-
 template <int R, bool TMA>
 __global__ void __launch_bounds__(kThreads, 2) blur_tile_kernel(const NmBlurArgs a, const __grid_constant__ CUtensorMap tmap)
 {
@@ -339,24 +276,7 @@ int launch_tile(const NmBlurArgs& a, cudaStream_t stream, const NmBlurTma* tma)
     }
     dim3 grid(nm_div_up(a.w, kTW), nm_div_up(a.h, kTH), a.batch);
     if (tma && tma->valid) {
-        static int n_sms = 0;
-        constexpr int psmem = blur_persist_smem_bytes(R);
-        if (n_sms == 0) {
-            int dev = 0;
-            NM_CUDA_TRY(cudaGetDevice(&dev));
-            NM_CUDA_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-        }
-        static bool pconfigured = false;
-        if (!pconfigured) {
-            NM_CUDA_TRY(cudaFuncSetAttribute(blur_persist_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem));
-            pconfigured = true;
-        }
-        const long long n_tiles = (long long)grid.x * grid.y * grid.z;
-        if (n_tiles >= 2LL * n_sms && n_tiles < (1LL << 31)) {
-            blur_persist_kernel<R><<<n_sms, kPThreads, psmem, stream>>>(a, tma->map, (int)grid.x, (int)grid.y, (int)n_tiles);
-        } else {
-            blur_tile_kernel<R, true><<<grid, kThreads, smem, stream>>>(a, tma->map);
-        }
+        blur_tile_kernel<R, true><<<grid, kThreads, smem, stream>>>(a, tma->map);
     } else {
         CUtensorMap dummy;
         memset(&dummy, 0, sizeof(dummy));
