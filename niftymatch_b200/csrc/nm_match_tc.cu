@@ -16,21 +16,24 @@
 //             three-term fp16 split, so the accumulator is directly the SCORE
 //                 S[a][b] = a^.b^ - |b^|^2/2        (maximise  <=>  minimise |a^-b^|^2)
 //             and the epilogue needs no per-column work besides a running maximum.
-//  2. scan:   one CTA per (256 query rows, database split).  Warp 0 streams B tiles through
-//             a 4-stage shared-memory ring (bulk copies, mbarrier completion); one thread of
-//             warp 1 issues tcgen05.mma (M=128, N=128, K=16, fp16 in / fp32 out) for the two
-//             128-row halves into double-buffered TMEM accumulators (4 x 128 columns = the
-//             whole 512-column TMEM); 8 epilogue warps read the accumulators with
-//             tcgen05.ld (one TMEM lane = one query row per thread) and keep the 4 best
-//             scores per row: FMNMX3 running maximum over 32 columns, and only when that
-//             beats the row's 4th-best score a (rare) insertion pass.
-//  3. rerank: one warp per query row gathers the <= 4 x splits candidates, evaluates the
-//             reference's exact fp32 distance for each, and takes the best two.  The row is
-//             CERTIFIED when the exact second distance is below a rigorous lower bound on
-//             the true distance of every non-candidate (fp16 rounding moves a point by at
-//             most 2^-11 of its norm); otherwise the row index is appended to
-//             a list and re-scanned by the exact fp32 engine (nm_match.cu).  Either way the
-//             record is exact, so match indices equal the reference's.
+//  2. scan:   one CTA (576 threads, 216 KB smem, all 512 TMEM columns) per (256 query rows, database
+//             split).  Warp 16 streams B tiles through a 4-stage shared-memory ring (bulk copies,
+//             mbarrier completion); one thread of warp 17 issues tcgen05.mma (M=128, N=128, K=16,
+//             fp16 in / fp32 out) for the two 128-row halves into double-buffered TMEM accumulators,
+//             handed over per (stage, half) with tcgen05.commit; 16 epilogue warps (one 64-column
+//             half of every tile each) read the accumulators with tcgen05.ld (one TMEM lane = one
+//             query row per thread) and keep the 4 best scores per row and list: FMNMX3 group
+//             maxima, warp-OR of the per-lane group masks, and only flagged 8-column groups are
+//             re-read from TMEM and inserted.  A SEED pass over the first 2048 database columns runs
+//             first; its 4 best per row start every list (a running top-k inserts at rate k/n).
+//  3. rerank: one warp per query row dedupes and ranks the <= 32 candidates by score, evaluates the
+//             reference's exact fp32 distance for the 4 best (up to 10 when needed), and takes the
+//             best two.  The row is CERTIFIED when the exact second distance is below a rigorous
+//             lower bound on the true distance of every non-candidate (the fp16 rounding
+//             displacement of both operands is measured, the fp32 accumulation error bounded;
+//             see DESIGN.md); otherwise the row index is appended to a list and re-scanned by the
+//             exact fp32 engine (nm_match.cu).  Either way the record is exact, so match indices
+//             equal the reference's.
 #include "nm_match.cuh"
 #include <cuda_fp16.h>
 #include <float.h>
