@@ -41,8 +41,9 @@ __global__ void __launch_bounds__(256, 4) extrema_grad_kernel(const NmOctave oc,
     const int f = blockIdx.z, x0 = blockIdx.x * EX_TW, y0 = blockIdx.y * EX_TH;
     const float* __restrict__ L = oc.levels + (long long)f * 6 * oc.level_elems;
 
-    for (int i = tid; i < (EX_TH + 2) * EX_P; i += 256) {
-        const int r = i / EX_P, c = i - r * EX_P;
+    // 34 x 34 tile incl. the 1-pixel halo, without div/mod: columns 0..31 by (warp row, lane), then the
+    // two right-hand halo columns by the first 68 threads
+    auto load_px = [&](int r, int c) {
         const int gy = y0 - 1 + r, gx = x0 - 1 + c;
         float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (gy >= 0 && gy < oc.h && gx >= 0 && gx < oc.w) {
@@ -53,7 +54,9 @@ __global__ void __launch_bounds__(256, 4) extrema_grad_kernel(const NmOctave oc,
 #pragma unroll
         for (int k = 0; k < 5; ++k) s_dog[k][r][c] = __fsub_rn(v[k + 1], v[k]);   // cudamath.cu:34
         s_lev[0][r][c] = v[1]; s_lev[1][r][c] = v[2]; s_lev[2][r][c] = v[3];
-    }
+    };
+    for (int r = threadIdx.y; r < EX_TH + 2; r += 8) load_px(r, threadIdx.x);
+    if (tid < 2 * (EX_TH + 2)) load_px(tid >> 1, 32 + (tid & 1));
     __syncthreads();
 
     const int lane = threadIdx.x;
