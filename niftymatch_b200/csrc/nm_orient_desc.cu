@@ -338,7 +338,12 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
 }
 
 // ---------------------- compat: flat keypoint lists (one octave) ----------------------
-__global__ void compat_fill_meta(int* meta, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) meta[i] = 0; }
+__global__ void compat_fill_meta(int* meta, int* count, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) meta[i] = 0;
+    if (i == 0) *count = n;
+}
 
 } // namespace
 
@@ -393,8 +398,7 @@ int compat_scratch(CompatScratch& sc, int n, cudaStream_t st)
 {
     NM_CUDA_TRY(cudaMallocAsync(&sc.counts, sizeof(int), st));
     NM_CUDA_TRY(cudaMallocAsync(&sc.meta, sizeof(int) * n, st));
-    NM_CUDA_TRY(cudaMemcpyAsync(sc.counts, &n, sizeof(int), cudaMemcpyHostToDevice, st));
-    compat_fill_meta<<<nm_div_up(n, 256), 256, 0, st>>>(sc.meta, n);
+    compat_fill_meta<<<nm_div_up(n, 256), 256, 0, st>>>(sc.meta, sc.counts, n);
     NM_LAUNCH_CHECK();
     return NM_OK;
 }
@@ -413,8 +417,6 @@ extern "C" int nm_orientations_f32(const float* kpts4, const float* grad2, int n
     if (rc == NM_OK)
         rc = nm_orient_launch(tab, 1, num_pts, sc.counts, reinterpret_cast<const float4*>(kpts4), sc.meta,
                               reinterpret_cast<float2*>(result2), st);
-    // the host int `n` passed to cudaMemcpyAsync lives on this frame: make sure it was consumed
-    cudaStreamSynchronize(st);
     if (sc.counts) cudaFreeAsync(sc.counts, st);
     if (sc.meta) cudaFreeAsync(sc.meta, st);
     return rc;
@@ -433,7 +435,6 @@ extern "C" int nm_descriptors_f32(const float* kpts4, const float* orient2, cons
     if (rc == NM_OK)
         rc = nm_describe_launch(tab, 1, num_pts, sc.counts, reinterpret_cast<const float4*>(kpts4), sc.meta,
                                 reinterpret_cast<const float2*>(orient2), desc, x, y, num_dogs, 0, st);
-    cudaStreamSynchronize(st);
     if (sc.counts) cudaFreeAsync(sc.counts, st);
     if (sc.meta) cudaFreeAsync(sc.meta, st);
     return rc;
