@@ -25,7 +25,8 @@ struct nm_sift_ctx {
         NmBlurTma lvl[NM_MAX_OCTAVES][5];   // source level i of octave o, box for radius radii[i+1]
     };
     std::vector<TmaSet*> tma_sets;
-    cudaStream_t s_in, s_out;            // nm_sift_run_host: H2D / D2H copy streams
+    cudaStream_t s_in, s_out, s_aux;     // nm_sift_run_host: H2D / D2H copy streams, second compute stream
+    cudaEvent_t ev_fork, ev_join;
     cudaEvent_t ev_in[NM_MAX_CHUNKS], ev_done[NM_MAX_CHUNKS], ev_out;
     float* taps[6];          // 0: base kernel, 1..5: level kernels (device)
     int    radii[6];
@@ -138,6 +139,9 @@ extern "C" int nm_sift_destroy(nm_sift_ctx* c)
     if (c->ev_out) cudaEventDestroy(c->ev_out);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
+    if (c->s_aux) cudaStreamDestroy(c->s_aux);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
     return NM_OK;
 }
@@ -158,7 +162,7 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
     c->P = P; c->B = max_batch; c->capacity = capacity; c->n_oct = P.num_octaves;
     c->scratch = nullptr; c->exact_desc = 0; c->last_launches = 0; c->timing = 0;
     for (int i = 0; i < 6; ++i) c->ev[i] = nullptr;
-    c->s_in = c->s_out = nullptr; c->ev_out = nullptr;
+    c->s_in = c->s_out = c->s_aux = nullptr; c->ev_out = c->ev_fork = c->ev_join = nullptr;
     for (int i = 0; i < NM_MAX_CHUNKS; ++i) c->ev_in[i] = c->ev_done[i] = nullptr;
     int rc = NM_OK;
     // Gaussian kernels
@@ -207,6 +211,9 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
         if (cudaEventCreate(&c->ev[i]) != cudaSuccess) rc = NM_ERR_ALLOC;
     if (rc == NM_OK && (cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) != cudaSuccess ||
                         cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) != cudaSuccess ||
+                        cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking) != cudaSuccess ||
+                        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
                         cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess))
         rc = NM_ERR_ALLOC;
     for (int i = 0; i < NM_MAX_CHUNKS && rc == NM_OK; ++i)
@@ -376,19 +383,26 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
                                     cudaMemcpyHostToDevice, c->s_in));
         NM_CUDA_TRY(cudaEventRecord(c->ev_in[k], c->s_in));
     }
+    // stages alternate between the caller's stream and a second one (forked from it): the launch-bound
+    // tail of one stage (small octaves, orientation) overlaps the big blur kernels of the next
+    NM_CUDA_TRY(cudaEventRecord(c->ev_fork, st));
+    NM_CUDA_TRY(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
     for (int k = 0; k < n_chunks; ++k) {
         const int f0 = bounds[k], n = bounds[k + 1] - bounds[k];
-        NM_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_in[k], 0));
-        int rc = sift_run_range(c, c->frames_stage + f0 * fpix, f0, n, st, false);
+        cudaStream_t sk = (k & 1) ? c->s_aux : st;
+        NM_CUDA_TRY(cudaStreamWaitEvent(sk, c->ev_in[k], 0));
+        int rc = sift_run_range(c, c->frames_stage + f0 * fpix, f0, n, sk, false);
         if (rc != NM_OK) return rc;
         launches += c->last_launches;
-        NM_CUDA_TRY(cudaMemcpyAsync(counts_host + f0, c->counts + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-        NM_CUDA_TRY(cudaEventRecord(c->ev_done[k], st));
+        NM_CUDA_TRY(cudaMemcpyAsync(counts_host + f0, c->counts + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, sk));
+        NM_CUDA_TRY(cudaEventRecord(c->ev_done[k], sk));
         if (k > 0 && (rc = drain(k - 1)) != NM_OK) return rc;
     }
     int rc = drain(n_chunks - 1);
     if (rc != NM_OK) return rc;
-    // the caller's stream is complete when the result copies are
+    // the caller's stream is complete when both compute streams and the result copies are
+    NM_CUDA_TRY(cudaEventRecord(c->ev_join, c->s_aux));
+    NM_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));
     NM_CUDA_TRY(cudaEventRecord(c->ev_out, c->s_out));
     NM_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_out, 0));
     NM_CUDA_TRY(cudaStreamSynchronize(st));
