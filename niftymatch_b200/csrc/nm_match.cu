@@ -399,7 +399,10 @@ extern "C" int nm_match_top2_f32(const float* A, int nA, const float* B, int nB,
 {
     if (!A || !rec4 || nA <= 0 || nB < 0 || (nB > 0 && !B)) return NM_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    if (nB > 0 && pick_engine((long long)nA * nB) == 1)
+    // the tensor-core engine reads rows with 16-byte loads; unaligned inputs take the exact engine
+    // (both return the same records)
+    const bool aligned = !((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15);
+    if (nB > 0 && aligned && pick_engine((long long)nA * nB) == 1)
         return nm_match_scan_tc(A, nA, B, nB, index_offset, reinterpret_cast<float4*>(rec4), st);
     return nm_match_scan_exact(A, 128, 1, nA, B, nB, 128, index_offset, reinterpret_cast<float4*>(rec4), nullptr, 0, 0, st);
 }
@@ -419,7 +422,8 @@ extern "C" int nm_match_f32(const float* A, int nA, const float* B, int nB, floa
     float4* rec = nullptr;
     NM_CUDA_TRY(cudaMallocAsync(&rec, sizeof(float4) * (size_t)nA, st));
     int rc;
-    if (distance || pick_engine((long long)nA * nB) == 0)
+    const bool aligned = !((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15);
+    if (distance || !aligned || pick_engine((long long)nA * nB) == 0)
         rc = nm_match_scan_exact(A, 128, 1, nA, B, nB, 128, 0, rec, distance, nB, 1, st);
     else
         rc = nm_match_scan_tc(A, nA, B, nB, 0, rec, st);

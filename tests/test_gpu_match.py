@@ -263,3 +263,20 @@ def test_full_size_100k_engines_agree_and_planted_rows_match(nm):
     ss = np.fromiter(last.values(), dtype=np.int64)
     hit = mm[rr] == ss
     assert hit.mean() > 0.999, hit.mean()
+
+
+def test_unaligned_descriptor_pointers(nm, oracle):
+    """Descriptor blocks that start at a 4-byte (not 16-byte) aligned address, e.g. a slice of a larger
+    buffer: the call must still succeed (exact engine) and agree with the oracle."""
+    B = synth.descriptors(2500, 51)
+    A = synth.descriptors(2000, 52, planted_from=B)
+    bufA = torch.zeros(A.size + 1, dtype=torch.float32, device="cuda")
+    bufB = torch.zeros(B.size + 1, dtype=torch.float32, device="cuda")
+    bufA[1:] = _cu(A).reshape(-1)
+    bufB[1:] = _cu(B).reshape(-1)
+    At, Bt = bufA[1:].view(2000, 128), bufB[1:].view(2500, 128)
+    assert At.data_ptr() % 16 == 4
+    nm.set_engine(1) if 1 in _engines(nm) else None
+    m = nm.match(At, Bt, 0.8).cpu().numpy()
+    nm.set_engine(-1)
+    assert np.array_equal(m, oracle.match(A, B, 0.8))
