@@ -178,6 +178,56 @@ __device__ __forceinline__ void blur_col_pass(const float* __restrict__ s_row, c
     }
 }
 
+// Persistent variant for TMA-describable sources: two CTAs per SM walk the tiles of the launch.  The
+// staged window is dead once the row pass has consumed it, so the TMA load of the CTA's NEXT tile is
+// issued right after the row pass and lands while the column pass runs -- no second window needed.
+template <int R>
+__global__ void __launch_bounds__(kThreads, 2) blur_walk_kernel(const NmBlurArgs a, const __grid_constant__ CUtensorMap tmap,
+                                                                int tiles_x, int tiles_y, int n_tiles)
+{
+    constexpr int IH = kTH + 2 * R, RA = radius_aligned(R), IP = in_pitch(R), NT = 2 * R + 1;
+    extern __shared__ __align__(128) float smem[];
+    float* s_in = smem;
+    float* s_row = smem + IH * IP;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_row + IH * kRowPitch);
+    const int tid = threadIdx.x;
+    auto tile_pos = [&](int tile, int& x0, int& y0, int& f) {
+        const int tx = tile % tiles_x, r = tile / tiles_x;
+        x0 = tx * kTW; y0 = (r % tiles_y) * kTH; f = r / tiles_y;
+    };
+    int tile = blockIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (tile < n_tiles) {
+            int x0, y0, f;
+            tile_pos(tile, x0, y0, f);
+            mbar_expect_tx(bar, IH * IP * (uint32_t)sizeof(float));
+            tma_load_3d(s_in, &tmap, bar, x0 - RA, y0 - R, f);
+        }
+    }
+    float t[NT];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) t[k] = __ldg(a.taps + k);
+    __syncthreads();                           // barrier initialised before anyone polls it
+    for (int k = 0; tile < n_tiles; ++k, tile += gridDim.x) {
+        int x0, y0, f;
+        tile_pos(tile, x0, y0, f);
+        mbar_wait(bar, k & 1);
+        blur_row_pass<R, kThreads>(s_in, s_row, t, tid);
+        __syncthreads();                       // every thread is done with the window
+        const int next = tile + gridDim.x;
+        if (tid == 0 && next < n_tiles) {
+            int nx0, ny0, nf;
+            tile_pos(next, nx0, ny0, nf);
+            mbar_expect_tx(bar, IH * IP * (uint32_t)sizeof(float));
+            tma_load_3d(s_in, &tmap, bar, nx0 - RA, ny0 - R, nf);
+        }
+        blur_col_pass<R, kThreads>(s_row, a, t, tid, x0, y0, f);
+        __syncthreads();                       // s_row is rewritten by the next row pass
+    }
+}
+
 template <int R, bool TMA>
 __global__ void __launch_bounds__(kThreads, 2) blur_tile_kernel(const NmBlurArgs a, const __grid_constant__ CUtensorMap tmap)
 {
@@ -276,7 +326,19 @@ int launch_tile(const NmBlurArgs& a, cudaStream_t stream, const NmBlurTma* tma)
     }
     dim3 grid(nm_div_up(a.w, kTW), nm_div_up(a.h, kTH), a.batch);
     if (tma && tma->valid) {
-        blur_tile_kernel<R, true><<<grid, kThreads, smem, stream>>>(a, tma->map);
+        static int n_sms = 0;
+        if (n_sms == 0) {
+            int dev = 0;
+            NM_CUDA_TRY(cudaGetDevice(&dev));
+            NM_CUDA_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+            NM_CUDA_TRY(cudaFuncSetAttribute(blur_walk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        }
+        const long long n_tiles = (long long)grid.x * grid.y * grid.z;
+        static const bool no_walk = getenv("NM_BLUR_TILE") != nullptr;        // tuning aid
+        if (!no_walk && n_tiles >= 4LL * n_sms && n_tiles < (1LL << 31))
+            blur_walk_kernel<R><<<2 * n_sms, kThreads, smem, stream>>>(a, tma->map, (int)grid.x, (int)grid.y, (int)n_tiles);
+        else
+            blur_tile_kernel<R, true><<<grid, kThreads, smem, stream>>>(a, tma->map);
     } else {
         CUtensorMap dummy;
         memset(&dummy, 0, sizeof(dummy));
