@@ -33,6 +33,11 @@ const char* nm_strerror(int code);
 int nm_device_cc(void);
 const char* nm_version(void);
 
+/* Self-test: compares the gradient kernels' atan2 (the CUDA library's main path without its
+ * special-case prologue) bit for bit with atan2f on n generated argument pairs (finite, not both
+ * zero: the only arguments the gradient produces); *mismatches_host must come back 0. */
+int nm_selftest_atan2(long long n, unsigned seed, long long* mismatches_host);
+
 /* ------------------------------------------------------------------------ */
 /* Parameters: mirror of class SiftParams (gpu/sift/siftparams.h:14-99).     */
 /* ------------------------------------------------------------------------ */

@@ -448,6 +448,59 @@ int nm_downsample_launch(float* dst, int dw, int dh, int dpitch, long long dfstr
     return NM_OK;
 }
 
+// Self-test of nm_atan2f_finite against the library atan2f (see nm_common.cuh).
+namespace {
+__device__ __forceinline__ unsigned st_hash(unsigned long long v)
+{
+    v ^= v >> 33; v *= 0xff51afd7ed558ccdULL; v ^= v >> 33; v *= 0xc4ceb9fe1a85ec53ULL; v ^= v >> 33;
+    return (unsigned)v;
+}
+// argument generator: random sign, log-uniform magnitude over 2^-60 .. 2^20, or special patterns
+__device__ __forceinline__ float st_value(unsigned h, unsigned mode)
+{
+    const float mant = 1.0f + (float)(h & 0x7fffff) * (1.0f / 8388608.0f);
+    const int e = (int)((h >> 23) & 0x7f) * 80 / 128 - 60;
+    float v = ldexpf(mant, e);
+    if (mode == 1) v = (float)((int)(h & 0x3ff) - 512) * 0.25f;         // quarter-integer pixel differences
+    if (mode == 2) v = 0.0f;
+    if (mode == 3) v = -0.0f;
+    if (mode == 4) v = ldexpf(mant, -140);                                // subnormal
+    return (h >> 31) ? -v : v;
+}
+__global__ void atan2_selftest_kernel(long long n, unsigned seed, unsigned long long* mismatches)
+{
+    unsigned long long bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned h0 = st_hash(((unsigned long long)seed << 40) ^ (unsigned long long)i);
+        const unsigned h1 = st_hash(((unsigned long long)seed << 40) ^ (unsigned long long)i ^ 0x9e3779b97f4a7c15ULL);
+        const unsigned sel = st_hash(h0 ^ 0x5bd1e995u) & 31;
+        const unsigned my = sel < 20 ? 0 : sel < 24 ? 1 : sel == 24 ? 2 : sel == 25 ? 3 : sel < 28 ? 4 : 0;
+        unsigned mxm = (sel == 28) ? 2 : (sel == 29) ? 3 : (sel == 30 ? 4 : (sel >= 20 && sel < 24 ? 1 : 0));
+        float y = st_value(h0, my), x = st_value(h1, mxm);
+        if (sel == 31) x = (h1 & 1) ? y : -y;                              // |x| == |y|
+        if (y == 0.0f && x == 0.0f) continue;                              // excluded by the caller contract
+        const float a = atan2f(y, x), b = nm_atan2f_finite(y, x);
+        if (__float_as_uint(a) != __float_as_uint(b)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+} // namespace
+
+extern "C" int nm_selftest_atan2(long long n, unsigned seed, long long* mismatches_host)
+{
+    if (n <= 0 || !mismatches_host) return NM_ERR_INVALID;
+    unsigned long long* d = nullptr;
+    NM_CUDA_TRY(cudaMalloc(&d, sizeof(*d)));
+    cudaMemset(d, 0, sizeof(*d));
+    atan2_selftest_kernel<<<148 * 8, 256>>>(n, seed, d);
+    cudaError_t e = cudaGetLastError();
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    *mismatches_host = (long long)h;
+    return nm_cuda_err(e);
+}
+
 // ---------------------------------------------------------------------------
 // C-ABI
 // ---------------------------------------------------------------------------
