@@ -33,10 +33,11 @@ const char* nm_strerror(int code);
 int nm_device_cc(void);
 const char* nm_version(void);
 
-/* Self-test: compares the gradient kernels' atan2 (the CUDA library's main path without its
- * special-case prologue) bit for bit with atan2f on n generated argument pairs (finite, not both
- * zero: the only arguments the gradient produces); *mismatches_host must come back 0. */
-int nm_selftest_atan2(long long n, unsigned seed, long long* mismatches_host);
+/* Self-test: compares the gradient kernels' arithmetic (the CUDA math library's main paths of sqrtf,
+ * IEEE division and atan2f inlined behind one range test) bit for bit with the expression on the
+ * library routines themselves (gpu/kernels/cudamath.cu:47-52) on n generated (dx, dy) pairs;
+ * *mismatches_host must come back 0. */
+int nm_selftest_gradient(long long n, unsigned seed, long long* mismatches_host);
 
 /* ------------------------------------------------------------------------ */
 /* Parameters: mirror of class SiftParams (gpu/sift/siftparams.h:14-99).     */

@@ -40,7 +40,7 @@ SIGNATURES = {
     "nm_strerror": (C.c_char_p, [_i]),
     "nm_device_cc": (_i, []),
     "nm_version": (C.c_char_p, []),
-    "nm_selftest_atan2": (_i, [C.c_longlong, C.c_uint, C.POINTER(C.c_longlong)]),
+    "nm_selftest_gradient": (_i, [C.c_longlong, C.c_uint, C.POINTER(C.c_longlong)]),
     "nm_sift_params_init": (_i, [C.POINTER(SiftParamsC), _i, _i]),
     "nm_gaussian_taps": (_i, [_f, _vp, C.POINTER(_i)]),
     "nm_blur_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp]),

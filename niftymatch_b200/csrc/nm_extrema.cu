@@ -19,45 +19,74 @@
 // keypoint at its final slot.  No dense float4 maps (16 B/pixel/level in the reference),
 // no thrust::fill, no device->host count round trips.
 #include "nm_sift_internal.cuh"
+#include "nm_pyramid.cuh"
 #include "nm_refine.cuh"
+#include <cstdlib>
 
 namespace {
 
-constexpr int EX_TW = 32, EX_TH = 32, EX_P = EX_TW + 2;
+// 34 rows x 40 columns per level: tile column 0 sits at window column EX_HL = 4, because the innermost
+// TMA coordinate has to stay 16-byte aligned (x0 - 4, not x0 - 1; unaligned starts raise an illegal-instruction fault)
+constexpr int EX_TW = 32, EX_TH = 32, EX_HL = 4, EX_P = EX_TW + 2 * EX_HL, EX_ROWS = EX_TH + 2;
+constexpr uint32_t EX_TILE_BYTES = 6u * EX_ROWS * EX_P * sizeof(float);   // 32 640
 
 struct SmemDogFetch {
-    const float (*dog)[EX_TH + 2][EX_P];   // [5]
+    const float (*dog)[EX_ROWS][EX_P];     // [5]
     int l, r, c;                           // detection level (0..2), tile row/col of the centre
     __device__ __forceinline__ float cur(int dx, int dy) const { return dog[l + 1][r + dy][c + dx]; }
     __device__ __forceinline__ float down(int dx, int dy) const { return dog[l][r + dy][c + dx]; }
     __device__ __forceinline__ float up(int dx, int dy) const { return dog[l + 2][r + dy][c + dx]; }
 };
 
-__global__ void __launch_bounds__(256, 4) extrema_grad_kernel(const NmOctave oc, const NmDetectParams dp)
+__device__ __forceinline__ uint32_t ex_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// One CTA = one 32 x 32 pixel tile of one frame.  The six Gaussian levels of the 34 x 36 window (1-pixel
+// halo; 40 columns keep the window start 16-byte aligned) arrive by ONE bulk tensor load (x, y, level) with hardware
+// zero fill outside the image.  Phase 1 turns levels 1..3 into the three gradient maps; phase 2 replaces the
+// window in place by the five DoG levels (cudamath.cu:34); phase 3 is the 26-neighbour test, the refinement
+// and the 1-bit-per-pixel result.
+template <bool TMA>
+__global__ void __launch_bounds__(256, 4) extrema_grad_kernel(const NmOctave oc, const NmDetectParams dp,
+                                                              const __grid_constant__ CUtensorMap tmap)
 {
-    __shared__ float s_dog[5][EX_TH + 2][EX_P];
-    __shared__ float s_lev[3][EX_TH + 2][EX_P];
+    __shared__ __align__(128) float s_tile[6][EX_ROWS][EX_P];
+    __shared__ __align__(8) uint64_t s_bar;
     const int tid = threadIdx.y * 32 + threadIdx.x;
     const int f = blockIdx.z, x0 = blockIdx.x * EX_TW, y0 = blockIdx.y * EX_TH;
-    const float* __restrict__ L = oc.levels + (long long)f * 6 * oc.level_elems;
 
-    // 34 x 34 tile incl. the 1-pixel halo, without div/mod: columns 0..31 by (warp row, lane), then the
-    // two right-hand halo columns by the first 68 threads
-    auto load_px = [&](int r, int c) {
-        const int gy = y0 - 1 + r, gx = x0 - 1 + c;
-        float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (gy >= 0 && gy < oc.h && gx >= 0 && gx < oc.w) {
-            const float* p = L + (long long)gy * oc.pitch + gx;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) v[k] = __ldg(p + k * oc.level_elems);
+    if (TMA) {
+        if (tid == 0) {
+            const uint32_t bar = ex_smem_u32(&s_bar);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(EX_TILE_BYTES) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"(ex_smem_u32(&s_tile[0][0][0])), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x0 - EX_HL), "r"(y0 - 1),
+                  "r"(f * 6), "r"(bar) : "memory");
         }
+        __syncthreads();                                   // barrier initialised before anyone polls it
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "LAB_WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+            "@p bra LAB_DONE_%=;\n"
+            "bra LAB_WAIT_%=;\n"
+            "LAB_DONE_%=:\n"
+            "}\n" ::"r"(ex_smem_u32(&s_bar)) : "memory");
+    } else {
+        const float* __restrict__ L = oc.levels + (long long)f * 6 * oc.level_elems;
+        for (int i = tid; i < EX_ROWS * EX_P; i += 256) {
+            const int r = i / EX_P, c = i - r * EX_P;
+            const int gy = y0 - 1 + r, gx = x0 - EX_HL + c;
+            const bool in = gy >= 0 && gy < oc.h && gx >= 0 && gx < oc.w;
 #pragma unroll
-        for (int k = 0; k < 5; ++k) s_dog[k][r][c] = __fsub_rn(v[k + 1], v[k]);   // cudamath.cu:34
-        s_lev[0][r][c] = v[1]; s_lev[1][r][c] = v[2]; s_lev[2][r][c] = v[3];
-    };
-    for (int r = threadIdx.y; r < EX_TH + 2; r += 8) load_px(r, threadIdx.x);
-    if (tid < 2 * (EX_TH + 2)) load_px(tid >> 1, 32 + (tid & 1));
-    __syncthreads();
+            for (int k = 0; k < 6; ++k)
+                s_tile[k][r][c] = in ? __ldg(L + k * oc.level_elems + (long long)gy * oc.pitch + gx) : 0.f;
+        }
+        __syncthreads();
+    }
 
     const int lane = threadIdx.x;
     const int gx = x0 + lane;
@@ -65,14 +94,51 @@ __global__ void __launch_bounds__(256, 4) extrema_grad_kernel(const NmOctave oc,
     const long long bm_words = (long long)oc.h * oc.wpr;
     uint32_t* __restrict__ BM = oc.bitmap + (long long)f * 3 * bm_words;
 
-    // ---- 26-neighbour extremum test for the thread's 4 pixels x 3 levels, separably -----------
+    // ---- phase 1: gradient maps of levels 1..3 (cudamath.cu:38-54; border pixels = (0, 0)) ----------
+    {
+        const bool inx = gx < oc.w, intx = gx >= 1 && gx <= oc.w - 2;
+        const int c = lane + EX_HL;
+#pragma unroll 1
+        for (int i = 0; i < EX_TH / 8; ++i) {
+            const int ly = threadIdx.y * (EX_TH / 8) + i, gy = y0 + ly, r = ly + 1;
+            if (gy >= oc.h) break;                              // warp uniform
+            const bool interior = intx && gy >= 1 && gy <= oc.h - 2;
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                float2 g = make_float2(0.f, 0.f);
+                if (interior)
+                    g = nm_gradient_at(s_tile[l + 1][r][c + 1], s_tile[l + 1][r][c - 1], s_tile[l + 1][r + 1][c], s_tile[l + 1][r - 1][c]);
+                if (inx) G[l * oc.level_elems + (long long)gy * oc.pitch + gx] = g;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: levels -> DoG in place: slot k = level k+1 - level k (k = 0..4), four columns per item ----
+    {
+        float4 (*t4)[EX_ROWS][EX_P / 4] = reinterpret_cast<float4 (*)[EX_ROWS][EX_P / 4]>(s_tile);
+        for (int i = tid; i < EX_ROWS * (EX_P / 4); i += 256) {
+            const int r = i / (EX_P / 4), q = i - r * (EX_P / 4);
+            float4 v[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) v[k] = t4[k][r][q];
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+                t4[k][r][q] = make_float4(__fsub_rn(v[k + 1].x, v[k].x), __fsub_rn(v[k + 1].y, v[k].y),
+                                          __fsub_rn(v[k + 1].z, v[k].z), __fsub_rn(v[k + 1].w, v[k].w));
+        }
+    }
+    __syncthreads();
+    const float (*s_dog)[EX_ROWS][EX_P] = s_tile;
+
+    // ---- phase 3: 26-neighbour extremum test for the thread's 4 pixels x 3 levels, separably --------
     // 3-wide row maxima / minima of every DoG level (with and without the centre column) are shared
     // by the vertically adjacent pixels of the thread, so a pixel costs ~46 FMNMX3 + 23 LDS instead of
-    // 78 + 81 (the kernel is issue bound: ncu 84 % issue slots busy).  Same comparisons as
-    // keypoint.cu:19-105: strict, against the max / min of the 26 neighbours.
+    // 78 + 81 (the kernel is issue bound).  Same comparisons as keypoint.cu:19-105: strict, against the
+    // max / min of the 26 neighbours.
     unsigned extmask = 0;                      // bit l * 4 + i
     {
-        const int c = lane + 1, rbase = threadIdx.y * (EX_TH / 8);      // tile row of the first pixel's upper neighbour
+        const int c = lane + EX_HL, rbase = threadIdx.y * (EX_TH / 8);      // tile row of the first pixel's upper neighbour
         const float t = __fmul_rn(0.8f, dp.peak);
         // levels are walked bottom-up with a 3-deep window of the 3x3 (centre included) maxima, so that
         // detection level l = k - 2 is decided as soon as DoG level k is reduced (keeps ~50 values live)
@@ -117,16 +183,8 @@ __global__ void __launch_bounds__(256, 4) extrema_grad_kernel(const NmOctave oc,
         const int ly = threadIdx.y * (EX_TH / 8) + i;
         const int gy = y0 + ly;
         if (gy >= oc.h) break;                                  // warp uniform
-        const bool inx = gx < oc.w;
         const bool interior = gx >= 1 && gx <= oc.w - 2 && gy >= 1 && gy <= oc.h - 2;
-        const int r = ly + 1, c = lane + 1;
-#pragma unroll
-        for (int l = 0; l < 3; ++l) {
-            float2 g = make_float2(0.f, 0.f);
-            if (interior)
-                g = nm_gradient_at(s_lev[l][r][c + 1], s_lev[l][r][c - 1], s_lev[l][r + 1][c], s_lev[l][r - 1][c]);
-            if (inx) G[l * oc.level_elems + (long long)gy * oc.pitch + gx] = g;
-        }
+        const int r = ly + 1, c = lane + EX_HL;
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
             bool acc = false;
@@ -367,10 +425,26 @@ __global__ void __launch_bounds__(256) collate_write_kernel(const float4* __rest
 
 } // namespace
 
-int nm_extrema_launch(const NmOctave& oc, int, int, const NmDetectParams& dp, int batch, cudaStream_t stream)
+bool nm_extrema_make_tma(NmBlurTma* t, const NmOctave& oc, int batch)
+{
+    // (x, y, level of frame): 6 * batch planes of h rows
+    const unsigned long long dims[3] = {(unsigned long long)oc.w, (unsigned long long)oc.h, 6ull * batch};
+    const unsigned long long strides[2] = {(unsigned long long)oc.pitch * 4, (unsigned long long)oc.level_elems * 4};
+    const unsigned box[3] = {EX_P, EX_ROWS, 6};
+    return nm_tma_encode_3d(t, oc.levels, dims, strides, box);
+}
+
+int nm_extrema_launch(const NmOctave& oc, int, int, const NmDetectParams& dp, int batch, cudaStream_t stream,
+                      const NmBlurTma* tma)
 {
     dim3 block(32, 8), grid(nm_div_up(oc.w, EX_TW), nm_div_up(oc.h, EX_TH), batch);
-    extrema_grad_kernel<<<grid, block, 0, stream>>>(oc, dp);
+    static const bool no_tma = getenv("NM_EXTREMA_NO_TMA") != nullptr;     // development aid
+    if (tma && tma->valid && !no_tma) {
+        extrema_grad_kernel<true><<<grid, block, 0, stream>>>(oc, dp, tma->map);
+    } else {
+        CUtensorMap none{};
+        extrema_grad_kernel<false><<<grid, block, 0, stream>>>(oc, dp, none);
+    }
     NM_LAUNCH_CHECK();
     return NM_OK;
 }

@@ -398,6 +398,24 @@ __global__ void gradient_kernel(const float* __restrict__ src, float2* __restric
 
 } // namespace
 
+bool nm_tma_encode_3d(NmBlurTma* t, const float* base, const unsigned long long dims[3],
+                      const unsigned long long strides_bytes[2], const unsigned box[3])
+{
+    t->valid = false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides_bytes[0] & 15) || (strides_bytes[1] & 15)) return false;
+    EncodeTiledFn enc = get_encoder();
+    if (!enc) return false;
+    const cuuint64_t d[3] = {dims[0], dims[1], dims[2]};
+    const cuuint64_t st[2] = {strides_bytes[0], strides_bytes[1]};
+    const cuuint32_t bx[3] = {box[0], box[1], box[2]};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&t->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), d, st, bx, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    t->valid = (r == CUDA_SUCCESS);
+    return t->valid;
+}
+
 bool nm_blur_make_tma(NmBlurTma* t, const float* src, int w, int h, int pitch, long long fstride,
                       int batch, int radius)
 {
@@ -448,51 +466,53 @@ int nm_downsample_launch(float* dst, int dw, int dh, int dpitch, long long dfstr
     return NM_OK;
 }
 
-// Self-test of nm_atan2f_finite against the library atan2f (see nm_common.cuh).
+// Self-test of nm_gradient_from_diff against the library-routine expression (see nm_common.cuh).
 namespace {
 __device__ __forceinline__ unsigned st_hash(unsigned long long v)
 {
     v ^= v >> 33; v *= 0xff51afd7ed558ccdULL; v ^= v >> 33; v *= 0xc4ceb9fe1a85ec53ULL; v ^= v >> 33;
     return (unsigned)v;
 }
-// argument generator: random sign, log-uniform magnitude over 2^-60 .. 2^20, or special patterns
+// argument generator: random sign; log-uniform magnitude over 2^-70 .. 2^66, or special patterns
 __device__ __forceinline__ float st_value(unsigned h, unsigned mode)
 {
     const float mant = 1.0f + (float)(h & 0x7fffff) * (1.0f / 8388608.0f);
-    const int e = (int)((h >> 23) & 0x7f) * 80 / 128 - 60;
+    const int e = (int)((h >> 23) & 0xff) * 136 / 256 - 70;
     float v = ldexpf(mant, e);
     if (mode == 1) v = (float)((int)(h & 0x3ff) - 512) * 0.25f;         // quarter-integer pixel differences
     if (mode == 2) v = 0.0f;
-    if (mode == 3) v = -0.0f;
+    if (mode == 3) v = ldexpf(mant, (int)((h >> 23) & 0x1f) - 16);        // image-scale magnitudes 2^-16 .. 2^15
     if (mode == 4) v = ldexpf(mant, -140);                                // subnormal
     return (h >> 31) ? -v : v;
 }
-__global__ void atan2_selftest_kernel(long long n, unsigned seed, unsigned long long* mismatches)
+__global__ void gradient_selftest_kernel(long long n, unsigned seed, unsigned long long* mismatches)
 {
     unsigned long long bad = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const unsigned h0 = st_hash(((unsigned long long)seed << 40) ^ (unsigned long long)i);
         const unsigned h1 = st_hash(((unsigned long long)seed << 40) ^ (unsigned long long)i ^ 0x9e3779b97f4a7c15ULL);
         const unsigned sel = st_hash(h0 ^ 0x5bd1e995u) & 31;
-        const unsigned my = sel < 20 ? 0 : sel < 24 ? 1 : sel == 24 ? 2 : sel == 25 ? 3 : sel < 28 ? 4 : 0;
-        unsigned mxm = (sel == 28) ? 2 : (sel == 29) ? 3 : (sel == 30 ? 4 : (sel >= 20 && sel < 24 ? 1 : 0));
-        float y = st_value(h0, my), x = st_value(h1, mxm);
-        if (sel == 31) x = (h1 & 1) ? y : -y;                              // |x| == |y|
-        if (y == 0.0f && x == 0.0f) continue;                              // excluded by the caller contract
-        const float a = atan2f(y, x), b = nm_atan2f_finite(y, x);
-        if (__float_as_uint(a) != __float_as_uint(b)) ++bad;
+        // 0..7 wide range both, 8..19 image scale both, 20..23 quarter integers, 24/25 one zero,
+        // 26/27 one subnormal, 28 wide x image scale, 29 both zero, 30 |dx| == |dy|, 31 image scale vs tiny
+        unsigned my = sel < 8 ? 0 : sel < 20 ? 3 : sel < 24 ? 1 : sel == 24 ? 2 : sel == 26 ? 4 : sel == 29 ? 2 : 3;
+        unsigned mxm = sel < 8 ? 0 : sel < 20 ? 3 : sel < 24 ? 1 : sel == 25 ? 2 : sel == 27 ? 4 : sel == 29 ? 2 : sel == 28 ? 0 : 3;
+        float dy = st_value(h0, my), dx = st_value(h1, mxm);
+        if (sel == 30) dx = (h1 & 1) ? dy : -dy;
+        if (sel == 31) dx = ldexpf(dx, -70);
+        const float2 a = nm_gradient_lib(dx, dy), b = nm_gradient_from_diff(dx, dy);
+        if (__float_as_uint(a.x) != __float_as_uint(b.x) || __float_as_uint(a.y) != __float_as_uint(b.y)) ++bad;
     }
     if (bad) atomicAdd(mismatches, bad);
 }
 } // namespace
 
-extern "C" int nm_selftest_atan2(long long n, unsigned seed, long long* mismatches_host)
+extern "C" int nm_selftest_gradient(long long n, unsigned seed, long long* mismatches_host)
 {
     if (n <= 0 || !mismatches_host) return NM_ERR_INVALID;
     unsigned long long* d = nullptr;
     NM_CUDA_TRY(cudaMalloc(&d, sizeof(*d)));
     cudaMemset(d, 0, sizeof(*d));
-    atan2_selftest_kernel<<<148 * 8, 256>>>(n, seed, d);
+    gradient_selftest_kernel<<<148 * 8, 256>>>(n, seed, d);
     cudaError_t e = cudaGetLastError();
     unsigned long long h = 0;
     if (e == cudaSuccess) e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);

@@ -26,6 +26,10 @@ struct NmBlurTma {
 bool nm_blur_make_tma(NmBlurTma* t, const float* src, int w, int h, int pitch, long long fstride,
                       int batch, int radius);
 
+// Generic 3-D fp32 tiled descriptor (no swizzle, zero fill outside the tensor); false if it cannot be encoded.
+bool nm_tma_encode_3d(NmBlurTma* t, const float* base, const unsigned long long dims[3],
+                      const unsigned long long strides_bytes[2], const unsigned box[3]);
+
 // Fused separable blur (rows then columns, zero padding, reference order of operations).
 int nm_blur_launch(const NmBlurArgs& a, cudaStream_t stream, const NmBlurTma* tma = nullptr);
 

@@ -23,6 +23,7 @@ struct nm_sift_ctx {
     struct TmaSet {          // TMA descriptors of the internal levels for frames [first, first + n)
         int first, n;
         NmBlurTma lvl[NM_MAX_OCTAVES][5];   // source level i of octave o, box for radius radii[i+1]
+        NmBlurTma ex[NM_MAX_OCTAVES];       // the six levels of octave o, box of the extrema kernel
     };
     std::vector<TmaSet*> tma_sets;
     cudaStream_t s_in, s_out, s_aux;     // nm_sift_run_host: H2D / D2H copy streams, second compute stream
@@ -266,6 +267,7 @@ static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, in
             for (int i = 0; i < 5; ++i)
                 nm_blur_make_tma(&ts->lvl[o][i], oc.levels + i * oc.level_elems, oc.w, oc.h, oc.pitch,
                                  6 * oc.level_elems, n, c->radii[i + 1]);
+            nm_extrema_make_tma(&ts->ex[o], oc, n);
         }
         c->tma_sets.push_back(ts);
     }
@@ -301,7 +303,7 @@ static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, in
     if (timing) cudaEventRecord(c->ev[1], st);
     // ---- DoG + extrema + refinement + gradients ----------------------------------
     for (int o = 0; o < c->n_oct; ++o) {
-        if ((rc = nm_extrema_launch(tab.o[o], o, c->n_oct, dp, n, st)) != NM_OK) return rc;
+        if ((rc = nm_extrema_launch(tab.o[o], o, c->n_oct, dp, n, st, &ts->ex[o])) != NM_OK) return rc;
         ++launches;
     }
     if (timing) cudaEventRecord(c->ev[2], st);
@@ -365,6 +367,14 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
     }
     if (n_chunks > NM_MAX_CHUNKS) return NM_ERR_INVALID;
     int launches = 0;
+    // NM_HOST_TRACE=1: device timeline of the stages on stderr (development aid)
+    static const bool trace = getenv("NM_HOST_TRACE") != nullptr;
+    cudaEvent_t tr0 = nullptr, tr_in[NM_MAX_CHUNKS], tr_k0[NM_MAX_CHUNKS], tr_k1[NM_MAX_CHUNKS], tr_out[NM_MAX_CHUNKS];
+    if (trace) {
+        cudaEventCreate(&tr0);
+        for (int k = 0; k < n_chunks; ++k) { cudaEventCreate(&tr_in[k]); cudaEventCreate(&tr_k0[k]); cudaEventCreate(&tr_k1[k]); cudaEventCreate(&tr_out[k]); }
+        cudaEventRecord(tr0, c->s_in);
+    }
     auto drain = [&](int k) -> int {
         // results of chunk k: wait for its counts, then copy the filled part of every frame
         NM_CUDA_TRY(cudaEventSynchronize(c->ev_done[k]));
@@ -375,6 +385,7 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
             if (x_host) NM_CUDA_TRY(cudaMemcpyAsync(x_host + off, c->x + off, n * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
             if (y_host) NM_CUDA_TRY(cudaMemcpyAsync(y_host + off, c->y + off, n * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
         }
+        if (trace) cudaEventRecord(tr_out[k], c->s_out);
         return NM_OK;
     };
     for (int k = 0; k < n_chunks; ++k) {        // the uploads do not depend on anything: queue them all
@@ -382,6 +393,7 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
         NM_CUDA_TRY(cudaMemcpyAsync(c->frames_stage + f0 * fpix, frames_host + f0 * fpix, fpix * n * sizeof(float),
                                     cudaMemcpyHostToDevice, c->s_in));
         NM_CUDA_TRY(cudaEventRecord(c->ev_in[k], c->s_in));
+        if (trace) cudaEventRecord(tr_in[k], c->s_in);
     }
     // stages alternate between the caller's stream and a second one (forked from it): the launch-bound
     // tail of one stage (small octaves, orientation) overlaps the big blur kernels of the next
@@ -391,11 +403,13 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
         const int f0 = bounds[k], n = bounds[k + 1] - bounds[k];
         cudaStream_t sk = (k & 1) ? c->s_aux : st;
         NM_CUDA_TRY(cudaStreamWaitEvent(sk, c->ev_in[k], 0));
+        if (trace) cudaEventRecord(tr_k0[k], sk);
         int rc = sift_run_range(c, c->frames_stage + f0 * fpix, f0, n, sk, false);
         if (rc != NM_OK) return rc;
         launches += c->last_launches;
         NM_CUDA_TRY(cudaMemcpyAsync(counts_host + f0, c->counts + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, sk));
         NM_CUDA_TRY(cudaEventRecord(c->ev_done[k], sk));
+        if (trace) cudaEventRecord(tr_k1[k], sk);
         if (k > 0 && (rc = drain(k - 1)) != NM_OK) return rc;
     }
     int rc = drain(n_chunks - 1);
@@ -406,6 +420,17 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
     NM_CUDA_TRY(cudaEventRecord(c->ev_out, c->s_out));
     NM_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_out, 0));
     NM_CUDA_TRY(cudaStreamSynchronize(st));
+    if (trace) {
+        for (int k = 0; k < n_chunks; ++k) {
+            float a = 0, b = 0, d = 0, e = 0;
+            cudaEventElapsedTime(&a, tr0, tr_in[k]); cudaEventElapsedTime(&b, tr0, tr_k0[k]);
+            cudaEventElapsedTime(&d, tr0, tr_k1[k]); cudaEventElapsedTime(&e, tr0, tr_out[k]);
+            fprintf(stderr, "[nm trace] stage %d frames %d..%d: uploaded %.2f  kernels %.2f..%.2f  downloaded %.2f ms\n",
+                    k, bounds[k], bounds[k + 1], a, b, d, e);
+            cudaEventDestroy(tr_in[k]); cudaEventDestroy(tr_k0[k]); cudaEventDestroy(tr_k1[k]); cudaEventDestroy(tr_out[k]);
+        }
+        cudaEventDestroy(tr0);
+    }
     c->last_launches = launches;
     return NM_OK;
 }

@@ -40,8 +40,12 @@ struct NmDetectParams {
 };
 
 // nm_extrema.cu
+struct NmBlurTma;
+// TMA descriptor of an octave's level planes for `batch` frames (oc.levels = first frame): box = the
+// extrema kernel's 36 x 34 x 6 window.  Without a valid descriptor the kernel stages the window with plain loads.
+bool nm_extrema_make_tma(NmBlurTma* t, const NmOctave& oc, int batch);
 int nm_extrema_launch(const NmOctave& oc, int octave_index, int n_oct, const NmDetectParams& dp,
-                      int batch, cudaStream_t stream);
+                      int batch, cudaStream_t stream, const NmBlurTma* tma = nullptr);
 int nm_rank_launch(const NmOctaveTable& tab, int batch, int* seg_raw, cudaStream_t stream);
 int nm_plan_launch(const int* seg_raw, int* seg_cnt, int* seg_off, int* counts, int n_oct, int batch,
                    int capacity, cudaStream_t stream);

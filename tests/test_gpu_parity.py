@@ -388,13 +388,13 @@ def test_stream_sharding_equals_single_run(nm):
     sb.close()
 
 
-def test_gradient_atan2_is_bitwise_the_library_atan2f(nm):
-    """The gradient kernels use the main path of the CUDA library's atan2f without its special-case
-    prologue (nm_atan2f_finite).  It must agree bit for bit with atan2f on every finite argument pair
-    that is not (0, 0): 2^28 generated pairs (random magnitudes over 80 binades, quarter-integer pixel
-    differences, signed zeros, subnormals, |x| == |y|)."""
+def test_gradient_arithmetic_is_bitwise_the_library_routines(nm):
+    """The gradient kernels inline the main paths of the CUDA library's sqrtf / division / atan2f behind
+    one range test (nm_gradient_from_diff).  It must agree bit for bit with the expression on the library
+    routines (cudamath.cu:47-52) on every (dx, dy): 2^28 generated pairs (136 binades, image-scale
+    magnitudes, quarter-integer pixel differences, zeros, subnormals, |dx| == |dy|, tiny vs large)."""
     import ctypes as C
     import niftymatch_b200._lib as L
     m = C.c_longlong(-1)
-    assert L.load().nm_selftest_atan2(1 << 28, 12345, C.byref(m)) == 0
+    assert L.load().nm_selftest_gradient(1 << 28, 12345, C.byref(m)) == 0
     assert m.value == 0

@@ -4,5 +4,5 @@ import niftymatch_b200 as nm
 lib = nm.load()
 for seed in range(4):
     m = C.c_longlong(-1)
-    rc = lib.nm_selftest_atan2(1 << 28, seed, C.byref(m))
+    rc = lib.nm_selftest_gradient(1 << 28, seed, C.byref(m))
     print("seed", seed, "rc", rc, "mismatches", m.value)
