@@ -6,6 +6,7 @@
 // no host synchronisation inside nm_sift_run.
 #include "nm_sift_internal.cuh"
 #include "nm_pyramid.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
@@ -14,7 +15,7 @@
 #include <vector>
 
 #define NM_MAX_CHUNKS 64
-#define NM_HOST_CHUNK 8       // frames per pipeline stage of nm_sift_run_host
+#define NM_AUX_STREAMS 3      // nm_sift_run_host: stages rotate over the caller's stream and up to 3 more
 
 struct nm_sift_ctx {
     nm_sift_params P;
@@ -26,8 +27,8 @@ struct nm_sift_ctx {
         NmBlurTma ex[NM_MAX_OCTAVES];       // the six levels of octave o, box of the extrema kernel
     };
     std::vector<TmaSet*> tma_sets;
-    cudaStream_t s_in, s_out, s_aux;     // nm_sift_run_host: H2D / D2H copy streams, second compute stream
-    cudaEvent_t ev_fork, ev_join;
+    cudaStream_t s_in, s_out, s_aux[NM_AUX_STREAMS];   // nm_sift_run_host: H2D / D2H copy streams, extra compute streams
+    cudaEvent_t ev_fork, ev_join[NM_AUX_STREAMS];
     cudaEvent_t ev_in[NM_MAX_CHUNKS], ev_done[NM_MAX_CHUNKS], ev_out;
     float* taps[6];          // 0: base kernel, 1..5: level kernels (device)
     int    radii[6];
@@ -140,9 +141,11 @@ extern "C" int nm_sift_destroy(nm_sift_ctx* c)
     if (c->ev_out) cudaEventDestroy(c->ev_out);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
-    if (c->s_aux) cudaStreamDestroy(c->s_aux);
+    for (int i = 0; i < NM_AUX_STREAMS; ++i) {
+        if (c->s_aux[i]) cudaStreamDestroy(c->s_aux[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
     return NM_OK;
 }
@@ -163,7 +166,8 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
     c->P = P; c->B = max_batch; c->capacity = capacity; c->n_oct = P.num_octaves;
     c->scratch = nullptr; c->exact_desc = 0; c->last_launches = 0; c->timing = 0;
     for (int i = 0; i < 6; ++i) c->ev[i] = nullptr;
-    c->s_in = c->s_out = c->s_aux = nullptr; c->ev_out = c->ev_fork = c->ev_join = nullptr;
+    c->s_in = c->s_out = nullptr; c->ev_out = c->ev_fork = nullptr;
+    for (int i = 0; i < NM_AUX_STREAMS; ++i) { c->s_aux[i] = nullptr; c->ev_join[i] = nullptr; }
     for (int i = 0; i < NM_MAX_CHUNKS; ++i) c->ev_in[i] = c->ev_done[i] = nullptr;
     int rc = NM_OK;
     // Gaussian kernels
@@ -212,11 +216,13 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
         if (cudaEventCreate(&c->ev[i]) != cudaSuccess) rc = NM_ERR_ALLOC;
     if (rc == NM_OK && (cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) != cudaSuccess ||
                         cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) != cudaSuccess ||
-                        cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking) != cudaSuccess ||
                         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-                        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
                         cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess))
         rc = NM_ERR_ALLOC;
+    for (int i = 0; i < NM_AUX_STREAMS && rc == NM_OK; ++i)
+        if (cudaStreamCreateWithFlags(&c->s_aux[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) != cudaSuccess)
+            rc = NM_ERR_ALLOC;
     for (int i = 0; i < NM_MAX_CHUNKS && rc == NM_OK; ++i)
         if (cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming) != cudaSuccess)
@@ -334,7 +340,7 @@ extern "C" int nm_sift_run(nm_sift_ctx* c, const float* frames_dev, int n_frames
     return sift_run_range(c, frames_dev, 0, n_frames, (cudaStream_t)stream, c->timing != 0);
 }
 
-// End to end from host memory, software pipelined in chunks of NM_HOST_CHUNK frames: the H2D copy
+// End to end from host memory, software pipelined in stages of a few frames: the H2D copy
 // of chunk k+1 (stream s_in), the kernels of chunk k (caller's stream) and the D2H copies of chunk
 // k-1 (stream s_out) overlap; the host only waits for a chunk's 4-byte counts before it sizes that
 // chunk's result copies.  Host buffers should be pinned for the copies to be asynchronous.
@@ -344,26 +350,26 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
     if (!c || !frames_host || !counts_host || n_frames <= 0 || n_frames > c->B) return NM_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t fpix = (size_t)c->P.width * c->P.height;
-    // Pipeline stages: the end-to-end time is (upload of the first stage) + (all kernels) + (download of
-    // the last stage), and every stage costs ~0.25 ms of under-filled launches, so the schedule is a small
-    // first and last stage around stages of up to 16 frames.  NM_HOST_CHUNK=<n> forces uniform stages.
+    // Pipeline stages: the uploads pace the pipeline (1080p: 6.7 frames/ms over PCIe against 7.1 frames/ms
+    // of kernels at full batch), so the end-to-end time is (all uploads) + (what the kernels still have to
+    // do when the last frame lands).  Small stages keep that tail short; their under-filled launches
+    // (octaves 2+ are a fraction of a wave) are covered by running up to four stages concurrently on
+    // separate streams.  Measured at 64 x 1080p: 6-frame stages on 4 streams 12.5 ms, 8 on 2: 12.8,
+    // 14-frame stages with small edge stages on 2 (previous schedule): 13.9.
+    // NM_HOST_CHUNK=<n> / NM_HOST_STREAMS=<1..4> override (tuning aid).
     static const int forced = [] {
         const char* e = getenv("NM_HOST_CHUNK");
         return e ? atoi(e) : 0;
     }();
+    const int stage = forced > 0 ? forced : 6;
     int bounds[NM_MAX_CHUNKS + 1];
     int n_chunks = 0;
     bounds[0] = 0;
-    if (forced > 0) {
-        for (int f = 0; f < n_frames && n_chunks < NM_MAX_CHUNKS; f += forced) bounds[++n_chunks] = f + forced < n_frames ? f + forced : n_frames;
-        if (bounds[n_chunks] != n_frames) return NM_ERR_INVALID;
-    } else if (n_frames <= 8) {
+    if (n_frames <= 8 && forced <= 0) {
         bounds[++n_chunks] = n_frames;
     } else {
-        const int edge = 4, mid = n_frames - 2 * edge, m = nm_div_up(mid, 16);
-        bounds[++n_chunks] = edge;
-        for (int i = 1; i <= m; ++i) bounds[++n_chunks] = edge + (int)((long long)mid * i / m);
-        bounds[++n_chunks] = n_frames;
+        const int per = std::max(stage, nm_div_up(n_frames, NM_MAX_CHUNKS));
+        for (int f = 0; f < n_frames; f += per) bounds[++n_chunks] = f + per < n_frames ? f + per : n_frames;
     }
     if (n_chunks > NM_MAX_CHUNKS) return NM_ERR_INVALID;
     int launches = 0;
@@ -397,11 +403,16 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
     }
     // stages alternate between the caller's stream and a second one (forked from it): the launch-bound
     // tail of one stage (small octaves, orientation) overlaps the big blur kernels of the next
+    static const int n_streams = [] {
+        const char* e = getenv("NM_HOST_STREAMS");
+        const int v = e ? atoi(e) : 4;
+        return v < 1 ? 1 : v > NM_AUX_STREAMS + 1 ? NM_AUX_STREAMS + 1 : v;
+    }();
     NM_CUDA_TRY(cudaEventRecord(c->ev_fork, st));
-    NM_CUDA_TRY(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
+    for (int i = 0; i + 1 < n_streams; ++i) NM_CUDA_TRY(cudaStreamWaitEvent(c->s_aux[i], c->ev_fork, 0));
     for (int k = 0; k < n_chunks; ++k) {
         const int f0 = bounds[k], n = bounds[k + 1] - bounds[k];
-        cudaStream_t sk = (k & 1) ? c->s_aux : st;
+        cudaStream_t sk = (k % n_streams) ? c->s_aux[k % n_streams - 1] : st;
         NM_CUDA_TRY(cudaStreamWaitEvent(sk, c->ev_in[k], 0));
         if (trace) cudaEventRecord(tr_k0[k], sk);
         int rc = sift_run_range(c, c->frames_stage + f0 * fpix, f0, n, sk, false);
@@ -410,13 +421,20 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
         NM_CUDA_TRY(cudaMemcpyAsync(counts_host + f0, c->counts + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, sk));
         NM_CUDA_TRY(cudaEventRecord(c->ev_done[k], sk));
         if (trace) cudaEventRecord(tr_k1[k], sk);
-        if (k > 0 && (rc = drain(k - 1)) != NM_OK) return rc;
+        // the host may only block on a stage once the next n_streams - 1 stages are queued behind it
+        const int lag = n_streams > 1 ? n_streams - 1 : 1;
+        if (k >= lag && (rc = drain(k - lag)) != NM_OK) return rc;
     }
-    int rc = drain(n_chunks - 1);
-    if (rc != NM_OK) return rc;
-    // the caller's stream is complete when both compute streams and the result copies are
-    NM_CUDA_TRY(cudaEventRecord(c->ev_join, c->s_aux));
-    NM_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));
+    for (int k = n_chunks - (n_streams > 1 ? n_streams - 1 : 1); k < n_chunks; ++k) {
+        if (k < 0) continue;
+        int rc = drain(k);
+        if (rc != NM_OK) return rc;
+    }
+    // the caller's stream is complete when all compute streams and the result copies are
+    for (int i = 0; i + 1 < n_streams; ++i) {
+        NM_CUDA_TRY(cudaEventRecord(c->ev_join[i], c->s_aux[i]));
+        NM_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join[i], 0));
+    }
     NM_CUDA_TRY(cudaEventRecord(c->ev_out, c->s_out));
     NM_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_out, 0));
     NM_CUDA_TRY(cudaStreamSynchronize(st));

@@ -341,6 +341,34 @@ def test_run_host_end_to_end(nm, oracle):
     sb.close()
 
 
+def test_run_host_pipeline_equals_device_run(nm):
+    """nm_sift_run_host splits a batch into stages of a few frames that run concurrently on several
+    streams (H2D, kernels and D2H overlapped).  20 frames = 4 stages: counts, descriptors and coordinates
+    must be bitwise those of the single whole-batch nm_sift_run on device-resident frames."""
+    n = 20
+    frames = np.stack([synth.scene(256, 192, synth.SEED_BASE + (i % 5), shift=(0.5 * (i // 5), 0.25 * (i // 5)))
+                       for i in range(n)])
+    P = nm.SiftParams(256, 192)
+    sb = nm.SiftBatch(P, n, 1024)
+    sb.run(torch.from_numpy(frames).cuda())
+    torch.cuda.synchronize()
+    r = sb.results()
+    counts = r["counts"].cpu().numpy().copy()
+    desc = r["desc"].cpu().numpy().copy()
+    xs = r["x"].cpu().numpy().copy()
+    ys = r["y"].cpu().numpy().copy()
+    for rep in range(2):                                   # second call reuses the cached stage descriptors
+        out = sb.run_host(torch.from_numpy(frames).pin_memory())
+        assert np.array_equal(out["counts"].numpy(), counts)
+        assert counts.min() > 20
+        for f in range(n):
+            k = int(counts[f])
+            assert np.array_equal(out["desc"][f, :k].numpy(), desc[f, :k]), (rep, f)
+            assert np.array_equal(out["x"][f, :k].numpy(), xs[f, :k])
+            assert np.array_equal(out["y"][f, :k].numpy(), ys[f, :k])
+    sb.close()
+
+
 def test_4k_six_octave_pyramid_and_extrema_vs_oracle(nm, oracle):
     """BASELINE.json configs[2]: 3840x2160, octave count forced to 6 (the default would be 7):
     Gaussian levels bitwise, keypoints bitwise, against the CPU oracle."""
