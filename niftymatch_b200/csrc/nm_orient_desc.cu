@@ -70,29 +70,55 @@ __global__ void __launch_bounds__(OR_WARPS * 32) orient_kernel(const NmOctaveTab
         const int nx = xmax - xmin + 1, ny = ymax - ymin + 1;
         const int total = (nx > 0 && ny > 0) ? nx * ny : 0;
         const float den = __fmul_rn(sigma_w, __fadd_rn(sigma_w, sigma_w));  // 2*sigma_w*sigma_w
-        const double lim = __dadd_rn((double)(W * W), 0.6);
+        // :55 compares (double)r2 < W*W + 0.6; W*W + 0.6 is not an fp32 number, so for fp32 r2 that is
+        // r2 < (the smallest fp32 above it)
+        const float lim_f = __double2float_ru(__dadd_rn((double)(W * W), 0.6));
         // Window samples in raster order, 32 per step; (cx, cy) advance incrementally (no division per
-        // sample) and the gradient of the next step is requested before the arithmetic of this one.
+        // sample).  The gradient maps of a batch live in HBM and only 8 warps per scheduler are resident,
+        // so OR_DEPTH steps of gradient loads stay in flight per lane (ncu: long-scoreboard waits on the
+        // single prefetched value were the top stall).
+        constexpr int OR_DEPTH = 4;
         int cx = xmin + lane % max(nx, 1), cy = ymin + lane / max(nx, 1);
         const int adv_y = 32 / max(nx, 1), adv_x = 32 % max(nx, 1);
-        float2 ngv = make_float2(0.f, 0.f);
-        if (lane < total) ngv = __ldg(G + (cy * pitch + cx));
-        for (int s = lane; s < total; s += 32) {
-            const int ccx = cx, ccy = cy;
-            const float2 gv = ngv;
+        int pcx[OR_DEPTH], pcy[OR_DEPTH];
+        float2 pg[OR_DEPTH];
+#pragma unroll
+        for (int d = 0; d < OR_DEPTH; ++d) {
+            pcx[d] = cx; pcy[d] = cy;
+            pg[d] = make_float2(0.f, 0.f);
+            if (lane + 32 * d < total) pg[d] = __ldg(G + (cy * pitch + cx));
             cx += adv_x; cy += adv_y;
             if (cx > xmax) { cx -= nx; ++cy; }
-            if (s + 32 < total) ngv = __ldg(G + (cy * pitch + cx));
-            const float dx = __fsub_rn((float)(ccx + g.xi), g.x);  // :52-53
-            const float dy = __fsub_rn((float)(ccy + g.yi), g.y);
-            const float r2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));         // :54
-            if ((double)r2 < lim) {                               // :55
-                const float wgt = expf(__fdiv_rn(r2, den));       // :56 (positive exponent)
-                int bin = (int)floorf((float)__ddiv_rn((double)__fmul_rn(36.0f, gv.y), NM_TWO_PI_D));  // :57
-                bin %= NBINS;
-                if (bin < 0) bin += NBINS;
-                float* p = priv + bin * OR_HP + lane;             // bank == lane: conflict free
-                *p = __fadd_rn(*p, __fmul_rn(gv.x, wgt));         // :58
+        }
+        for (int s = lane; s < total; s += 32 * OR_DEPTH) {
+#pragma unroll
+            for (int d = 0; d < OR_DEPTH; ++d) {
+                const int ccx = pcx[d], ccy = pcy[d];
+                const float2 gv = pg[d];
+                const bool valid = s + 32 * d < total;
+                pcx[d] = cx; pcy[d] = cy;
+                if (s + 32 * (d + OR_DEPTH) < total) pg[d] = __ldg(G + (cy * pitch + cx));
+                cx += adv_x; cy += adv_y;
+                if (cx > xmax) { cx -= nx; ++cy; }
+                const float dx = __fsub_rn((float)(ccx + g.xi), g.x);  // :52-53
+                const float dy = __fsub_rn((float)(ccy + g.yi), g.y);
+                const float r2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));         // :54
+                if (valid && r2 < lim_f) {                            // :55
+                    const float wgt = expf(__fdiv_rn(r2, den));       // :56 (positive exponent)
+                    // :57  bin = floor((float)((double)(36 theta) / 2 pi)).  The fp32 product v * (1 / 2 pi) is within
+                    // 7e-6 of that quotient (v <= 227), so its floor is the reference's unless it lies within 1e-5
+                    // of an integer; only then (2e-5 of the samples) the double division decides.
+                    const float v36 = __fmul_rn(36.0f, gv.y);
+                    const float qf = __fmul_rn(v36, 0.15915494309189535f);
+                    float qfl = floorf(qf);
+                    const float fr = __fsub_rn(qf, qfl);
+                    if (!(fr > 1e-5f && fr < 0.99999f)) qfl = floorf((float)__ddiv_rn((double)v36, NM_TWO_PI_D));
+                    int bin = (int)qfl;
+                    bin %= NBINS;
+                    if (bin < 0) bin += NBINS;
+                    float* p = priv + bin * OR_HP + lane;             // bank == lane: conflict free
+                    *p = __fadd_rn(*p, __fmul_rn(gv.x, wgt));         // :58
+                }
             }
         }
         __syncwarp();
@@ -209,7 +235,8 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
     const int ymin = max(-W, -g.yi), ymax = min(W, oc.h - 1 - g.yi);
     const int max_dims = max(xmax - xmin, ymax - ymin);
     const int chunks = (int)ceilf(__fdiv_rn(__fadd_rn((float)max_dims, 1.f), 16.f));     // :65
-    const float th0 = orient[kidx].x;                                                    // :89
+    const float th0 = orient[kidx].x;                                                    // :89; in [0, 2 pi] or -1 (no peak),
+                                                                                         // so gradient angle - th0 is in (-2 pi, 2 pi + 1]
     const float st0f = sinf(th0), ct0f = cosf(th0);                                      // :90-91 (float overloads)
     const double st0 = (double)st0f, ct0 = (double)ct0f;
     const float inv_sbp = __fdiv_rn(1.0f, SBP);
@@ -234,7 +261,7 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
         float nx, ny, nt, win, rbinx, rbiny;
         int binx, biny;
         if (EXACT) {
-            const float theta = nm_mod_2pi_f(__fsub_rn(gv.y, th0));                                       // :100
+            const float theta = nm_mod_2pi_once(__fsub_rn(gv.y, th0));                                       // :100
             nx = (float)__ddiv_rn(__fma_rn(ct0, (double)dx, __dmul_rn(st0, (double)dy)), (double)SBP);    // :104
             ny = (float)__ddiv_rn(__fma_rn(ct0, (double)dy, -__dmul_rn(st0, (double)dx)), (double)SBP);   // :105
             nt = (float)__ddiv_rn((double)__fmul_rn(8.0f, theta), NM_TWO_PI_D);                           // :107
@@ -251,7 +278,7 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
             // about a third of the window (corners outside the rotated 4x4 cell grid) lands in no
             // bin (:122-125 rejects all four cells): skip before the exponential and the angle
             act = act && !(binx < -3 || binx > 1 || biny < -3 || biny > 1);
-            const float theta = nm_mod_2pi_f(__fsub_rn(gv.y, th0));   // :100
+            const float theta = nm_mod_2pi_once(__fsub_rn(gv.y, th0));   // :100
             nt = __fmul_rn(theta, 1.2732395447351628f);               // 8 / (2 pi)
             win = expf(__fmul_rn(__fmaf_rn(nx, nx, __fmul_rn(ny, ny)), 0.125f));
             rbinx = __fsub_rn(nx, __fadd_rn(fx, 0.5f));
@@ -276,6 +303,7 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
         const float a0 = __fmul_rn(wm, ax0), a1 = __fmul_rn(wm, ax1);
         constexpr int OX = 8 * DE_COPIES, OY = 32 * DE_COPIES;        // next cell in x / y (floats)
         // lanes l and l + 16 share a private copy: the two half-warps update one after the other
+        // (computing the eight contributions once, outside the phases, measured slower: 2.27 -> 2.61 ms)
 #pragma unroll
         for (int ph = 0; ph < 32 / DE_COPIES; ++ph) {
         if (act && (lane / DE_COPIES) == ph) {
