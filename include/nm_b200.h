@@ -202,6 +202,16 @@ int nm_sift_run_host(nm_sift_ctx* ctx, const float* frames_host, int n_frames,
                      int* counts_host, float* desc_host, float* x_host, float* y_host,
                      nm_stream_t stream);
 
+/* compute_keypoints_with_mask (gpu/sift/siftfunctions.h:49-57; siftfunctions.cu:65-98) for the batched
+ * path: tex_mask = the caller's cudaTextureObject_t, sampled at ((x+.5)*xper, (y+.5)*xper) in every octave;
+ * pixels whose sample is < 1 produce no keypoint (gpu/kernels/keypoint.cu:214).  0 = unmasked (default).
+ * The texture must outlive the runs that use it. */
+int nm_sift_set_mask(nm_sift_ctx* ctx, unsigned long long tex_mask);
+/* Convenience for callers without a texture: binds a width x height float mask image (host or device
+ * memory) as a cudaArray texture with the reference's CudaTex2D settings (gpu/utils/cudatex2D.cu:12-19:
+ * border addressing, linear filter, unnormalised coordinates; element-type reads).  Owned by the context. */
+int nm_sift_set_mask_image(nm_sift_ctx* ctx, const float* mask, int width, int height);
+
 /* Device-side results of the last run (valid until the next run / destroy).
  * desc: [max_batch][capacity][128]; x, y: [max_batch][capacity]; kpts4/orient2 likewise;
  * counts: [max_batch] descriptors per frame; seg_counts: [max_batch][num_octaves*3]

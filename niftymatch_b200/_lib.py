@@ -65,6 +65,8 @@ SIGNATURES = {
     "nm_sift_create": (_i, [C.POINTER(_vp), C.POINTER(SiftParamsC), _i, _i]),
     "nm_sift_destroy": (_i, [_vp]),
     "nm_sift_run": (_i, [_vp, _vp, _i, _vp]),
+    "nm_sift_set_mask": (_i, [_vp, _ull]),
+    "nm_sift_set_mask_image": (_i, [_vp, _vp, _i, _i]),
     "nm_sift_run_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "nm_sift_results": (_i, [_vp] + [C.POINTER(_vp)] * 7),
     "nm_sift_level": (_i, [_vp, _i, _i, _i, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),

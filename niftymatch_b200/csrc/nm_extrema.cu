@@ -189,9 +189,15 @@ __global__ void __launch_bounds__(256, 4) extrema_grad_kernel(const NmOctave oc,
         for (int l = 0; l < 3; ++l) {
             bool acc = false;
             if (interior && ((extmask >> (l * 4 + i)) & 1u)) {
-                SmemDogFetch ft{s_dog, l, r, c};
-                float4 out;
-                acc = nm_refine(ft, gx, gy, dp.peak, dp.edge, oc.xper, dp.sigma_0, dp.num_dogs, l, out);
+                // compute_keypoints_with_mask: pixels whose mask sample is < 1 are skipped (keypoint.cu:214; the
+                // reference tests it first, the outcome is the same) -- one texture fetch per extremum candidate
+                const bool masked_out = dp.mask != 0 &&
+                    tex2D<float>((cudaTextureObject_t)dp.mask, (gx + 0.5f) * oc.xper, (gy + 0.5f) * oc.xper) < 1.f;
+                if (!masked_out) {
+                    SmemDogFetch ft{s_dog, l, r, c};
+                    float4 out;
+                    acc = nm_refine(ft, gx, gy, dp.peak, dp.edge, oc.xper, dp.sigma_0, dp.num_dogs, l, out);
+                }
             }
             const unsigned m = __ballot_sync(0xffffffffu, acc);
             if (lane == 0) BM[l * bm_words + (long long)gy * oc.wpr + blockIdx.x] = m;

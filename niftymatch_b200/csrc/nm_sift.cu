@@ -39,6 +39,9 @@ struct nm_sift_ctx {
     float* frames_stage;     // device staging for nm_sift_run_host: [B][h][w]
     float* scratch;          // generic-radius blur scratch (lazily allocated)
     int exact_desc;
+    unsigned long long mask_tex;   // detector mask (0 = none); mask_arr/mask_own: texture made by nm_sift_set_mask_image
+    cudaArray_t mask_arr;
+    cudaTextureObject_t mask_own;
     int last_launches;
     int timing;
     cudaEvent_t ev[6];
@@ -128,9 +131,16 @@ extern "C" int nm_gaussian_taps(float sigma, float* taps_host, int* radius)
     return NM_OK;
 }
 
+static void release_own_mask(nm_sift_ctx* c)
+{
+    if (c->mask_own) { if (c->mask_tex == c->mask_own) c->mask_tex = 0; cudaDestroyTextureObject(c->mask_own); c->mask_own = 0; }
+    if (c->mask_arr) { cudaFreeArray(c->mask_arr); c->mask_arr = nullptr; }
+}
+
 extern "C" int nm_sift_destroy(nm_sift_ctx* c)
 {
     if (!c) return NM_OK;
+    release_own_mask(c);
     for (void* p : c->allocs) cudaFree(p);
     for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (auto* t : c->tma_sets) delete t;
@@ -165,6 +175,7 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
     if (!c) return NM_ERR_ALLOC;
     c->P = P; c->B = max_batch; c->capacity = capacity; c->n_oct = P.num_octaves;
     c->scratch = nullptr; c->exact_desc = 0; c->last_launches = 0; c->timing = 0;
+    c->mask_tex = 0; c->mask_arr = nullptr; c->mask_own = 0;
     for (int i = 0; i < 6; ++i) c->ev[i] = nullptr;
     c->s_in = c->s_out = nullptr; c->ev_out = c->ev_fork = nullptr;
     for (int i = 0; i < NM_AUX_STREAMS; ++i) { c->s_aux[i] = nullptr; c->ev_join[i] = nullptr; }
@@ -239,7 +250,7 @@ static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, in
 {
     const nm_sift_params& P = c->P;
     int launches = 0, rc;
-    NmDetectParams dp{P.peak_threshold, P.edge_threshold, P.sigma_0, P.num_dog_levels};
+    NmDetectParams dp{P.peak_threshold, P.edge_threshold, P.sigma_0, P.num_dog_levels, c->mask_tex};
     // workspace views of the range
     NmOctaveTable tab = c->tab;
     for (int o = 0; o < c->n_oct; ++o) {
@@ -450,6 +461,41 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
         cudaEventDestroy(tr0);
     }
     c->last_launches = launches;
+    return NM_OK;
+}
+
+// compute_keypoints_with_mask (gpu/sift/siftfunctions.cu:65-98) for the batched path: the caller's
+// texture object, sampled at ((x+.5)*xper, (y+.5)*xper) in every octave (keypoint.cu:214).  0 = unmasked.
+extern "C" int nm_sift_set_mask(nm_sift_ctx* c, unsigned long long tex_mask)
+{
+    if (!c) return NM_ERR_INVALID;
+    if (tex_mask != c->mask_own) release_own_mask(c);
+    c->mask_tex = tex_mask;
+    return NM_OK;
+}
+
+// Convenience: bind a width x height float mask image (host or device memory) the way a reference client
+// does -- a cudaArray behind a texture with the CudaTex2D settings (gpu/utils/cudatex2D.cu:12-19: border
+// addressing, linear filter, unnormalised coordinates) and element-type reads.  The context owns it.
+extern "C" int nm_sift_set_mask_image(nm_sift_ctx* c, const float* mask, int width, int height)
+{
+    if (!c || !mask || width <= 0 || height <= 0) return NM_ERR_INVALID;
+    release_own_mask(c);
+    cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
+    if (cudaMallocArray(&c->mask_arr, &fd, width, height) != cudaSuccess) { cudaGetLastError(); c->mask_arr = nullptr; return NM_ERR_ALLOC; }
+    cudaError_t e = cudaMemcpy2DToArray(c->mask_arr, 0, 0, mask, (size_t)width * sizeof(float), (size_t)width * sizeof(float),
+                                        height, cudaMemcpyDefault);
+    if (e != cudaSuccess) { release_own_mask(c); return nm_cuda_err(e); }
+    cudaResourceDesc rd; std::memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray; rd.res.array.array = c->mask_arr;
+    cudaTextureDesc td; std::memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeBorder;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    e = cudaCreateTextureObject(&c->mask_own, &rd, &td, nullptr);
+    if (e != cudaSuccess) { c->mask_own = 0; release_own_mask(c); return nm_cuda_err(e); }
+    c->mask_tex = c->mask_own;
     return NM_OK;
 }
 

@@ -37,6 +37,7 @@ struct NmOctaveTable {
 struct NmDetectParams {
     float peak, edge, sigma_0;
     int   num_dogs;
+    unsigned long long mask;   // cudaTextureObject_t of the caller's mask (compute_keypoints_with_mask), 0 = none
 };
 
 // nm_extrema.cu

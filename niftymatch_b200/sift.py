@@ -156,6 +156,22 @@ class SiftBatch:
     def last_launches(self) -> int:
         return self.lib.nm_sift_last_launches(self._ctx)
 
+    def set_mask(self, mask=None):
+        """Detector mask (compute_keypoints_with_mask, siftfunctions.cu:65-98): an h x w float image (numpy
+        array or torch tensor, host or device); None removes it.  Pixels whose mask sample is < 1 give no keypoint."""
+        if mask is None:
+            check(self.lib.nm_sift_set_mask(self._ctx, 0), "nm_sift_set_mask")
+            return
+        import torch
+        if isinstance(mask, torch.Tensor):
+            mask = mask.contiguous().float()
+            ptr, (h, w) = mask.data_ptr(), mask.shape
+        else:
+            mask = np.ascontiguousarray(mask, dtype=np.float32)
+            ptr, (h, w) = mask.ctypes.data, mask.shape
+        assert (h, w) == (self.params._height, self.params._width)
+        check(self.lib.nm_sift_set_mask_image(self._ctx, C.c_void_p(ptr), int(w), int(h)), "nm_sift_set_mask_image")
+
     def enable_timing(self, on: bool = True):
         check(self.lib.nm_sift_enable_timing(self._ctx, int(on)), "nm_sift_enable_timing")
 

@@ -249,15 +249,37 @@ static void refine(int x, int y, const float* cur, const float* down, const floa
     }
 }
 
-/* find_keypoints, unmasked (keypoint.cu:183-200, 240-251).  `result` is the dense
- * per-pixel map; the caller pre-fills it with (-1,-1,-1,-1) (siftfunctions.cu:120). */
-void orc_find_keypoints(const float* cur, const float* down, const float* up, int w, int h,
-                        float peak, float edge, float xper, float sigma_0, int num_dogs,
-                        int level, f4* result)
+/* tex2D<float> of a linear-filter, border-addressed, unnormalised-coordinate texture
+ * (cudatex2D.cu:12-19) over a mw x mh float image, CUDA programming guide "Linear Filtering":
+ * xB = x - 0.5, i = floor(xB), alpha = frac(xB) held in 1.8 fixed point, texels outside the
+ * image are 0.  The detector samples the mask at ((x+.5)*xper, (y+.5)*xper) with xper = 2^o
+ * (keypoint.cu:214): alpha = beta = 0 for octave 0 (the texel itself), exactly 1/2 for the others
+ * (the mean of the four texels around the block centre), so the weights are exact here. */
+static float tex2d_linear_border(const float* img, int mw, int mh, float x, float y)
+{
+    const float xb = x - 0.5f, yb = y - 0.5f;
+    const float fi = floorf(xb), fj = floorf(yb);
+    const float a = floorf((xb - fi) * 256.0f + 0.5f) / 256.0f;   /* 8 fractional bits */
+    const float b = floorf((yb - fj) * 256.0f + 0.5f) / 256.0f;
+    const int i = (int)fi, j = (int)fj;
+#define NMO_T(ii, jj) (((ii) >= 0 && (ii) < mw && (jj) >= 0 && (jj) < mh) ? img[(size_t)(jj) * mw + (ii)] : 0.0f)
+    const float t00 = NMO_T(i, j), t10 = NMO_T(i + 1, j), t01 = NMO_T(i, j + 1), t11 = NMO_T(i + 1, j + 1);
+#undef NMO_T
+    return (1 - a) * (1 - b) * t00 + a * (1 - b) * t10 + (1 - a) * b * t01 + a * b * t11;
+}
+
+/* find_keypoints (keypoint.cu:183-200, 240-251; masked variant :204-222, 226-237 when mask != NULL:
+ * pixels whose mask sample is < 1 are skipped, :214).  `result` is the dense per-pixel map; the
+ * caller pre-fills it with (-1,-1,-1,-1) (siftfunctions.cu:120 / :86). */
+void orc_find_keypoints_masked(const float* cur, const float* down, const float* up, int w, int h,
+                               float peak, float edge, float xper, float sigma_0, int num_dogs,
+                               int level, f4* result, const float* mask, int mw, int mh)
 {
     const float t = 0.8f * peak;                                 /* :195 */
     for (int y = 1; y <= h - 2; ++y)
         for (int x = 1; x <= w - 2; ++x) {
+            if (mask && tex2d_linear_border(mask, mw, mh, ((float)x + 0.5f) * xper, ((float)y + 0.5f) * xper) < 1.0f)
+                continue;                                        /* :214 */
             const float c = cur[(size_t)y * w + x];
             int is_min = c <= t, is_max = c >= t, ok = 0;
             if (is_min) {
@@ -282,6 +304,13 @@ void orc_find_keypoints(const float* cur, const float* down, const float* up, in
             }
             if (ok) refine(x, y, cur, down, up, w, peak, edge, xper, sigma_0, num_dogs, level, result);
         }
+}
+
+void orc_find_keypoints(const float* cur, const float* down, const float* up, int w, int h,
+                        float peak, float edge, float xper, float sigma_0, int num_dogs,
+                        int level, f4* result)
+{
+    orc_find_keypoints_masked(cur, down, up, w, h, peak, edge, xper, sigma_0, num_dogs, level, result, NULL, 0, 0);
 }
 
 /* gpu_collate_keypoints_for_level (gpu/sift/pyramidata.cu:9-15,84-91): stable
@@ -536,17 +565,18 @@ void orc_match(const float* A, int nA, const float* B, int nB, float ambiguity, 
 /* Whole frame: the client loop of SURVEY.md 3.1 around                        */
 /* compute_dog/_gradients/_keypoints/_orientations/_descriptors                */
 /* (gpu/sift/siftfunctions.cu:42-181).  Same signature and dump layout as      */
-/* nmref_sift_frame in oracle/ref_driver.cu.                                   */
+/* nmref_sift_frame(_masked) in oracle/ref_driver.cu; mask = NULL or a w x h   */
+/* float image for compute_keypoints_with_mask (siftfunctions.cu:65-98).       */
 /* cfg6 = {peak_threshold, edge_threshold(<=0 default), num_octaves(<=0        */
 /*         default), capacity(<=0: 2048), clear_grad, orient_mode}             */
 /* orient_mode 0: public-API orientation (window clamp 10); 1: arithmetic of   */
 /* kernel_orientations_naive (no clamp); 2: orientations injected (orient_in,  */
 /* float2 per keypoint in segment order).                                      */
 /* ------------------------------------------------------------------------- */
-int orc_sift_frame(const float* image, int w, int h, const float* cfg5,
-                   float* desc, float* xo, float* yo, int* num_items,
-                   float* levels_out, float* kpts_out, float* orient_out, int* seg_counts,
-                   int kp_cap, float* grad_out, const float* orient_in)
+int orc_sift_frame_masked(const float* image, int w, int h, const float* cfg5,
+                          float* desc, float* xo, float* yo, int* num_items,
+                          float* levels_out, float* kpts_out, float* orient_out, int* seg_counts,
+                          int kp_cap, float* grad_out, const float* orient_in, const float* mask)
 {
     const int orient_mode = (int)cfg5[5];
     int inject_off = 0;
@@ -590,8 +620,9 @@ int orc_sift_frame(const float* image, int w, int h, const float* cfg5,
         int stopped = 0;
         for (int l = 0; l < 3 && !stopped; ++l) {
             for (size_t i = 0; i < n; ++i) { dense[i].x = dense[i].y = dense[i].z = dense[i].w = -1.f; }
-            orc_find_keypoints(dog[l + 1], dog[l], dog[l + 2], ow, oh, P.peak_threshold,
-                               P.edge_threshold, xper, P.sigma_0, P.num_dog_levels, l, dense);   /* :119-126 */
+            orc_find_keypoints_masked(dog[l + 1], dog[l], dog[l + 2], ow, oh, P.peak_threshold,
+                                      P.edge_threshold, xper, P.sigma_0, P.num_dog_levels, l, dense,
+                                      mask, w, h);               /* :119-126 / :83-92 with a mask */
             cnt[l] = orc_collate(dense, (int)n, coll[l]);        /* :144 */
             if (cnt[l] == 0) { stopped = 1; break; }             /* :145 `return` */
             for (int i = 0; i < cnt[l]; ++i) { orient[l][i].x = -1.f; orient[l][i].y = -1.f; }
@@ -635,6 +666,15 @@ int orc_sift_frame(const float* image, int w, int h, const float* cfg5,
     for (int i = 0; i < 3; ++i) { free(coll[i]); free(orient[i]); }
     free(buffer); free(grad); free(dense); free(dloc); free(xl); free(yl);
     return P.num_octaves;
+}
+
+int orc_sift_frame(const float* image, int w, int h, const float* cfg5,
+                   float* desc, float* xo, float* yo, int* num_items,
+                   float* levels_out, float* kpts_out, float* orient_out, int* seg_counts,
+                   int kp_cap, float* grad_out, const float* orient_in)
+{
+    return orc_sift_frame_masked(image, w, h, cfg5, desc, xo, yo, num_items, levels_out, kpts_out, orient_out,
+                                 seg_counts, kp_cap, grad_out, orient_in, NULL);
 }
 
 /* CPU-baseline leg of bench.py: n_frames independent frames on `threads` OpenMP

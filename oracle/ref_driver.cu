@@ -18,6 +18,7 @@
 #include "cudamath.h"
 #include "match.h"
 #include "transpose.h"
+#include "cudatex2D.h"
 // Textual include of the reference source (not a copy: resolved at build time from
 // /root/reference/src/gpu/kernels): gives this client access to BOTH orientation kernels
 // the reference ships.  Needed because the kernel its public API launches
@@ -113,7 +114,7 @@ SiftParams make_params(int w, int h, const Cfg& c)
 void run_frame(const float* image_dev, int w, int h, const SiftParams& P, PyramidData& py,
                SiftData& data, int clear_grad, int orient_mode, const float* orient_in,
                float* levels_out, float* kpts_out, float* orient_out, int* seg_counts, int kp_cap,
-               float* grad_out)
+               float* grad_out, cudaTextureObject_t mask = 0)
 {
     data._num_items = 0;
     int inject_off = 0;
@@ -133,7 +134,12 @@ void run_frame(const float* image_dev, int w, int h, const SiftParams& P, Pyrami
         if (clear_grad) thrust::fill(py._grad.begin(), py._grad.end(), make_float2(0.f, 0.f));
         compute_gradients(py, P, ow, oh);
         trace("compute_gradients", o);
-        compute_keypoints(py, P, o, ow, oh);
+        if (mask) {
+            SiftParams Pm = P;                                   // the masked entry takes a non-const reference
+            compute_keypoints_with_mask(py, Pm, mask, o, ow, oh);
+        } else {
+            compute_keypoints(py, P, o, ow, oh);
+        }
         trace("compute_keypoints", o);
         if (orient_mode == 0) compute_orientations(py, P, o, ow, oh);
         else orientations_step(py, P, o, ow, oh, orient_mode, orient_in, &inject_off);
@@ -254,6 +260,49 @@ int NMREF(sift_frame)(const float* image_host, int w, int h, const float* cfg6,
         if (x) cudaMemcpy(x, raw(data._x), n * sizeof(float), cudaMemcpyDeviceToHost);
         if (y) cudaMemcpy(y, raw(data._y), n * sizeof(float), cudaMemcpyDeviceToHost);
     }
+    return P._num_octaves;
+}
+
+// The same with the reference's masked detector (compute_keypoints_with_mask, siftfunctions.cu:65-98):
+// mask_host = w*h floats, bound the way a client binds it -- a float cudaArray behind the reference's own
+// CudaTex2D (linear filter, border addressing, unnormalised coordinates, element-type reads, cudatex2D.cu:4-21).
+int NMREF(sift_frame_masked)(const float* image_host, int w, int h, const float* cfg6,
+                            float* desc, float* x, float* y, int* num_items,
+                            float* levels_out, float* kpts_out, float* orient_out, int* seg_counts,
+                            int kp_cap, float* grad_out, const float* orient_in, const float* mask_host)
+{
+    Cfg c = { cfg6[0], cfg6[1], (int)cfg6[2], (int)cfg6[3], (int)cfg6[4], (int)cfg6[5] };
+#ifndef NM_COMPAT_BUILD
+    if (c.orient_mode == 0 && !std::getenv("NMREF_ALLOW_DEADLOCK")) return -1;
+#else
+    if (c.orient_mode == 1) return -3;
+#endif
+    if (c.orient_mode == 2 && !orient_in) return -2;
+    if (!mask_host) return -4;
+    SiftParams P = make_params(w, h, c);
+    PyramidData py(P);
+    SiftData data(c.capacity > 0 ? c.capacity : MAX_DESCRIPTORS);
+    thrust::device_vector<float> img(image_host, image_host + (size_t)w * h);
+    cudaArray* arr = nullptr;
+    cudaChannelFormatDesc desc_f = cudaCreateChannelDesc<float>();
+    if (cudaMallocArray(&arr, &desc_f, w, h) != cudaSuccess) return -5;
+    cudaMemcpy2DToArray(arr, 0, 0, mask_host, (size_t)w * sizeof(float), (size_t)w * sizeof(float), h,
+                        cudaMemcpyHostToDevice);
+    int n = 0;
+    {
+        CudaTex2D tex;
+        tex.set(arr, cudaReadModeElementType);                   // float texels read as they are
+        run_frame(raw(img), w, h, P, py, data, c.clear_grad, c.orient_mode, orient_in, levels_out, kpts_out,
+                  orient_out, seg_counts, kp_cap, grad_out, (cudaTextureObject_t)tex);
+        n = data._num_items;
+        *num_items = n;
+        if (n > 0) {
+            if (desc) cudaMemcpy(desc, raw(data._desc), (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToHost);
+            if (x) cudaMemcpy(x, raw(data._x), n * sizeof(float), cudaMemcpyDeviceToHost);
+            if (y) cudaMemcpy(y, raw(data._y), n * sizeof(float), cudaMemcpyDeviceToHost);
+        }
+    }
+    cudaFreeArray(arr);
     return P._num_octaves;
 }
 

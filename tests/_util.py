@@ -30,15 +30,19 @@ class FrameChecker:
         self.lib, self.prefix = lib, prefix
         self._frame = getattr(lib, prefix + "_sift_frame")
         self._frame.restype = C.c_int
+        self._frame_masked = getattr(lib, prefix + "_sift_frame_masked", None)
+        if self._frame_masked is not None:
+            self._frame_masked.restype = C.c_int
         self._match = getattr(lib, prefix + "_match")
         self._match.restype = C.c_int
 
     def sift_frame(self, image, peak=0.0, edge=-1.0, num_octaves=-1, capacity=65536, clear_grad=1,
-                   kp_cap=200000, want_levels=True, want_grad=False, orient_mode=None, orient_in=None):
+                   kp_cap=200000, want_levels=True, want_grad=False, orient_mode=None, orient_in=None, mask=None):
         """orient_mode: 0 = public-API orientation semantics (window clamp 10; the reference's
         own kernel deadlocks on sm_70+, so the reference build refuses it), 1 = arithmetic of the
         reference's kernel_orientations_naive (no clamp), 2 = injected orientations.
-        Default: 0 for the CPU oracle, 1 for the reference build."""
+        Default: 0 for the CPU oracle, 1 for the reference build.
+        mask: optional h x w float image -> the masked detector (compute_keypoints_with_mask)."""
         if orient_mode is None:
             orient_mode = 0 if self.prefix == "orc" else 1
         if orient_in is not None:
@@ -57,8 +61,14 @@ class FrameChecker:
         kpts = np.zeros((kp_cap, 4), np.float32)
         orient = np.zeros((kp_cap, 2), np.float32)
         seg = np.zeros(max_oct * 3, np.int32)
-        n_oct = self._frame(_p(image), w, h, _p(cfg), _p(desc), _p(x), _p(y), C.byref(n), _p(levels), _p(kpts),
-                            _p(orient), _p(seg), kp_cap, _p(grad), _p(orient_in))
+        if mask is None:
+            n_oct = self._frame(_p(image), w, h, _p(cfg), _p(desc), _p(x), _p(y), C.byref(n), _p(levels), _p(kpts),
+                                _p(orient), _p(seg), kp_cap, _p(grad), _p(orient_in))
+        else:
+            mask = np.ascontiguousarray(mask, dtype=np.float32)
+            assert mask.shape == (h, w) and self._frame_masked is not None
+            n_oct = self._frame_masked(_p(image), w, h, _p(cfg), _p(desc), _p(x), _p(y), C.byref(n), _p(levels),
+                                       _p(kpts), _p(orient), _p(seg), kp_cap, _p(grad), _p(orient_in), _p(mask))
         if n_oct < 0:
             raise RuntimeError(f"{self.prefix}_sift_frame refused (code {n_oct}): orient_mode {orient_mode}")
         out = {"n_oct": n_oct, "n": n.value, "desc": desc[: n.value], "x": x[: n.value], "y": y[: n.value],

@@ -3,7 +3,8 @@ by oracle/build_ref.sh from /root/reference) on a B200.  Run on the GPU box:
 
     python tests/golden/make_golden.py gpurun_out/golden
 
-and copy the .npz files into tests/golden/.  The fixtures pin the CPU oracle
+and copy the .npz files into tests/golden/ (`... gpurun_out/golden masked` regenerates only the
+masked-detector fixture).  The fixtures pin the CPU oracle
 (tests/test_oracle_golden.py, no GPU needed) and the CUDA product (tests/test_gpu_*.py).
 
 What the reference can and cannot produce on sm_100: everything up to the collated
@@ -45,6 +46,43 @@ def crafted_match_sets():
     A[3] = B[20] + 1.0
     m0 = np.full(200, 77, np.int32)           # sentinel initial values
     return A.astype(np.float32), B.astype(np.float32), m0
+
+
+def detector_masks(w, h):
+    """Masks for compute_keypoints_with_mask: a fetoscope-style circular field of view (binary), and a
+    mask with a half-valued ring and a rectangular hole (exercises the `< 1` test on filtered samples:
+    in octaves >= 1 the sample is the mean of four texels)."""
+    yy, xx = np.mgrid[0:h, 0:w]
+    r2 = (xx - w / 2 + 0.5) ** 2 + (yy - h / 2 + 0.5) ** 2
+    fov = (r2 < (0.42 * h) ** 2).astype(np.float32)
+    soft = np.where(r2 < (0.46 * h) ** 2, 1.0, 0.0).astype(np.float32)
+    soft[(r2 >= (0.40 * h) ** 2) & (r2 < (0.46 * h) ** 2)] = 0.5
+    soft[h // 3: h // 3 + 21, w // 4: w // 4 + 37] = 0.0
+    return {"fov": fov, "soft": soft}
+
+
+def masked(outdir):
+    """compute_keypoints_with_mask of the reference (siftfunctions.cu:65-98) on a float mask texture."""
+    os.makedirs(outdir, exist_ok=True)
+    ref, orc = load_reflib(), load_oracle()
+    assert ref is not None, "oracle/_ref/libnmref.so missing"
+    w, h = 256, 192
+    img = synth.scene(w, h, synth.SEED_BASE)
+    out = {"image": img}
+    for name, mask in detector_masks(w, h).items():
+        r = ref.sift_frame(img, peak=0.0, want_levels=False, orient_mode=1, mask=mask)
+        c = orc.sift_frame(img, peak=0.0, want_levels=False, orient_mode=0, mask=mask)
+        assert np.array_equal(r["seg_counts"], c["seg_counts"]), (name, r["seg_counts"], c["seg_counts"])
+        ri = ref.sift_frame(img, peak=0.0, want_levels=False, orient_mode=2, orient_in=c["orient"], mask=mask)
+        out[f"{name}_mask"] = mask
+        out[f"{name}_seg_counts"] = r["seg_counts"]
+        out[f"{name}_kpts"] = r["kpts"]
+        out[f"{name}_orient_in"] = c["orient"]
+        out[f"{name}_desc"] = ri["desc"]
+        out[f"{name}_x"] = ri["x"]
+        out[f"{name}_y"] = ri["y"]
+        print("masked", name, "n =", r["n"], r["seg_counts"])
+    np.savez_compressed(os.path.join(outdir, f"sift_{w}x{h}_masked.npz"), **out)
 
 
 def main(outdir):
@@ -105,4 +143,9 @@ def main(outdir):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"))
+    out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
+    if len(sys.argv) > 2 and sys.argv[2] == "masked":      # only the masked-detector fixture
+        masked(out)
+    else:
+        main(out)
+        masked(out)

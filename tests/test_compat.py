@@ -110,6 +110,25 @@ def test_reference_client_on_dropin_matches_reference_golden(oracle):
 
 
 @pytest.mark.gpu
+def test_reference_client_masked_detector_on_dropin(oracle):
+    """compute_keypoints_with_mask through the drop-in headers / libraries, driven by the same client code
+    that drove the reference (a float cudaArray behind CudaTex2D): keypoints bitwise the reference's."""
+    if not os.path.exists(CLIENT):
+        pytest.skip("build/compat/libnmcompat.so not built")
+    from tests._util import FrameChecker, GOLDEN
+    cl = FrameChecker(C.CDLL(CLIENT), "nmcompat")
+    g = np.load(os.path.join(GOLDEN, "sift_256x192_masked.npz"))
+    img = g["image"]
+    for name in ("fov", "soft"):
+        r = cl.sift_frame(img, peak=0.0, orient_mode=0, want_levels=False, mask=g[f"{name}_mask"])
+        assert np.array_equal(r["seg_counts"], g[f"{name}_seg_counts"][: len(r["seg_counts"])]), name
+        assert np.array_equal(r["kpts"], g[f"{name}_kpts"]), name
+        rel = np.linalg.norm(r["desc"] - g[f"{name}_desc"], axis=1) / np.linalg.norm(g[f"{name}_desc"], axis=1)
+        assert rel.max() < 1e-3, rel.max()
+        assert np.array_equal(r["x"], g[f"{name}_x"]) and np.array_equal(r["y"], g[f"{name}_y"])
+
+
+@pytest.mark.gpu
 def test_reference_client_matcher_on_dropin():
     if not os.path.exists(CLIENT):
         pytest.skip("build/compat/libnmcompat.so not built")

@@ -341,6 +341,44 @@ def test_run_host_end_to_end(nm, oracle):
     sb.close()
 
 
+def test_masked_detector_batched_vs_reference_and_oracle(nm, oracle):
+    """compute_keypoints_with_mask in the batched path (nm_sift_set_mask_image): keypoints bitwise the
+    reference's (tests/golden, captured from compute_keypoints_with_mask on a B200) and the oracle's;
+    descriptors within tolerance; removing the mask restores the unmasked result."""
+    g = _gold("sift_256x192_masked.npz")
+    img = g["image"]
+    P = nm.SiftParams(256, 192)
+    sb = nm.SiftBatch(P, 2, 4096)
+    frames = _cu(np.stack([img, img]))
+
+    def grab(f):
+        r = sb.results()
+        seg = r["seg_counts"][f].cpu().numpy()
+        n = int(r["counts"][f].item())
+        return {"n": n, "seg_counts": seg, "kpts": r["kpts"][f, :int(seg.sum())].cpu().numpy(),
+                "orient": r["orient"][f, :int(seg.sum())].cpu().numpy(), "desc": r["desc"][f, :n].cpu().numpy(),
+                "x": r["x"][f, :n].cpu().numpy(), "y": r["y"][f, :n].cpu().numpy()}
+
+    for name in ("fov", "soft"):
+        mask = g[f"{name}_mask"]
+        sb.set_mask(mask if name == "fov" else _cu(mask))          # host and device mask images
+        sb.run(frames)
+        torch.cuda.synchronize()
+        c = oracle.sift_frame(img, peak=0.0, want_levels=False, mask=mask)
+        for f in range(2):
+            p = grab(f)
+            assert np.array_equal(p["seg_counts"], g[f"{name}_seg_counts"][: len(p["seg_counts"])]), name
+            assert np.array_equal(p["kpts"], g[f"{name}_kpts"]), name
+            assert_frame_matches(p, c, check_levels=False)
+            relg = np.linalg.norm(p["desc"] - g[f"{name}_desc"], axis=1) / np.linalg.norm(g[f"{name}_desc"], axis=1)
+            assert relg.max() <= 1e-3
+    sb.set_mask(None)
+    sb.run(frames)
+    torch.cuda.synchronize()
+    assert_frame_matches(grab(1), oracle.sift_frame(img, peak=0.0, want_levels=False), check_levels=False)
+    sb.close()
+
+
 def test_run_host_pipeline_equals_device_run(nm):
     """nm_sift_run_host splits a batch into stages of a few frames that run concurrently on several
     streams (H2D, kernels and D2H overlapped).  20 frames = 4 stages: counts, descriptors and coordinates

@@ -94,6 +94,31 @@ def test_sift_frame_against_reference(oracle, name):
         assert np.array_equal(c0["orient"], g[f"{tag}_orient_in"])
 
 
+def test_masked_detector_against_reference(oracle):
+    """compute_keypoints_with_mask (siftfunctions.cu:65-98): the oracle's restatement of the mask texture
+    sample (linear filter at block centres, border addressing) against the reference run on a B200 with a
+    binary field-of-view mask and a mask with half-valued texels."""
+    g = _load("sift_256x192_masked.npz")
+    img = g["image"]
+    unmasked = oracle.sift_frame(img, peak=0.0, want_levels=False)
+    for name in ("fov", "soft"):
+        mask = g[f"{name}_mask"]
+        r = oracle.sift_frame(img, peak=0.0, want_levels=False, mask=mask)
+        assert np.array_equal(r["seg_counts"], g[f"{name}_seg_counts"]), name
+        assert np.array_equal(r["kpts"], g[f"{name}_kpts"]), name
+        assert np.array_equal(r["orient"], g[f"{name}_orient_in"])
+        assert 0 < r["n"] < unmasked["n"]
+        # the mask only removes candidates: every surviving keypoint is one of the unmasked run
+        all_kp = {tuple(k) for k in unmasked["kpts"]}
+        assert all(tuple(k) in all_kp for k in r["kpts"])
+        c = oracle.sift_frame(img, peak=0.0, want_levels=False, orient_mode=2, orient_in=g[f"{name}_orient_in"], mask=mask)
+        ref_d = g[f"{name}_desc"]
+        assert c["n"] == len(ref_d)
+        rel = np.linalg.norm(c["desc"] - ref_d, axis=1) / np.maximum(np.linalg.norm(ref_d, axis=1), 1e-20)
+        assert rel.max() <= DESC_REL_TOL, rel.max()
+        assert np.array_equal(c["x"], g[f"{name}_x"]) and np.array_equal(c["y"], g[f"{name}_y"])
+
+
 def test_match_against_reference(oracle):
     g = _load("match_200x250.npz")
     m, D = oracle.match(g["A"], g["B"], 0.8, match_io=g["m0"], want_distance=True)
