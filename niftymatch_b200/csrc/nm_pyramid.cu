@@ -15,6 +15,9 @@
 // shared-memory port, is the limiter.  Each output accumulates k = -R..R in the
 // reference's order with explicit fmaf, so the result is bitwise the reference's.
 // Algorithmic traffic: 8 B/pixel/level (one read, one write).
+// Large launches (octaves 0 and 1 of a batch) take blur_strip_kernel below, which walks down
+// 128-column strips and keeps the row-pass result in a shared-memory ring, so no halo row is
+// convolved twice.
 //
 // The input window is fetched by TMA (cp.async.bulk.tensor.3d, one elected thread, mbarrier
 // completion): the hardware zero-fills everything outside the (w, h) tensor, which is
@@ -228,6 +231,178 @@ __global__ void __launch_bounds__(kThreads, 2) blur_walk_kernel(const NmBlurArgs
     }
 }
 
+// ---- strip-walking variant: no redundant row-pass work ------------------------------------------
+// blur_tile/blur_walk run the row pass over all 64 + 2R staged rows of every 64-row tile, i.e. the 2R
+// halo rows are convolved twice (R = 13: 41 % more row-pass FMAs, and the FMA pipe is what bounds the
+// kernel).  Here a CTA walks DOWN a 128-column strip in chunks of 64 input rows: the row pass of chunk c
+// (row-pass rows i = 64c .. 64c+63, i = image row + R) goes to one half of a 128-row ring in shared
+// memory, and the column pass then emits the 64 output rows whose 2R+1 inputs are now complete
+// (y = 64c - 2R .. 64c + 63 - 2R), reading the 2R carried rows from the other half.  Every row-pass
+// row is computed once per strip.  The launch's chunks (strips x chunks-per-strip) are split evenly over
+// the persistent CTAs; a CTA whose range starts inside a strip first runs the row pass of the last 2R
+// rows of the previous chunk.  Arithmetic per output is unchanged (bitwise the reference).
+constexpr int kCH = 64;            // input rows per chunk
+constexpr int kRing = 128;         // ring rows (>= kCH + 2R for R <= 16; power of two)
+__host__ __device__ constexpr int strip_smem_bytes(int R)
+{
+    return (kCH * in_pitch(R) + kRing * kRowPitch) * (int)sizeof(float) + 16 + 128;
+}
+
+template <int R>
+__device__ __forceinline__ void strip_row_pass(const float* __restrict__ s_in, float* __restrict__ s_ring,
+                                               const float (&t)[2 * R + 1], int tid, int ring_base, int r_begin,
+                                               int y_first, int h)
+{
+    constexpr int SH = radius_aligned(R) - R, IP = in_pitch(R), NT = 2 * R + 1;
+    constexpr int P = 8;
+    constexpr int NV = (SH + P + 2 * R + 3) / 4;
+    for (int it = tid; it < kCH * (kTW / P); it += kThreads) {
+        const int xs = it >> 6, r = it & (kCH - 1);
+        if (r < r_begin) continue;
+        float2* o2 = reinterpret_cast<float2*>(s_ring + (ring_base + r) * kRowPitch + xs * P);
+        const int y = y_first + r;
+        if (y < 0 || y >= h) {                  // zero padding rows: the row pass of zeros
+#pragma unroll
+            for (int j = 0; j < P / 2; ++j) o2[j] = make_float2(0.f, 0.f);
+            continue;
+        }
+        float wv[NV * 4 + 1];
+        const float4* p4 = reinterpret_cast<const float4*>(s_in + r * IP + xs * P);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const float4 q = p4[j];
+            wv[4 * j] = q.x; wv[4 * j + 1] = q.y; wv[4 * j + 2] = q.z; wv[4 * j + 3] = q.w;
+        }
+        wv[NV * 4] = 0.f;
+        // Taps whose window offset is even read aligned register pairs (FFMA2); for the odd ones an FFMA2 would
+        // need pairs that straddle two aligned pairs, which the compiler can only build with MOVs (61 per item,
+        // R = 10: a quarter of the row pass's issue slots) -- those taps are issued as scalar FFMAs instead.
+        float acc[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < NT; ++kk) {
+            if (((SH + kk) & 1) == 0) {
+#pragma unroll
+                for (int j = 0; j < P / 2; ++j) {
+                    const float2 d = nm_ffma2(make_float2(wv[SH + 2 * j + kk], wv[SH + 2 * j + kk + 1]), t[2 * R - kk],
+                                              make_float2(acc[2 * j], acc[2 * j + 1]));
+                    acc[2 * j] = d.x; acc[2 * j + 1] = d.y;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < P; ++j) acc[j] = __fmaf_rn(wv[SH + j + kk], t[2 * R - kk], acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < P / 2; ++j) o2[j] = make_float2(acc[2 * j], acc[2 * j + 1]);
+    }
+}
+
+template <int R, bool WRAP>
+__device__ __forceinline__ void strip_col_item(const float* __restrict__ s_ring, const NmBlurArgs& a, float* __restrict__ dst,
+                                               const float (&t)[2 * R + 1], int cp, int gx, int gy0, int f)
+{
+    constexpr int NT = 2 * R + 1;
+    constexpr int P = 8;
+    float2 wv[P + 2 * R];
+    if (WRAP) {
+        // the window crosses the end of the ring once, after n1 rows (warp-uniform)
+        const int lo = gy0 & (kRing - 1), n1 = kRing - lo;
+        const float* p_lo = s_ring + lo * kRowPitch + 2 * cp;
+        const float* p_hi = p_lo - kRing * kRowPitch;
+#pragma unroll
+        for (int j = 0; j < P + 2 * R; ++j)
+            wv[j] = *reinterpret_cast<const float2*>((j < n1 ? p_lo : p_hi) + j * kRowPitch);
+    } else {
+        const float* p = s_ring + (gy0 & (kRing - 1)) * kRowPitch + 2 * cp;
+#pragma unroll
+        for (int j = 0; j < P + 2 * R; ++j) wv[j] = *reinterpret_cast<const float2*>(p + j * kRowPitch);
+    }
+    float2 acc[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int kk = 0; kk < NT; ++kk)
+#pragma unroll
+        for (int j = 0; j < P; ++j) acc[j] = nm_ffma2(wv[j + kk], t[2 * R - kk], acc[j]);
+    float* o = dst + (long long)gy0 * a.dst_pitch + gx;
+    const bool two = gx + 1 < a.w;
+    const bool vec = two && !(a.dst_pitch & 1) && !(reinterpret_cast<uintptr_t>(dst) & 7);
+#pragma unroll
+    for (int j = 0; j < P; ++j)
+        if (gy0 + j >= 0 && gy0 + j < a.h) {
+            float* oj = o + (long long)j * a.dst_pitch;
+            if (vec) *reinterpret_cast<float2*>(oj) = acc[j];
+            else { oj[0] = acc[j].x; if (two) oj[1] = acc[j].y; }
+        }
+    if (a.dst2 != nullptr && (gx >> 1) < (a.w >> 1)) {
+        float* o2 = a.dst2 + (long long)f * a.dst2_fstride + (gx >> 1);
+#pragma unroll
+        for (int j = 0; j < P; j += 2) {
+            const int gy = gy0 + j;              // gy0 is even (64c - 2R + 8 ys)
+            if (gy >= 0 && (gy >> 1) < (a.h >> 1)) o2[(long long)(gy >> 1) * a.dst2_pitch] = acc[j].x;
+        }
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(kThreads, 2) blur_strip_kernel(const NmBlurArgs a, const __grid_constant__ CUtensorMap tmap,
+                                                                 int tiles_x, int chunks, long long total)
+{
+    constexpr int RA = radius_aligned(R), IP = in_pitch(R), NT = 2 * R + 1;
+    extern __shared__ __align__(128) float smem[];
+    float* s_in = smem;                        // [kCH][IP]
+    float* s_ring = smem + kCH * IP;           // [kRing][kRowPitch]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_ring + kRing * kRowPitch);
+    const int tid = threadIdx.x;
+    const long long g0 = total * blockIdx.x / gridDim.x, g1 = total * (blockIdx.x + 1) / gridDim.x;
+    if (g0 >= g1) return;
+    // a range that starts inside a strip is preceded by the row pass of the previous chunk's last 2R rows
+    long long g = (g0 % chunks) ? g0 - 1 : g0;
+    int c = (int)(g % chunks), tx, f;
+    {
+        const int s = (int)(g / chunks);
+        tx = s % tiles_x; f = s / tiles_x;
+    }
+    auto issue = [&](int cc, int txx, int ff) {
+        mbar_expect_tx(bar, kCH * IP * (uint32_t)sizeof(float));
+        tma_load_3d(s_in, &tmap, bar, txx * kTW - RA, cc * kCH - R, ff);
+    };
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue(c, tx, f);
+    }
+    float t[NT];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) t[k] = __ldg(a.taps + k);
+    __syncthreads();
+    for (uint32_t phase = 0; g < g1; ++g, phase ^= 1) {
+        const bool pre = g < g0;
+        // position of the next chunk: down the strip, then the next strip of the frame, then the next frame
+        int nc = c + 1, ntx = tx, nf = f;
+        if (nc == chunks) { nc = 0; if (++ntx == tiles_x) { ntx = 0; ++nf; } }
+        mbar_wait(bar, phase);
+        strip_row_pass<R>(s_in, s_ring, t, tid, (c & 1) * kCH, pre ? kCH - 2 * R : 0, c * kCH - R, a.h);
+        __syncthreads();                       // window consumed, ring rows visible
+        if (tid == 0 && g + 1 < g1) issue(nc, ntx, nf);
+        if (!pre) {
+            float* __restrict__ dst = a.dst + (long long)f * a.dst_fstride;
+            for (int it = tid; it < (kTW / 2) * (kCH / 8); it += kThreads) {
+                const int ys = it / (kTW / 2), cp = it - ys * (kTW / 2);
+                const int gx = tx * kTW + 2 * cp;
+                const int gy0 = c * kCH - 2 * R + ys * 8;
+                if (gx >= a.w || gy0 + 8 <= 0 || gy0 >= a.h) continue;
+                if ((gy0 & (kRing - 1)) + 8 + 2 * R <= kRing) strip_col_item<R, false>(s_ring, a, dst, t, cp, gx, gy0, f);
+                else strip_col_item<R, true>(s_ring, a, dst, t, cp, gx, gy0, f);
+            }
+        }
+        c = nc; tx = ntx; f = nf;
+        __syncthreads();                       // the next row pass overwrites ring rows this pass read
+    }
+}
+
 template <int R, bool TMA>
 __global__ void __launch_bounds__(kThreads, 2) blur_tile_kernel(const NmBlurArgs a, const __grid_constant__ CUtensorMap tmap)
 {
@@ -334,8 +509,22 @@ int launch_tile(const NmBlurArgs& a, cudaStream_t stream, const NmBlurTma* tma)
             NM_CUDA_TRY(cudaFuncSetAttribute(blur_walk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         }
         const long long n_tiles = (long long)grid.x * grid.y * grid.z;
-        static const bool no_walk = getenv("NM_BLUR_TILE") != nullptr;        // tuning aid
-        if (!no_walk && n_tiles >= 4LL * n_sms && n_tiles < (1LL << 31))
+        static const bool no_walk = getenv("NM_BLUR_TILE") != nullptr;        // tuning aids
+        static const bool no_strip = no_walk || getenv("NM_BLUR_WALK") != nullptr;
+        const int chunks = nm_div_up(a.h + 2 * R, kCH);
+        const long long total = (long long)grid.x * a.batch * chunks;
+        // below ~8 chunks per CTA the lead-in row pass of a range that starts inside a strip costs more
+        // than the tile kernels' halo rows; NM_BLUR_STRIP_MIN overrides the threshold (tests force 1)
+        static const long long strip_min = getenv("NM_BLUR_STRIP_MIN") ? atoll(getenv("NM_BLUR_STRIP_MIN")) : 16LL * n_sms;
+        if (!no_strip && tma->valid_strip && total >= strip_min && (long long)grid.x * a.batch < (1LL << 31)) {
+            static bool strip_configured = false;
+            if (!strip_configured) {
+                NM_CUDA_TRY(cudaFuncSetAttribute(blur_strip_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 strip_smem_bytes(R)));
+                strip_configured = true;
+            }
+            blur_strip_kernel<R><<<2 * n_sms, kThreads, strip_smem_bytes(R), stream>>>(a, tma->map_strip, (int)grid.x, chunks, total);
+        } else if (!no_walk && n_tiles >= 4LL * n_sms && n_tiles < (1LL << 31))
             blur_walk_kernel<R><<<2 * n_sms, kThreads, smem, stream>>>(a, tma->map, (int)grid.x, (int)grid.y, (int)n_tiles);
         else
             blur_tile_kernel<R, true><<<grid, kThreads, smem, stream>>>(a, tma->map);
@@ -401,7 +590,7 @@ __global__ void gradient_kernel(const float* __restrict__ src, float2* __restric
 bool nm_tma_encode_3d(NmBlurTma* t, const float* base, const unsigned long long dims[3],
                       const unsigned long long strides_bytes[2], const unsigned box[3])
 {
-    t->valid = false;
+    t->valid = t->valid_strip = false;
     if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides_bytes[0] & 15) || (strides_bytes[1] & 15)) return false;
     EncodeTiledFn enc = get_encoder();
     if (!enc) return false;
@@ -419,7 +608,7 @@ bool nm_tma_encode_3d(NmBlurTma* t, const float* base, const unsigned long long 
 bool nm_blur_make_tma(NmBlurTma* t, const float* src, int w, int h, int pitch, long long fstride,
                       int batch, int radius)
 {
-    t->valid = false;
+    t->valid = t->valid_strip = false;
     if (radius < 1 || radius > 16 || w <= 0 || h <= 0 || batch <= 0) return false;
     if ((reinterpret_cast<uintptr_t>(src) & 15) || (pitch & 3) || (batch > 1 && (fstride & 3))) return false;
     EncodeTiledFn enc = get_encoder();
@@ -432,6 +621,13 @@ bool nm_blur_make_tma(NmBlurTma* t, const float* src, int w, int h, int pitch, l
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     t->valid = (r == CUDA_SUCCESS);
+    if (t->valid) {
+        const cuuint32_t box_strip[3] = {(cuuint32_t)in_pitch(radius), (cuuint32_t)kCH, 1};
+        r = enc(&t->map_strip, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(src), dims, strides, box_strip, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        t->valid_strip = (r == CUDA_SUCCESS);
+    }
     return t->valid;
 }
 

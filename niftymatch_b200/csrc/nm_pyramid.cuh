@@ -19,6 +19,8 @@ struct NmBlurArgs {
 struct NmBlurTma {
     CUtensorMap map;
     bool        valid;
+    CUtensorMap map_strip;      // same tensor, box of 64 rows: the strip-walking kernel's chunk
+    bool        valid_strip;
 };
 // Returns false when the source cannot be described to TMA (pointer / pitch not 16-byte
 // aligned, radius outside the tiled kernel's range): the caller then uses the plain-load

@@ -108,7 +108,7 @@ def test_blur_vs_reference_golden(nm):
     assert np.array_equal(out.cpu().numpy(), g["result"])
 
 
-@pytest.mark.parametrize("shape", [(77, 131), (64, 128), (1, 5), (200, 33), (130, 260)])
+@pytest.mark.parametrize("shape", [(77, 131), (64, 128), (1, 5), (200, 33), (130, 260), (700, 300)])
 @pytest.mark.parametrize("radius", [1, 4, 5, 7, 8, 10, 13, 16, 20])
 def test_blur_vs_oracle_bitwise(nm, oracle, shape, radius):
     from niftymatch_b200 import sift as S
@@ -324,6 +324,33 @@ def test_1080p_single_frame_vs_oracle(nm, oracle):
     c = oracle.sift_frame(img, capacity=16384)
     assert_frame_matches(p, c)
     assert p["n"] > 5000
+
+
+def test_1080p_batch_strip_blur_vs_oracle(nm, oracle):
+    """Ten 1080p frames: octave 0 of a batch this size takes the strip-walking blur kernel
+    (nm_pyramid.cu, blur_strip_kernel); first and last frame against the CPU oracle, levels bitwise."""
+    frames = np.stack([synth.scene(1920, 1080, synth.SEED_BASE + (i % 2)) for i in range(10)])
+    out = run_product(nm, frames, capacity=16384)
+    for f in (0, 9):
+        c = oracle.sift_frame(frames[f], capacity=16384)
+        assert_frame_matches(out[f], c)
+
+
+def test_forced_strip_blur_parity_suite():
+    """The strip-walking blur is only chosen for large launches; NM_BLUR_STRIP_MIN=1 forces it for every
+    TMA-describable source, and the blur / SIFT parity tests are re-run that way in a child process
+    (ranges that start inside a strip, one-chunk strips, 1-row images, the decimated second output)."""
+    import subprocess
+    import sys
+    if os.environ.get("NM_BLUR_STRIP_MIN"):
+        pytest.skip("already the forced run")
+    env = dict(os.environ, NM_BLUR_STRIP_MIN="1")
+    sel = ("test_blur_vs_oracle_bitwise or test_blur_vs_reference_golden or test_sift_vs_oracle or "
+           "test_sift_vs_reference_golden or test_4k_six_octave or test_forced_octave_count")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", __file__, "-k", sel],
+                       env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
 
 
 def test_run_host_end_to_end(nm, oracle):
