@@ -9,10 +9,10 @@
 //             src/gpu/utils/{cudatex2D.h:11-53, cudatimer.h:14-40, exception.h:27-86}
 //   functions src/gpu/sift/siftfunctions.h:19-101, src/gpu/kernels/{convolution.h:20,
 //             downsample.h, cudamath.h:18-87, keypoint.h:25-63, orientation.h:19,
-//             descriptor.h:25, match.h:19-46, transpose.h:17}
+//             descriptor.h:25, match.h:19-46, transpose.h:17, ransac.h:8-22}
 // The bodies (compat/src/*.cu) unwrap thrust vectors to raw pointers, call the C-ABI and turn a
-// non-zero status into the reference's exception type.  Out of scope (not provided): ransac.h,
-// resample.h, undistort.h, bgra_2_gray.h, cast.h, cudautils.h.
+// non-zero status into the reference's exception type.  ransac.h (align_points, ransac_*) is served
+// too.  Out of scope (not provided): resample.h, undistort.h, bgra_2_gray.h, cast.h, cudautils.h.
 #ifndef NM_COMPAT_HPP
 #define NM_COMPAT_HPP
 
@@ -259,6 +259,23 @@ void get_sift_matches(const TYPE* distance, const int rows, const int cols, cons
 
 template <typename TYPE>
 void transpose(TYPE* odata, const TYPE* idata, int width, int height, cudaStream_t stream = 0);
+
+// ---- gpu/kernels/ransac.h:8-22 -------------------------------------------------------------------
+void align_points(const float* src_x, const float* src_y, const float* dst_x, const float* dst_y,
+                  float* c_src_x, float* c_src_y, float* c_dst_x, float* c_dst_y,
+                  const int* matches, const int num_pts, cudaStream_t stream = 0);
+// The reference seeds std::mt19937 from std::random_device on every call; so do these wrappers, unless the
+// environment variable NM_RANSAC_SEED holds a number (reproducible runs).  They block on `stream` to
+// return the reference's bool (false: fewer than 2 / 4 usable correspondences, `homography` untouched).
+bool ransac_homography(float* src_x, float* src_y, float* dst_x, float* dst_y,
+                       const int src_size, const int dst_size, float inlier_threshold,
+                       int iterations, float* homography, cudaStream_t stream = 0);
+bool ransac_translation(float* src_x, float* src_y, float* dst_x, float* dst_y,
+                        const int src_size, const int dst_size, float inlier_threshold,
+                        int iterations, float* homography, cudaStream_t stream = 0);
+bool ransac_similarity(float* src_x, float* src_y, float* dst_x, float* dst_y,
+                       const int src_size, const int dst_size, float inlier_threshold,
+                       int iterations, float* homography, cudaStream_t stream = 0);
 
 // ---- gpu/sift/siftfunctions.h ------------------------------------------------------------------
 void compute_sift_matches(SiftData* A, SiftData* B, float* distance, float ambiguity = 0.8f,

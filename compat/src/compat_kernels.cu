@@ -111,3 +111,54 @@ void transpose<float>(float* odata, const float* idata, int width, int height, c
 {
     nm_check(nm_transpose_f32(odata, idata, width, height, stream), "transpose");
 }
+
+// ransac.h:8-22 (ransac.cu:50-59, :526-694)
+#include <random>
+void align_points(const float* src_x, const float* src_y, const float* dst_x, const float* dst_y, float* c_src_x,
+                  float* c_src_y, float* c_dst_x, float* c_dst_y, const int* matches, const int num_pts, cudaStream_t stream)
+{
+    nm_check(nm_align_points_f32(src_x, src_y, dst_x, dst_y, c_src_x, c_src_y, c_dst_x, c_dst_y, matches, num_pts, stream),
+             "align_points");
+}
+
+namespace {
+bool ransac_any(int kind, const float* src_x, const float* src_y, const float* dst_x, const float* dst_y, int src_size,
+                float inlier_threshold, int iterations, float* homography, cudaStream_t stream, const char* what)
+{
+    unsigned long long seed;
+    if (const char* e = std::getenv("NM_RANSAC_SEED")) seed = std::strtoull(e, nullptr, 0);
+    else {
+        std::random_device seeder;                       // ransac.cu:546: a fresh seed per call
+        seed = ((unsigned long long)seeder() << 32) | seeder();
+    }
+    int* status = nullptr;
+    if (cudaMallocAsync(&status, 3 * sizeof(int), stream) != cudaSuccess) RUNTIME_EXCEPTION(std::string(what) + ": allocation failed");
+    const int rc = nm_ransac_f32(kind, src_x, src_y, dst_x, dst_y, src_size, inlier_threshold, iterations, seed, homography,
+                                 status, stream);
+    int h[3] = {0, 0, 0};
+    cudaMemcpyAsync(h, status, sizeof(h), cudaMemcpyDeviceToHost, stream);
+    cudaFreeAsync(status, stream);
+    cudaStreamSynchronize(stream);
+    nm_check(rc, what);
+    return h[0] != 0;
+}
+} // namespace
+
+bool ransac_homography(float* src_x, float* src_y, float* dst_x, float* dst_y, const int src_size, const int,
+                       float inlier_threshold, int iterations, float* homography, cudaStream_t stream)
+{
+    return ransac_any(NM_RANSAC_HOMOGRAPHY, src_x, src_y, dst_x, dst_y, src_size, inlier_threshold, iterations, homography,
+                      stream, "ransac_homography");
+}
+bool ransac_translation(float* src_x, float* src_y, float* dst_x, float* dst_y, const int src_size, const int,
+                        float inlier_threshold, int iterations, float* homography, cudaStream_t stream)
+{
+    return ransac_any(NM_RANSAC_TRANSLATION, src_x, src_y, dst_x, dst_y, src_size, inlier_threshold, iterations, homography,
+                      stream, "ransac_translation");
+}
+bool ransac_similarity(float* src_x, float* src_y, float* dst_x, float* dst_y, const int src_size, const int,
+                       float inlier_threshold, int iterations, float* homography, cudaStream_t stream)
+{
+    return ransac_any(NM_RANSAC_SIMILARITY, src_x, src_y, dst_x, dst_y, src_size, inlier_threshold, iterations, homography,
+                      stream, "ransac_similarity");
+}

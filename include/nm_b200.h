@@ -180,6 +180,42 @@ int nm_match_tc_probe(const float* A, int nA, const float* B, int nB, float* rec
                       int* n_lists, float* scale, nm_stream_t stream);
 
 /* ------------------------------------------------------------------------ */
+/* Registration after matching: align_points and the    */
+/* three RANSAC estimators of gpu/kernels/ransac.h, Jacobi SVD of svd.cu.      */
+/* ------------------------------------------------------------------------ */
+
+/* align_points (gpu/kernels/ransac.h:8; ransac.cu:29-59): correspondence i is
+ * (src[i], dst[matches[i]]), or (-1,-1,-1,-1) when matches[i] == -1.  Device pointers. */
+int nm_align_points_f32(const float* src_x, const float* src_y, const float* dst_x, const float* dst_y,
+                        float* c_src_x, float* c_src_y, float* c_dst_x, float* c_dst_y,
+                        const int* matches, int num_pts, nm_stream_t stream);
+
+/* Estimator kinds. */
+#define NM_RANSAC_TRANSLATION 0   /* 1 correspondence / hypothesis (ransac.cu:467-486) */
+#define NM_RANSAC_SIMILARITY  1   /* 2 (ransac.cu:437-464, :322-435) */
+#define NM_RANSAC_HOMOGRAPHY  2   /* 4 (ransac.cu:488-520, :84-214) */
+
+/* The hypothesis stage on a caller-supplied index list -- what translation_kernel /
+ * similarity_transformation_kernel / homography_kernel compute: rand_list holds 1 / 2 / 4 indices per
+ * iteration; homographies[it*9..] and inliers[it] are written for every iteration (0 for an iteration
+ * with a repeated index).  inlier rule: squared reprojection error < inlier_threshold over the
+ * correspondences with src_x >= 0 (ransac.cu:61-82). */
+int nm_ransac_hypotheses_f32(int kind, const float* src_x, const float* src_y, const float* dst_x,
+                             const float* dst_y, int num_pts, const int* rand_list, int iterations,
+                             float inlier_threshold, float* homographies, int* inliers, nm_stream_t stream);
+
+/* ransac_translation / ransac_similarity / ransac_homography (gpu/kernels/ransac.h:12-22; ransac.cu:
+ * 526-694) without their host round trips: valid-index list, index draws (counter-based generator on
+ * `seed`: reproducible, where the reference seeds std::mt19937 from std::random_device), hypotheses,
+ * scores and the first-maximum selection all run on `stream`.  homography: 9 floats, device.
+ * status: 3 ints, device: {1 = model written | 0 = fewer than 2 (homography: 4) valid correspondences,
+ * the reference's `return false`, homography untouched; inliers of the chosen model; its iteration}. */
+int nm_ransac_f32(int kind, const float* src_x, const float* src_y, const float* dst_x, const float* dst_y,
+                  int num_pts, float inlier_threshold, int iterations, unsigned long long seed,
+                  float* homography, int* status, nm_stream_t stream);
+
+
+/* ------------------------------------------------------------------------ */
 /* Batched SIFT detect+describe: the client loop of the reference             */
 /* (compute_dog/_gradients/_keypoints/_orientations/_descriptors,             */
 /* gpu/sift/siftfunctions.h:30-101, driven per octave) for a batch of frames, */

@@ -60,6 +60,9 @@ SIGNATURES = {
     "nm_match_top2_f32": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
     "nm_match_merge_top2": (_i, [_vp, _i, _i, _f, _vp, _vp]),
     "nm_match_tc_probe": (_i, [_vp, _i, _vp, _i, _vp, C.POINTER(_i), _vp, _vp, C.POINTER(_i), C.POINTER(_f), _vp]),
+    "nm_align_points_f32": (_i, [_vp] * 9 + [_i, _vp]),
+    "nm_ransac_hypotheses_f32": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp, _i, _f, _vp, _vp, _vp]),
+    "nm_ransac_f32": (_i, [_i, _vp, _vp, _vp, _vp, _i, _f, _i, _ull, _vp, _vp, _vp]),
     "nm_match_set_engine": (_i, [_i]),
     "nm_match_get_engine": (_i, []),
     "nm_sift_create": (_i, [C.POINTER(_vp), C.POINTER(SiftParamsC), _i, _i]),

@@ -1,0 +1,52 @@
+"""Registration after matching through the C-ABI (nm_align_points_f32, nm_ransac_*): the
+reference's align_points / ransac_translation / ransac_similarity / ransac_homography
+(src/gpu/kernels/ransac.h:8-22)."""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _lib
+from ._lib import check
+from .sift import _stream_ptr
+
+TRANSLATION, SIMILARITY, HOMOGRAPHY = 0, 1, 2
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def align_points(src_x, src_y, dst_x, dst_y, matches):
+    """Correspondences (c_src_x, c_src_y, c_dst_x, c_dst_y): src[i] with dst[matches[i]], -1 where unmatched."""
+    import torch
+    n = matches.shape[0]
+    out = [torch.empty(n, dtype=torch.float32, device=src_x.device) for _ in range(4)]
+    check(_lib.load().nm_align_points_f32(_p(src_x), _p(src_y), _p(dst_x), _p(dst_y), *[_p(o) for o in out],
+                                          _p(matches), n, _stream_ptr()), "nm_align_points_f32")
+    return tuple(out)
+
+
+def ransac_hypotheses(kind, src_x, src_y, dst_x, dst_y, rand_list, inlier_threshold):
+    """All hypotheses of a caller-supplied index list: (iterations, 9) homographies and inlier counts."""
+    import torch
+    m = (1, 2, 4)[kind]
+    iterations = rand_list.numel() // m
+    H = torch.empty((iterations, 9), dtype=torch.float32, device=src_x.device)
+    inl = torch.empty(iterations, dtype=torch.int32, device=src_x.device)
+    check(_lib.load().nm_ransac_hypotheses_f32(kind, _p(src_x), _p(src_y), _p(dst_x), _p(dst_y), src_x.shape[0],
+                                               _p(rand_list), iterations, inlier_threshold, _p(H), _p(inl),
+                                               _stream_ptr()), "nm_ransac_hypotheses_f32")
+    return H, inl
+
+
+def ransac(kind, src_x, src_y, dst_x, dst_y, inlier_threshold, iterations, seed=0, homography=None):
+    """Best model of `iterations` random hypotheses; no host synchronisation.  Returns (homography (9,) cuda,
+    status (3,) cuda int32 = [ok, inliers, iteration])."""
+    import torch
+    if homography is None:
+        homography = torch.zeros(9, dtype=torch.float32, device=src_x.device)
+    status = torch.zeros(3, dtype=torch.int32, device=src_x.device)
+    check(_lib.load().nm_ransac_f32(kind, _p(src_x), _p(src_y), _p(dst_x), _p(dst_y), src_x.shape[0], inlier_threshold,
+                                    iterations, seed & 0xFFFFFFFFFFFFFFFF, _p(homography), _p(status), _stream_ptr()),
+          "nm_ransac_f32")
+    return homography, status

@@ -694,3 +694,225 @@ int orc_sift_batch(const float* frames, int n_frames, int w, int h, const float*
     }
     return 0;
 }
+
+/* ========================================================================= */
+/* align_points + RANSAC (gpu/kernels/ransac.cu) with  */
+/* the one-sided Jacobi SVD of gpu/kernels/svd.cu (the reference's port of    */
+/* GSL's gsl_linalg_SV_decomp_jacobi).  Restated from the published           */
+/* algorithm (Hestenes / Nash plane rotations with GSL's error-estimate       */
+/* skip rule) in the order of operations of the reference; fp32 throughout.   */
+/* Parity of the homographies is tolerance based (the CPU evaluates a*b+c*d   */
+/* without the GPU's FMA contractions; the null vector is determined up to     */
+/* rounding), see tests/test_oracle_golden.py.                                 */
+/* ========================================================================= */
+
+/* establish_correspondences (ransac.cu:29-48) */
+void orc_align_points(const float* src_x, const float* src_y, const float* dst_x, const float* dst_y,
+                      float* c_src_x, float* c_src_y, float* c_dst_x, float* c_dst_y,
+                      const int* matches, int num_pts)
+{
+    for (int i = 0; i < num_pts; ++i) {
+        const int m = matches[i];
+        if (m != -1) { c_src_x[i] = src_x[i]; c_src_y[i] = src_y[i]; c_dst_x[i] = dst_x[m]; c_dst_y[i] = dst_y[m]; }
+        else c_src_x[i] = c_src_y[i] = c_dst_x[i] = c_dst_y[i] = -1.f;
+    }
+}
+
+#define ORC_EPS 1.1920928955078125e-07f          /* svd.cu:33 */
+
+/* scaled 2-norm of column `col` of the rows x cols row-major matrix (svd.cu:159-195, :86-93) */
+static float col_norm(const float* A, int rows, int cols, int col)
+{
+    float scale = 0.f, ssq = 1.f;
+    if (rows == 1) return fabsf(A[col]);
+    for (int i = 0; i < rows; ++i) {
+        const float x = A[i * cols + col];
+        if (x != 0.f) {
+            const float ax = fabsf(x);
+            if (scale < ax) { ssq = 1.f + ssq * (scale / ax) * (scale / ax); scale = ax; }
+            else ssq += (ax / scale) * (ax / scale);
+        }
+    }
+    return scale * sqrtf(ssq);
+}
+
+/* svd.cu:133-157 */
+static float hyp(float x, float y)
+{
+    const float xa = fabsf(x), ya = fabsf(y);
+    const float mn = xa < ya ? xa : ya, mx = xa < ya ? ya : xa;
+    if (mn == 0.f) return mx;
+    const float u = mn / mx;
+    return mx * sqrtf(1.f + u * u);
+}
+
+/* linalg_SV_decomp_jacobi (svd.cu:197-360): A (M x N, overwritten), Q (N x N) = right vectors.
+ * Returns 1 when the sweeps converged.  The singular values / column normalisation at the end
+ * (:318-352) do not touch Q, which is all the callers read, and are omitted. */
+static int jacobi_sv(float* A, int M, int N, float* Q)
+{
+    float S[16];
+    int count = 1, sweep = 0, sweepmax = 5 * N;
+    const float tol = (float)(10 * M) * ORC_EPS;               /* :211 */
+    if (sweepmax < 12) sweepmax = 12;                          /* :214 */
+    for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) Q[i * N + j] = i == j ? 1.f : 0.f;   /* :217 */
+    for (int j = 0; j < N; ++j) S[j] = ORC_EPS * col_norm(A, M, N, j);                          /* :222-227 */
+    while (count > 0 && sweep <= sweepmax) {                   /* :231 */
+        count = N * (N - 1) / 2;
+        for (int j = 0; j < N - 1; ++j)
+            for (int k = j + 1; k < N; ++k) {
+                float p = 0.f;
+                for (int i = 0; i < M; ++i) p += A[i * N + j] * A[i * N + k];   /* ddot :123-131 */
+                p *= 2.0f;                                     /* :259 */
+                const float a = col_norm(A, M, N, j), b = col_norm(A, M, N, k);
+                const float q = a * a - b * b;
+                const float v = hyp(p, q);
+                const float ea = S[j], eb = S[k];
+                const int sorted = a >= b;
+                const int orthog = fabsf(p) <= tol * (a * b);
+                const int noisya = a < ea, noisyb = b < eb;
+                if (sorted && (orthog || noisya || noisyb)) { --count; continue; }   /* :277-281 */
+                float c, s;
+                if (v == 0.f || !sorted) { c = 0.f; s = 1.f; }  /* :284-288 */
+                else {
+                    c = (float)sqrt((double)(v + q) / (2.0 * (double)v));     /* :291 (2.0 * v in double) */
+                    s = (float)((double)p / (2.0 * (double)v * (double)c));   /* :292 */
+                }
+                for (int i = 0; i < M; ++i) {                  /* :296-302 */
+                    const float Aik = A[i * N + k], Aij = A[i * N + j];
+                    A[i * N + j] = Aij * c + Aik * s;
+                    A[i * N + k] = -Aij * s + Aik * c;
+                }
+                S[j] = fabsf(c) * ea + fabsf(s) * eb;          /* :304-305 */
+                S[k] = fabsf(s) * ea + fabsf(c) * eb;
+                for (int i = 0; i < N; ++i) {                  /* :308-314 */
+                    const float Qij = Q[i * N + j], Qik = Q[i * N + k];
+                    Q[i * N + j] = Qij * c + Qik * s;
+                    Q[i * N + k] = -Qij * s + Qik * c;
+                }
+            }
+        ++sweep;
+    }
+    return count > 0 ? 0 : 1;
+}
+
+/* inv(dst_transform) * H * src_transform, expanded (ransac.cu:201-212 = :424-434) */
+static void denormalise(const float H[9], float s1, float s2, float tx1, float ty1, float tx2, float ty2, float R[9])
+{
+    R[0] = s1 * tx2 * H[6] + s1 * H[0] / s2;
+    R[1] = s1 * tx2 * H[7] + s1 * H[1] / s2;
+    R[2] = tx2 * (H[8] - s1 * ty1 * H[7] - s1 * tx1 * H[6]) + (H[2] - s1 * ty1 * H[1] - s1 * tx1 * H[0]) / s2;
+    R[3] = s1 * ty2 * H[6] + s1 * H[3] / s2;
+    R[4] = s1 * ty2 * H[7] + s1 * H[4] / s2;
+    R[5] = ty2 * (H[8] - s1 * ty1 * H[7] - s1 * tx1 * H[6]) + (H[5] - s1 * ty1 * H[4] - s1 * tx1 * H[3]) / s2;
+    R[6] = s1 * H[6];
+    R[7] = s1 * H[7];
+    R[8] = H[8] - s1 * ty1 * H[7] - s1 * tx1 * H[6];
+}
+
+/* compute_homography_2 (ransac.cu:84-214): normalised 4-point DLT, null vector by Jacobi SVD */
+static void homography4(const float sx[4], const float sy[4], const float dx[4], const float dy[4], float R[9])
+{
+    const float smx = (sx[0] + sx[1] + sx[2] + sx[3]) * 0.25f, smy = (sy[0] + sy[1] + sy[2] + sy[3]) * 0.25f;
+    const float dmx = (dx[0] + dx[1] + dx[2] + dx[3]) * 0.25f, dmy = (dy[0] + dy[1] + dy[2] + dy[3]) * 0.25f;
+    float sv = 0.f, dv = 0.f;
+    for (int i = 0; i < 4; ++i) {
+        sv += (sx[i] - smx) * (sx[i] - smx) + (sy[i] - smy) * (sy[i] - smy);
+        dv += (dx[i] - dmx) * (dx[i] - dmx) + (dy[i] - dmy) * (dy[i] - dmy);
+    }
+    sv *= 0.25f; dv *= 0.25f;
+    const float s1 = sqrtf(2.0f) / sqrtf(sv), s2 = sqrtf(2.0f) / sqrtf(dv);      /* :117-118 */
+    float X[81], V[81];
+    for (int i = 0; i < 4; ++i) {
+        const float a = (sx[i] - smx) * s1, b = (sy[i] - smy) * s1, u = (dx[i] - dmx) * s2, w = (dy[i] - dmy) * s2;
+        float* r1 = X + (2 * i) * 9; float* r2 = X + (2 * i + 1) * 9;
+        r1[0] = r1[1] = r1[2] = 0.f; r1[3] = -a; r1[4] = -b; r1[5] = -1.f; r1[6] = w * a; r1[7] = w * b; r1[8] = w;
+        r2[0] = a; r2[1] = b; r2[2] = 1.f; r2[3] = r2[4] = r2[5] = 0.f; r2[6] = -u * a; r2[7] = -u * b; r2[8] = -u;
+        if (i == 3) {                                                             /* :159-176 */
+            float* r3 = X + 72;
+            r3[0] = -w * a; r3[1] = -w * b; r3[2] = -w; r3[3] = u * a; r3[4] = u * b; r3[5] = u; r3[6] = r3[7] = r3[8] = 0.f;
+        }
+    }
+    jacobi_sv(X, 9, 9, V);
+    float H[9];
+    const float div = V[80];                                                      /* :181 */
+    for (int i = 0; i < 8; ++i) H[i] = V[i * 9 + 8] / div;
+    H[8] = 1.f;
+    denormalise(H, s1, s2, smx, smy, dmx, dmy, R);
+}
+
+/* compute_similarity_transform (ransac.cu:320-435): X is 4 x 5, V 5 x 5 */
+static void similarity2(const float sx[2], const float sy[2], const float dx[2], const float dy[2], float R[9])
+{
+    const float smx = (sx[0] + sx[1]) * 0.5f, smy = (sy[0] + sy[1]) * 0.5f;
+    const float dmx = (dx[0] + dx[1]) * 0.5f, dmy = (dy[0] + dy[1]) * 0.5f;
+    float sv = 0.f, dv = 0.f;
+    for (int i = 0; i < 2; ++i) {
+        sv += (sx[i] - smx) * (sx[i] - smx) + (sy[i] - smy) * (sy[i] - smy);
+        dv += (dx[i] - dmx) * (dx[i] - dmx) + (dy[i] - dmy) * (dy[i] - dmy);
+    }
+    sv = (float)((double)sv * 0.5); dv = (float)((double)dv * 0.5);               /* :336-337 (double literal) */
+    const float r2 = sqrtf(2.0f);
+    const float s1 = r2 / sqrtf(sv), s2 = r2 / sqrtf(dv);
+    float X[20], V[25];
+    for (int i = 0; i < 2; ++i) {
+        const float a = (sx[i] - smx) * s1, b = (sy[i] - smy) * s1, u = (dx[i] - dmx) * s2, w = (dy[i] - dmy) * s2;
+        float* r1 = X + (2 * i) * 5; float* r2_ = X + (2 * i + 1) * 5;
+        r1[0] = a; r1[1] = 1.f; r1[2] = -b; r1[3] = 0.f; r1[4] = u;               /* :367-372 */
+        r2_[0] = b; r2_[1] = 0.f; r2_[2] = a; r2_[3] = 1.f; r2_[4] = w;           /* :374-379 */
+    }
+    jacobi_sv(X, 4, 5, V);
+    const float div = V[24];
+    const float a0 = -V[4] / div, a1 = -V[9] / div, b0 = -V[14] / div, b1 = -V[19] / div;   /* :384-388 */
+    const float H[9] = {a0, -b0, a1, b0, a0, b1, 0.f, 0.f, 1.f};
+    denormalise(H, s1, s2, smx, smy, dmx, dmy, R);
+}
+
+/* eval_transformation (ransac.cu:61-82): squared reprojection error < threshold */
+static int count_inliers(const float* sx, const float* sy, const float* dx, const float* dy, int n, const float H[9], float thr)
+{
+    int inl = 0;
+    for (int i = 0; i < n; ++i)
+        if (sx[i] >= 0) {
+            float x = H[0] * sx[i] + H[1] * sy[i] + H[2];
+            float y = H[3] * sx[i] + H[4] * sy[i] + H[5];
+            const float z = H[6] * sx[i] + H[7] * sy[i] + H[8];
+            x /= z; y /= z;
+            const float d2 = (dx[i] - x) * (dx[i] - x) + (dy[i] - y) * (dy[i] - y);
+            if (d2 < thr) ++inl;
+        }
+    return inl;
+}
+
+/* The three hypothesis kernels (ransac.cu:437-520) on a caller-supplied random index list
+ * (kind 0: translation, 1 index / iteration; 1: similarity, 2; 2: homography, 4).  Iterations with a
+ * repeated index keep H = 0 and 0 inliers (:446, :497-502; the buffers start zeroed :556-561). */
+void orc_ransac_hypotheses(int kind, const float* sx, const float* sy, const float* dx, const float* dy, int n,
+                           const int* rand_list, int iterations, float thr, float* H_out, int* inliers_out)
+{
+    const int m = kind == 0 ? 1 : kind == 1 ? 2 : 4;
+    for (int it = 0; it < iterations; ++it) {
+        float* H = H_out + (size_t)it * 9;
+        for (int i = 0; i < 9; ++i) H[i] = 0.f;
+        inliers_out[it] = 0;
+        const int* r = rand_list + (size_t)it * m;
+        int dup = 0;
+        for (int a = 0; a < m; ++a) for (int b = a + 1; b < m; ++b) if (r[a] == r[b]) dup = 1;
+        if (dup) continue;
+        float px[4], py[4], qx[4], qy[4];
+        for (int a = 0; a < m; ++a) { px[a] = sx[r[a]]; py[a] = sy[r[a]]; qx[a] = dx[r[a]]; qy[a] = dy[r[a]]; }
+        if (kind == 0) {                                       /* compute_translation :304-310 */
+            H[0] = H[4] = H[8] = 1.f; H[2] = qx[0] - px[0]; H[5] = qy[0] - py[0];
+        } else if (kind == 1) similarity2(px, py, qx, qy, H);
+        else homography4(px, py, qx, qy, H);
+        inliers_out[it] = count_inliers(sx, sy, dx, dy, n, H, thr);
+    }
+}
+
+/* thrust::max_element over the inlier counts (first maximum, ransac.cu:566-570): best iteration */
+int orc_ransac_best(const int* inliers, int iterations)
+{
+    int best = 0;
+    for (int i = 1; i < iterations; ++i) if (inliers[i] > inliers[best]) best = i;
+    return best;
+}

@@ -106,6 +106,60 @@ class FrameChecker:
         return (m, D) if want_distance else m
 
 
+# ---- registration (align_points / RANSAC) checkers: oracle (orc_*) and reference (nmref_*) -------
+def ransac_scene(n=400, seed=7, outliers=0.3, invalid=0.1, noise=0.3):
+    """Correspondences under a known homography: `outliers` of them wrong, `invalid` marked -1 (unmatched),
+    Gaussian noise on the rest.  Returns src_x, src_y, dst_x, dst_y (float32) and the 3x3 ground truth."""
+    rng = np.random.default_rng(seed)
+    Ht = np.array([[1.02, 0.03, 12.5], [-0.025, 0.99, -7.25], [2.0e-5, -1.5e-5, 1.0]])
+    sx = rng.random(n) * 1900 + 10
+    sy = rng.random(n) * 1060 + 10
+    q = Ht @ np.stack([sx, sy, np.ones(n)])
+    dx = q[0] / q[2] + rng.normal(0, noise, n)
+    dy = q[1] / q[2] + rng.normal(0, noise, n)
+    bad = rng.random(n) < outliers
+    dx[bad] = rng.random(bad.sum()) * 1900
+    dy[bad] = rng.random(bad.sum()) * 1060
+    inv = rng.random(n) < invalid
+    sx[inv] = sy[inv] = dx[inv] = dy[inv] = -1.0
+    return tuple(np.ascontiguousarray(a, np.float32) for a in (sx, sy, dx, dy)) + (Ht,)
+
+
+def ransac_rand_lists(sx, iterations=192, seed=11):
+    """Index lists (valid correspondences only, like ransac.cu:533-555) for the three estimators, with
+    repeated-index iterations planted (they must score 0 with H = 0)."""
+    rng = np.random.default_rng(seed)
+    valid = np.nonzero(sx >= 0)[0]
+    out = {}
+    for kind, m in ((0, 1), (1, 2), (2, 4)):
+        rl = valid[rng.integers(0, len(valid), size=(iterations, m))].astype(np.int32)
+        if m > 1:
+            rl[5, 1] = rl[5, 0]
+            rl[17, m - 1] = rl[17, 0]
+        out[kind] = np.ascontiguousarray(rl.reshape(-1))
+    return out
+
+
+def checker_ransac_hypotheses(lib, prefix, kind, sx, sy, dx, dy, rand_list, thr):
+    m = (1, 2, 4)[kind]
+    it = len(rand_list) // m
+    H = np.zeros((it, 9), np.float32)
+    inl = np.zeros(it, np.int32)
+    fn = getattr(lib, prefix + "_ransac_hypotheses")
+    fn.restype = C.c_int
+    rc = fn(kind, _p(sx), _p(sy), _p(dx), _p(dy), len(sx), _p(rand_list), it, C.c_float(thr), _p(H), _p(inl))
+    assert not rc, rc
+    return H, inl
+
+
+def normalise_h(H):
+    """Homographies up to scale: divide by the Frobenius norm, sign of the largest element positive."""
+    H = np.asarray(H, np.float64).reshape(-1, 9)
+    nrm = np.linalg.norm(H, axis=1, keepdims=True)
+    nrm[nrm == 0] = 1.0
+    return H / nrm
+
+
 def load_oracle():
     if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(ROOT, "oracle", "nm_oracle.c")):
         subprocess.check_call(["make", "-C", ROOT, "oracle/libnm_oracle.so"], stdout=subprocess.DEVNULL)

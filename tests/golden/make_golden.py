@@ -4,7 +4,7 @@ by oracle/build_ref.sh from /root/reference) on a B200.  Run on the GPU box:
     python tests/golden/make_golden.py gpurun_out/golden
 
 and copy the .npz files into tests/golden/ (`... gpurun_out/golden masked` regenerates only the
-masked-detector fixture).  The fixtures pin the CPU oracle
+masked-detector fixture, `... ransac` only the registration fixture).  The fixtures pin the CPU oracle
 (tests/test_oracle_golden.py, no GPU needed) and the CUDA product (tests/test_gpu_*.py).
 
 What the reference can and cannot produce on sm_100: everything up to the collated
@@ -85,6 +85,35 @@ def masked(outdir):
     np.savez_compressed(os.path.join(outdir, f"sift_{w}x{h}_masked.npz"), **out)
 
 
+def ransac(outdir):
+    """The reference's hypothesis kernels (ransac.cu:437-520, Jacobi SVD of svd.cu) on supplied index lists,
+    and align_points (ransac.cu:29-59)."""
+    from tests._util import ransac_scene, ransac_rand_lists, checker_ransac_hypotheses, _p
+    os.makedirs(outdir, exist_ok=True)
+    ref = load_reflib()
+    assert ref is not None, "oracle/_ref/libnmref.so missing"
+    sx, sy, dx, dy, Ht = ransac_scene()
+    out = {"src_x": sx, "src_y": sy, "dst_x": dx, "dst_y": dy, "H_true": Ht, "thr": np.float32(4.0)}
+    for kind, rl in ransac_rand_lists(sx).items():
+        H, inl = checker_ransac_hypotheses(ref.lib, "nmref", kind, sx, sy, dx, dy, rl, 4.0)
+        out[f"rand_{kind}"] = rl
+        out[f"H_{kind}"] = H
+        out[f"inliers_{kind}"] = inl
+        print("ransac kind", kind, "best", inl.max(), "at", int(inl.argmax()), "zero rows", int((H == 0).all(axis=1).sum()))
+    # align_points: 300 source points, 260 destination points, a fifth unmatched
+    rng = np.random.default_rng(3)
+    ax, ay = (rng.random(300) * 640).astype(np.float32), (rng.random(300) * 480).astype(np.float32)
+    bx, by = (rng.random(260) * 640).astype(np.float32), (rng.random(260) * 480).astype(np.float32)
+    m = rng.integers(0, 260, 300).astype(np.int32)
+    m[rng.random(300) < 0.2] = -1
+    c = [np.zeros(300, np.float32) for _ in range(4)]
+    rc = ref.lib.nmref_align_points(_p(ax), _p(ay), 300, _p(bx), _p(by), 260, _p(m), *[_p(a) for a in c])
+    assert rc == 0, rc
+    out.update(al_src_x=ax, al_src_y=ay, al_dst_x=bx, al_dst_y=by, al_matches=m,
+               al_c_src_x=c[0], al_c_src_y=c[1], al_c_dst_x=c[2], al_c_dst_y=c[3])
+    np.savez_compressed(os.path.join(outdir, "ransac_400.npz"), **out)
+
+
 def main(outdir):
     os.makedirs(outdir, exist_ok=True)
     ref, orc = load_reflib(), load_oracle()
@@ -146,6 +175,9 @@ if __name__ == "__main__":
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
     if len(sys.argv) > 2 and sys.argv[2] == "masked":      # only the masked-detector fixture
         masked(out)
+    elif len(sys.argv) > 2 and sys.argv[2] == "ransac":    # only the registration fixture
+        ransac(out)
     else:
         main(out)
         masked(out)
+        ransac(out)

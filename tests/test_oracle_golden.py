@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from tests._util import GOLDEN, ang_diff
+from tests._util import GOLDEN, ang_diff, _p
 
 # Tolerances of BASELINE.json north_star: keypoint position 0.01 px, scale/orientation 1e-3,
 # descriptor L2 1e-3 relative, identical match indices.  The oracle is held to much tighter
@@ -154,3 +154,33 @@ def test_edge_cases(oracle):
     # row 0: d=0 -> 0/2.1e9 < .8 -> 0 ; row 1: 100/2.1e9 -> 0 ; row 2: 2.5e9/2.139e9 > .8 -> -1
     assert list(m) == [0, 0, -1]
     # capacity truncation and the early-return rule are covered in test_host_logic.py
+
+
+# ------------------------------------------------------------------ registration
+def test_align_points_oracle_vs_reference_golden(oracle):
+    g = np.load(os.path.join(GOLDEN, "ransac_400.npz"))
+    c = [np.zeros(300, np.float32) for _ in range(4)]
+    oracle.lib.orc_align_points(_p(g["al_src_x"]), _p(g["al_src_y"]), _p(g["al_dst_x"]), _p(g["al_dst_y"]),
+                                *[_p(a) for a in c], _p(g["al_matches"]), 300)
+    for got, key in zip(c, ("al_c_src_x", "al_c_src_y", "al_c_dst_x", "al_c_dst_y")):
+        assert np.array_equal(got, g[key]), key
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_ransac_hypotheses_oracle_vs_reference_golden(oracle, kind):
+    """The reference's hypothesis kernels (ransac.cu:437-520, Jacobi SVD of svd.cu) on the fixture's index lists.
+    Translation is exact.  Similarity / homography: the CPU evaluates a*b+c*d without the GPU's FMA
+    contractions and the null vector of the DLT system is determined up to rounding, so the normalised
+    homography is compared to 5e-4 and the inlier counts to +-2 (measured: 1e-4, 1)."""
+    from tests._util import checker_ransac_hypotheses, normalise_h
+    g = np.load(os.path.join(GOLDEN, "ransac_400.npz"))
+    H, inl = checker_ransac_hypotheses(oracle.lib, "orc", kind, g["src_x"], g["src_y"], g["dst_x"], g["dst_y"],
+                                       g[f"rand_{kind}"], float(g["thr"]))
+    Hg, ig = g[f"H_{kind}"], g[f"inliers_{kind}"]
+    assert np.array_equal((H == 0).all(axis=1), (Hg == 0).all(axis=1))
+    if kind == 0:
+        assert np.array_equal(H, Hg) and np.array_equal(inl, ig)
+        return
+    assert np.abs(normalise_h(H) - normalise_h(Hg)).max() < 5e-4
+    assert np.abs(inl - ig).max() <= 2
+    assert oracle.lib.orc_ransac_best(_p(inl), len(inl)) == int(ig.argmax())     # first maximum, same winner
