@@ -27,28 +27,7 @@ namespace {
 
 constexpr float kEps = 1.1920928955078125e-07f;      // svd.cu:33 (FLT_EPSILON)
 
-// ---- one-sided Jacobi SVD of a ROWS x COLS matrix held in thread-local arrays ---------------------
-// scaled 2-norm of a column (svd.cu:159-198)
-template <int ROWS, int COLS>
-__device__ float col_norm(const float* A, int col)
-{
-    float scale = 0.f, ssq = 1.f;
-#pragma unroll 1
-    for (int i = 0; i < ROWS; ++i) {
-        const float x = A[i * COLS + col];
-        if (x != 0.f) {
-            const float ax = fabsf(x);
-            if (scale < ax) {
-                ssq = 1.f + ssq * (scale / ax) * (scale / ax);
-                scale = ax;
-            } else {
-                ssq += (ax / scale) * (ax / scale);
-            }
-        }
-    }
-    return scale * sqrtf(ssq);
-}
-
+// ---- one-sided Jacobi SVD ---------------------------------------------------------------------------
 // svd.cu:133-157
 __device__ float hyp(float x, float y)
 {
@@ -59,18 +38,39 @@ __device__ float hyp(float x, float y)
     return mx * sqrtf(1.f + u * u);
 }
 
+// A thread's matrix lives in shared memory, element e of lane l at [e * kHypThreads + l]: dynamic column
+// indices (j, k) would put a thread-local array in local memory; this layout is bank-conflict free and the
+// rotations read and write it at shared-memory latency.
+constexpr int kHypThreads = 32;
+struct SMat {
+    float* p;
+    __device__ __forceinline__ float& operator[](int e) const { return p[e * kHypThreads]; }
+};
+
 // Right singular vectors Q (COLS x COLS) of A (ROWS x COLS, destroyed); svd.cu:200-316.  The singular
 // values and the column normalisation of A that follow in the reference (:318-352) are not read by any
-// caller and are not computed.
+// caller and are not computed.  err: COLS column error estimates (the reference's S).
 template <int ROWS, int COLS>
-__device__ void jacobi_right_vectors(float* A, float* Q)
+__device__ void jacobi_right_vectors(SMat A, SMat Q, SMat err)
 {
-    float err[COLS];
     const float tol = (float)(10 * ROWS) * kEps;
     const int sweepmax = 5 * COLS > 12 ? 5 * COLS : 12;
     for (int i = 0; i < COLS * COLS; ++i) Q[i] = 0.f;
     for (int i = 0; i < COLS; ++i) Q[i * COLS + i] = 1.f;
-    for (int j = 0; j < COLS; ++j) err[j] = kEps * col_norm<ROWS, COLS>(A, j);
+    for (int j = 0; j < COLS; ++j) {
+        // dnrm2 (svd.cu:159-198)
+        float scale = 0.f, ssq = 1.f;
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            const float x = A[i * COLS + j];
+            if (x != 0.f) {
+                const float ax = fabsf(x);
+                if (scale < ax) { ssq = 1.f + ssq * (scale / ax) * (scale / ax); scale = ax; }
+                else ssq += (ax / scale) * (ax / scale);
+            }
+        }
+        err[j] = kEps * (scale * sqrtf(ssq));
+    }
     int count = 1, sweep = 0;
     while (count > 0 && sweep <= sweepmax) {
         count = COLS * (COLS - 1) / 2;
@@ -81,10 +81,13 @@ __device__ void jacobi_right_vectors(float* A, float* Q)
                 // dot product and the two scaled norms in ONE pass over the rows: three independent dependency
                 // chains in flight instead of three loops back to back (each quantity sees the operations of
                 // ddot / dnrm2, svd.cu:123-131 and :159-198, in the same order)
+                float cj[ROWS], ck[ROWS];
+#pragma unroll
+                for (int i = 0; i < ROWS; ++i) { cj[i] = A[i * COLS + j]; ck[i] = A[i * COLS + k]; }
                 float p = 0.f, sa = 0.f, qa = 1.f, sb = 0.f, qb = 1.f;
 #pragma unroll
                 for (int i = 0; i < ROWS; ++i) {
-                    const float xj = A[i * COLS + j], xk = A[i * COLS + k];
+                    const float xj = cj[i], xk = ck[i];
                     p += xj * xk;
                     if (xj != 0.f) {
                         const float ax = fabsf(xj);
@@ -111,13 +114,15 @@ __device__ void jacobi_right_vectors(float* A, float* Q)
                     c = (float)sqrt((double)(v + q) / (2.0 * (double)v));
                     s = (float)((double)p / (2.0 * (double)v * (double)c));
                 }
+#pragma unroll
                 for (int i = 0; i < ROWS; ++i) {
-                    const float Aik = A[i * COLS + k], Aij = A[i * COLS + j];
+                    const float Aik = ck[i], Aij = cj[i];
                     A[i * COLS + j] = Aij * c + Aik * s;
                     A[i * COLS + k] = -Aij * s + Aik * c;
                 }
                 err[j] = fabsf(c) * ea + fabsf(s) * eb;
                 err[k] = fabsf(s) * ea + fabsf(c) * eb;
+#pragma unroll
                 for (int i = 0; i < COLS; ++i) {
                     const float Qij = Q[i * COLS + j], Qik = Q[i * COLS + k];
                     Q[i * COLS + j] = Qij * c + Qik * s;
@@ -159,26 +164,26 @@ __device__ void normaliser(const float2* p, float& mx, float& my, float& scale)
 }
 
 // 4-point homography, ransac.cu:84-214: nine DLT rows (the two of every point + the third of point 3)
-__device__ void homography4(const float2* src, const float2* dst, float* R)
+__device__ void homography4(const float2* src, const float2* dst, float* R, SMat X, SMat V, SMat err)
 {
     float smx, smy, s1, dmx, dmy, s2;
     normaliser<4>(src, smx, smy, s1);
     normaliser<4>(dst, dmx, dmy, s2);
-    float X[81], V[81];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float a = (src[i].x - smx) * s1, b = (src[i].y - smy) * s1;
         const float u = (dst[i].x - dmx) * s2, w = (dst[i].y - dmy) * s2;
-        float* r1 = X + 18 * i;
-        float* r2 = r1 + 9;
-        r1[0] = 0.f; r1[1] = 0.f; r1[2] = 0.f; r1[3] = -a; r1[4] = -b; r1[5] = -1.f; r1[6] = w * a; r1[7] = w * b; r1[8] = w;
-        r2[0] = a; r2[1] = b; r2[2] = 1.f; r2[3] = 0.f; r2[4] = 0.f; r2[5] = 0.f; r2[6] = -u * a; r2[7] = -u * b; r2[8] = -u;
+        const float r1[9] = {0.f, 0.f, 0.f, -a, -b, -1.f, w * a, w * b, w};
+        const float r2[9] = {a, b, 1.f, 0.f, 0.f, 0.f, -u * a, -u * b, -u};
+#pragma unroll
+        for (int e = 0; e < 9; ++e) { X[18 * i + e] = r1[e]; X[18 * i + 9 + e] = r2[e]; }
         if (i == 3) {
-            float* r3 = X + 72;
-            r3[0] = -w * a; r3[1] = -w * b; r3[2] = -w; r3[3] = u * a; r3[4] = u * b; r3[5] = u; r3[6] = 0.f; r3[7] = 0.f; r3[8] = 0.f;
+            const float r3[9] = {-w * a, -w * b, -w, u * a, u * b, u, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 9; ++e) X[72 + e] = r3[e];
         }
     }
-    jacobi_right_vectors<9, 9>(X, V);
+    jacobi_right_vectors<9, 9>(X, V, err);
     float H[9];
     const float div = V[80];
 #pragma unroll
@@ -188,22 +193,21 @@ __device__ void homography4(const float2* src, const float2* dst, float* R)
 }
 
 // 2-point similarity, ransac.cu:320-435: 4 x 5 system in (a, tx, b, ty, 1)
-__device__ void similarity2(const float2* src, const float2* dst, float* R)
+__device__ void similarity2(const float2* src, const float2* dst, float* R, SMat X, SMat V, SMat err)
 {
     float smx, smy, s1, dmx, dmy, s2;
     normaliser<2>(src, smx, smy, s1);
     normaliser<2>(dst, dmx, dmy, s2);
-    float X[20], V[25];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const float a = (src[i].x - smx) * s1, b = (src[i].y - smy) * s1;
         const float u = (dst[i].x - dmx) * s2, w = (dst[i].y - dmy) * s2;
-        float* r1 = X + 10 * i;
-        float* r2 = r1 + 5;
-        r1[0] = a; r1[1] = 1.f; r1[2] = -b; r1[3] = 0.f; r1[4] = u;
-        r2[0] = b; r2[1] = 0.f; r2[2] = a; r2[3] = 1.f; r2[4] = w;
+        const float r1[5] = {a, 1.f, -b, 0.f, u};
+        const float r2[5] = {b, 0.f, a, 1.f, w};
+#pragma unroll
+        for (int e = 0; e < 5; ++e) { X[10 * i + e] = r1[e]; X[10 * i + 5 + e] = r2[e]; }
     }
-    jacobi_right_vectors<4, 5>(X, V);
+    jacobi_right_vectors<4, 5>(X, V, err);
     const float div = V[24];
     const float a0 = -V[4] / div, a1 = -V[9] / div, b0 = -V[14] / div, b1 = -V[19] / div;
     const float H[9] = {a0, -b0, a1, b0, a0, b1, 0.f, 0.f, 1.f};
@@ -281,10 +285,8 @@ __global__ void draw_kernel(const int* __restrict__ valid, const int* __restrict
 // One thread per iteration: the hypothesis (translation_kernel / similarity_transformation_kernel /
 // homography_kernel, ransac.cu:437-520, without their scoring loop).  skip[it] = 1 for an iteration with a
 // repeated index: H stays 0 and it scores 0, as in the reference (zero-filled buffers, early return).
-// CTAs of kHypThreads = 32: the Jacobi rotations go through two double-precision divisions and a square
-// root each (svd.cu:291-292), and a B200 SM has little FP64 throughput, so the hypotheses are spread over
-// as many SMs as possible instead of packed 128 or 256 to a CTA.
-constexpr int kHypThreads = 32;
+// CTAs of kHypThreads = 32: a hypothesis is one long dependent chain (5-9 Jacobi sweeps of 36 rotations), so
+// the hypotheses are spread over as many SMs as possible instead of packed 128 or 256 to a CTA.
 template <int KIND>
 __global__ void __launch_bounds__(kHypThreads) hypothesis_kernel(const float* __restrict__ sx, const float* __restrict__ sy,
                                                          const float* __restrict__ dx, const float* __restrict__ dy,
@@ -294,6 +296,8 @@ __global__ void __launch_bounds__(kHypThreads) hypothesis_kernel(const float* __
                                                          unsigned char* __restrict__ skip)
 {
     constexpr int M = KIND == 0 ? 1 : KIND == 1 ? 2 : 4;
+    __shared__ float ws[KIND == 0 ? 1 : (81 + 81 + 9) * kHypThreads];
+    const SMat X{ws + threadIdx.x}, V{ws + 81 * kHypThreads + threadIdx.x}, err{ws + 162 * kHypThreads + threadIdx.x};
     const int it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= iterations) return;
     float H[9];
@@ -318,8 +322,8 @@ __global__ void __launch_bounds__(kHypThreads) hypothesis_kernel(const float* __
             H[0] = H[4] = H[8] = 1.f;
             H[2] = dst[0].x - src[0].x;
             H[5] = dst[0].y - src[0].y;
-        } else if (KIND == 1) similarity2(src, dst, H);
-        else homography4(src, dst, H);
+        } else if (KIND == 1) similarity2(src, dst, H, X, V, err);
+        else homography4(src, dst, H, X, V, err);
     }
 #pragma unroll
     for (int i = 0; i < 9; ++i) H_all[(long long)it * 9 + i] = H[i];
