@@ -366,7 +366,7 @@ def main():
         pyr_ms = stage["pyramid"]
         n_blur = 1 + 5 * N_OCT
         achieved = PYR_BYTES_PER_FRAME * BATCH / (pyr_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "blur_walk_kernel<R> / blur_tile_kernel<R> (31 launches per step: base + 5 levels x 6 octaves)",
+        roofline = {"bound": "hbm", "kernel": "blur_strip_kernel<R> (octaves 0-1) / blur_walk_kernel<R> / blur_tile_kernel<R> (31 launches per step: base + 5 levels x 6 octaves)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": PYR_BYTES_PER_FRAME * BATCH / n_blur,

@@ -238,9 +238,8 @@ __global__ void __launch_bounds__(kThreads, 2) blur_walk_kernel(const NmBlurArgs
 // (row-pass rows i = 64c .. 64c+63, i = image row + R) goes to one half of a 128-row ring in shared
 // memory, and the column pass then emits the 64 output rows whose 2R+1 inputs are now complete
 // (y = 64c - 2R .. 64c + 63 - 2R), reading the 2R carried rows from the other half.  Every row-pass
-// row is computed once per strip.  The launch's chunks (strips x chunks-per-strip) are split evenly over
-// the persistent CTAs; a CTA whose range starts inside a strip first runs the row pass of the last 2R
-// rows of the previous chunk.  Arithmetic per output is unchanged (bitwise the reference).
+// row is computed once per strip (see the work assignment at the kernel).  Arithmetic per output is
+// unchanged (bitwise the reference).
 constexpr int kCH = 64;            // input rows per chunk
 constexpr int kRing = 128;         // ring rows (>= kCH + 2R for R <= 16; power of two)
 __host__ __device__ constexpr int strip_smem_bytes(int R)
@@ -346,9 +345,15 @@ __device__ __forceinline__ void strip_col_item(const float* __restrict__ s_ring,
     }
 }
 
+// Work assignment (strips = tiles_x * batch, `chunks` per strip, G = gridDim.x persistent CTAs): in round r <
+// full_rounds CTA b walks the WHOLE strip r*G + b, so the strips in flight at any time are neighbours in the
+// image and the RA + R halo columns a strip shares with its neighbours are L2 hits (a flat split of the chunk
+// list had every CTA ~3 strips away from the next one: 12 % more DRAM traffic than the algorithmic bytes); the
+// strips left over after the full rounds are split evenly as one flat chunk list, CTA b taking the b-th piece,
+// which may start inside a strip (then it is preceded by the row pass of the previous chunk's last 2R rows).
 template <int R>
 __global__ void __launch_bounds__(kThreads, 2) blur_strip_kernel(const NmBlurArgs a, const __grid_constant__ CUtensorMap tmap,
-                                                                 int tiles_x, int chunks, long long total)
+                                                                 int tiles_x, int chunks, int full_rounds, long long total)
 {
     constexpr int RA = radius_aligned(R), IP = in_pitch(R), NT = 2 * R + 1;
     extern __shared__ __align__(128) float smem[];
@@ -356,19 +361,29 @@ __global__ void __launch_bounds__(kThreads, 2) blur_strip_kernel(const NmBlurArg
     float* s_ring = smem + kCH * IP;           // [kRing][kRowPitch]
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_ring + kRing * kRowPitch);
     const int tid = threadIdx.x;
-    const long long g0 = total * blockIdx.x / gridDim.x, g1 = total * (blockIdx.x + 1) / gridDim.x;
-    if (g0 >= g1) return;
-    // a range that starts inside a strip is preceded by the row pass of the previous chunk's last 2R rows
-    long long g = (g0 % chunks) ? g0 - 1 : g0;
-    int c = (int)(g % chunks), tx, f;
-    {
+    const long long G = gridDim.x, rem0 = (long long)full_rounds * G * chunks, rem = total - rem0;
+    // piece ri of this CTA: chunks [g0, g1) of the strip-major chunk list
+    auto piece = [&](int ri, long long& g0, long long& g1) {
+        if (ri < full_rounds) { g0 = ((long long)ri * G + blockIdx.x) * chunks; g1 = g0 + chunks; }
+        else { g0 = rem0 + rem * blockIdx.x / G; g1 = rem0 + rem * (blockIdx.x + 1) / G; }
+    };
+    auto locate = [&](long long g, int& c, int& tx, int& f) {
         const int s = (int)(g / chunks);
-        tx = s % tiles_x; f = s / tiles_x;
-    }
+        c = (int)(g - (long long)s * chunks); tx = s % tiles_x; f = s / tiles_x;
+    };
     auto issue = [&](int cc, int txx, int ff) {
         mbar_expect_tx(bar, kCH * IP * (uint32_t)sizeof(float));
         tma_load_3d(s_in, &tmap, bar, txx * kTW - RA, cc * kCH - R, ff);
     };
+    int ri = 0;
+    long long g0, g1;
+    piece(ri, g0, g1);
+    if (g0 >= g1) {
+        if (ri >= full_rounds) return;         // (only the remainder piece can be empty)
+    }
+    long long g = (g0 % chunks) ? g0 - 1 : g0;
+    int c, tx, f;
+    locate(g, c, tx, f);
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -378,15 +393,27 @@ __global__ void __launch_bounds__(kThreads, 2) blur_strip_kernel(const NmBlurArg
 #pragma unroll
     for (int k = 0; k < NT; ++k) t[k] = __ldg(a.taps + k);
     __syncthreads();
-    for (uint32_t phase = 0; g < g1; ++g, phase ^= 1) {
+    for (uint32_t phase = 0;; phase ^= 1) {
         const bool pre = g < g0;
-        // position of the next chunk: down the strip, then the next strip of the frame, then the next frame
-        int nc = c + 1, ntx = tx, nf = f;
-        if (nc == chunks) { nc = 0; if (++ntx == tiles_x) { ntx = 0; ++nf; } }
+        // the chunk after this one: down the strip inside a piece, else the first chunk of the next piece
+        long long ng = g + 1, ng0 = g0, ng1 = g1;
+        int nri = ri, nc = c + 1, ntx = tx, nf = f;
+        bool more = true;
+        if (ng < g1) {
+            if (nc == chunks) { nc = 0; if (++ntx == tiles_x) { ntx = 0; ++nf; } }
+        } else if (ri < full_rounds) {
+            nri = ri + 1;
+            piece(nri, ng0, ng1);
+            more = ng0 < ng1;
+            if (more) {
+                ng = (ng0 % chunks) ? ng0 - 1 : ng0;
+                locate(ng, nc, ntx, nf);
+            }
+        } else more = false;
         mbar_wait(bar, phase);
         strip_row_pass<R>(s_in, s_ring, t, tid, (c & 1) * kCH, pre ? kCH - 2 * R : 0, c * kCH - R, a.h);
         __syncthreads();                       // window consumed, ring rows visible
-        if (tid == 0 && g + 1 < g1) issue(nc, ntx, nf);
+        if (tid == 0 && more) issue(nc, ntx, nf);
         if (!pre) {
             float* __restrict__ dst = a.dst + (long long)f * a.dst_fstride;
             for (int it = tid; it < (kTW / 2) * (kCH / 8); it += kThreads) {
@@ -398,7 +425,8 @@ __global__ void __launch_bounds__(kThreads, 2) blur_strip_kernel(const NmBlurArg
                 else strip_col_item<R, true>(s_ring, a, dst, t, cp, gx, gy0, f);
             }
         }
-        c = nc; tx = ntx; f = nf;
+        if (!more) break;
+        g = ng; g0 = ng0; g1 = ng1; ri = nri; c = nc; tx = ntx; f = nf;
         __syncthreads();                       // the next row pass overwrites ring rows this pass read
     }
 }
@@ -523,7 +551,9 @@ int launch_tile(const NmBlurArgs& a, cudaStream_t stream, const NmBlurTma* tma)
                                                  strip_smem_bytes(R)));
                 strip_configured = true;
             }
-            blur_strip_kernel<R><<<2 * n_sms, kThreads, strip_smem_bytes(R), stream>>>(a, tma->map_strip, (int)grid.x, chunks, total);
+            const long long n_strips = (long long)grid.x * a.batch;
+            blur_strip_kernel<R><<<2 * n_sms, kThreads, strip_smem_bytes(R), stream>>>(a, tma->map_strip, (int)grid.x, chunks,
+                                                                                      (int)(n_strips / (2 * n_sms)), total);
         } else if (!no_walk && n_tiles >= 4LL * n_sms && n_tiles < (1LL << 31))
             blur_walk_kernel<R><<<2 * n_sms, kThreads, smem, stream>>>(a, tma->map, (int)grid.x, (int)grid.y, (int)n_tiles);
         else

@@ -327,13 +327,15 @@ def test_1080p_single_frame_vs_oracle(nm, oracle):
 
 
 def test_1080p_batch_strip_blur_vs_oracle(nm, oracle):
-    """Ten 1080p frames: octave 0 of a batch this size takes the strip-walking blur kernel
-    (nm_pyramid.cu, blur_strip_kernel); first and last frame against the CPU oracle, levels bitwise."""
-    frames = np.stack([synth.scene(1920, 1080, synth.SEED_BASE + (i % 2)) for i in range(10)])
+    """Twenty 1080p frames = 300 column strips in octave 0: the strip-walking blur kernel (nm_pyramid.cu,
+    blur_strip_kernel) runs one round of whole strips on its 296 CTAs and splits the 4 strips left over as a flat
+    chunk list (most pieces empty, some starting inside a strip).  First, a middle and the last frame against the
+    CPU oracle, levels bitwise."""
+    frames = np.stack([synth.scene(1920, 1080, synth.SEED_BASE + (i % 2)) for i in range(20)])
     out = run_product(nm, frames, capacity=16384)
-    for f in (0, 9):
-        c = oracle.sift_frame(frames[f], capacity=16384)
-        assert_frame_matches(out[f], c)
+    ref = [oracle.sift_frame(frames[f], capacity=16384) for f in (0, 1)]
+    for f in (0, 9, 19):
+        assert_frame_matches(out[f], ref[f % 2])
 
 
 def test_forced_strip_blur_parity_suite():
