@@ -12,7 +12,8 @@
 //             descriptor.h:25, match.h:19-46, transpose.h:17, ransac.h:8-22}
 // The bodies (compat/src/*.cu) unwrap thrust vectors to raw pointers, call the C-ABI and turn a
 // non-zero status into the reference's exception type.  ransac.h (align_points, ransac_*) is served
-// too.  Out of scope (not provided): resample.h, undistort.h, bgra_2_gray.h, cast.h, cudautils.h.
+// too, and the pipeline-input functions of bgra_2_gray.h, cast.h, undistort.h and
+// resample.h (rank 2).  Not provided: the mosaic functions of resample.h, cudautils.h (rank 4).
 #ifndef NM_COMPAT_HPP
 #define NM_COMPAT_HPP
 
@@ -259,6 +260,19 @@ void get_sift_matches(const TYPE* distance, const int rows, const int cols, cons
 
 template <typename TYPE>
 void transpose(TYPE* odata, const TYPE* idata, int width, int height, cudaStream_t stream = 0);
+
+// ---- gpu/kernels/bgra_2_gray.h (cuda_grayscale), cast.h, undistort.h:29, resample.h:36 -----------------
+// Served instantiations: cuda_grayscale<float>, cuda_cast<float, unsigned char> (the ones the reference
+// instantiates for its pipeline input); cuda_extract_channel / cuda_put_channel / cuda_set_alpha_to_const and
+// the mosaic functions of resample.h are not provided.
+template <typename OutputType>
+void cuda_grayscale(const uchar4* bgra, OutputType* output, const int width, const int height, cudaStream_t stream = 0);
+template <typename FROM, typename TO>
+void cuda_cast(const FROM* src, const size_t cols, const size_t rows, TO* dst, TO max_val = 0, cudaStream_t stream = 0);
+void cuda_undistort(const float* x, const float* y, const size_t cols, const size_t rows, const float* camera_matrix,
+                    const float* distortion_coeffs, float* u, float* v, cudaStream_t stream = 0);
+void resample_undistort(cudaTextureObject_t tex, const float* x, const float* y, const size_t cols, const size_t rows,
+                        float* undistorted, cudaStream_t stream = 0);
 
 // ---- gpu/kernels/ransac.h:8-22 -------------------------------------------------------------------
 void align_points(const float* src_x, const float* src_y, const float* dst_x, const float* dst_y,

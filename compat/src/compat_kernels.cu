@@ -162,3 +162,26 @@ bool ransac_similarity(float* src_x, float* src_y, float* dst_x, float* dst_y, c
     return ransac_any(NM_RANSAC_SIMILARITY, src_x, src_y, dst_x, dst_y, src_size, inlier_threshold, iterations, homography,
                       stream, "ransac_similarity");
 }
+
+// bgra_2_gray.h / cast.h / undistort.h / resample.h
+template <>
+void cuda_grayscale<float>(const uchar4* bgra, float* output, const int width, const int height, cudaStream_t stream)
+{
+    nm_check(nm_grayscale_bgra_f32(bgra, output, width, height, stream), "cuda_grayscale");
+}
+template <>
+void cuda_cast<float, unsigned char>(const float* src, const size_t cols, const size_t rows, unsigned char* dst,
+                                     unsigned char max_val, cudaStream_t stream)
+{
+    nm_check(nm_cast_f32_u8(src, (int)cols, (int)rows, dst, max_val, stream), "cuda_cast");
+}
+void cuda_undistort(const float* x, const float* y, const size_t cols, const size_t rows, const float* camera_matrix,
+                    const float* distortion_coeffs, float* u, float* v, cudaStream_t stream)
+{
+    nm_check(nm_undistort_map_f32(x, y, (int)cols, (int)rows, camera_matrix, distortion_coeffs, u, v, stream), "cuda_undistort");
+}
+void resample_undistort(cudaTextureObject_t tex, const float* x, const float* y, const size_t cols, const size_t rows,
+                        float* undistorted, cudaStream_t stream)
+{
+    nm_check(nm_resample_tex_f32(tex, x, y, (int)cols, (int)rows, undistorted, stream), "resample_undistort");
+}

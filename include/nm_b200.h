@@ -180,6 +180,30 @@ int nm_match_tc_probe(const float* A, int nA, const float* B, int nB, float* rec
                       int* n_lists, float* scale, nm_stream_t stream);
 
 /* ------------------------------------------------------------------------ */
+/* Input preprocessing.                                  */
+/* ------------------------------------------------------------------------ */
+
+/* cuda_grayscale<float> (gpu/kernels/bgra_2_gray.h; bgra_2_gray.cu:8-29): bgra = width*height uchar4
+ * pixels (b, g, r, a), output[i] = (float)(0.07*b + 0.72*g + 0.21*r) as the reference's double expression
+ * rounds it.  Device pointers; bgra 4-byte aligned. */
+int nm_grayscale_bgra_f32(const void* bgra, float* output, int width, int height, nm_stream_t stream);
+
+/* cuda_cast<float, unsigned char> (gpu/kernels/cast.h; cast.cu:7-39): dst = (max_val != 0 && src >= max_val)
+ * ? max_val : (unsigned char)src. */
+int nm_cast_f32_u8(const float* src, int cols, int rows, unsigned char* dst, unsigned char max_val,
+                   nm_stream_t stream);
+
+/* cuda_undistort (gpu/kernels/undistort.h:29; undistort.cu:6-64): radial distortion map.  camera_matrix =
+ * {fx, fy, cx, cy}, distortion_coeffs = {k1, k2, k3}, all device pointers (as in the reference). */
+int nm_undistort_map_f32(const float* x, const float* y, int cols, int rows, const float* camera_matrix,
+                         const float* distortion_coeffs, float* u, float* v, nm_stream_t stream);
+
+/* resample_undistort (gpu/kernels/resample.h:36; resample.cu:104-117, :235-248): result[i] =
+ * tex2D<float>(tex, x[i] + 0.5, y[i] + 0.5) * 255.9999f through the caller's texture object. */
+int nm_resample_tex_f32(unsigned long long tex, const float* x, const float* y, int cols, int rows,
+                        float* result, nm_stream_t stream);
+
+/* ------------------------------------------------------------------------ */
 /* Registration after matching: align_points and the    */
 /* three RANSAC estimators of gpu/kernels/ransac.h, Jacobi SVD of svd.cu.      */
 /* ------------------------------------------------------------------------ */
@@ -230,6 +254,11 @@ int nm_sift_destroy(nm_sift_ctx* ctx);
 /* frames_dev: n_frames dense width*height fp32 images on the device.  Results stay in
  * the context's device buffers (accessors below). */
 int nm_sift_run(nm_sift_ctx* ctx, const float* frames_dev, int n_frames, nm_stream_t stream);
+/* The same on BGRA video frames (n_frames x height x width uchar4, device): the grey conversion of
+ * cuda_grayscale<float> is fused into the base blur (the BGRA words are staged by TMA and converted in
+ * shared memory), so no grey frame is written to HBM; launches too small for that kernel convert through
+ * the context's staging buffer first.  Results equal nm_grayscale_bgra_f32 followed by nm_sift_run. */
+int nm_sift_run_bgra(nm_sift_ctx* ctx, const void* frames_bgra_dev, int n_frames, nm_stream_t stream);
 
 /* End-to-end: frames in (pinned or pageable) HOST memory; copies H2D, runs, and copies
  * counts[n_frames], desc[n_frames*capacity*128], x/y[n_frames*capacity] back to the host

@@ -1,0 +1,147 @@
+// nm_preprocess.cu -- the step BEFORE the pyramid: BGRA -> grey, cast to bytes, the
+// lens-undistortion coordinate map and the resampling through it.
+//
+// Replaces cuda_grayscale<float> (gpu/kernels/bgra_2_gray.cu:8-29), cuda_cast<float, unsigned char>
+// (cast.cu:7-39), cuda_undistort (undistort.cu:6-64) and resample_undistort (resample.cu:104-117, :235-248).
+//
+// Grey value.  The reference evaluates 0.07*b + 0.72*g + 0.21*r in DOUBLE (the literals are doubles) and
+// rounds the sum to float.  In real arithmetic that is N/100 with N = 7b + 72g + 21r <= 25 500, an integer.
+// N/100 is either a float itself (N a multiple of 25) or at least 1/(100 * 2^17) away from every midpoint
+// between two floats below 256, which is ~10^8 times the rounding error of the three double operations, so
+// the reference's result is RN_float(N/100) for every input -- computed here as one 4-way byte dot product
+// (dp4a with the packed weights 7, 72, 21, 0), an int -> float conversion (exact) and ONE correctly rounded
+// fp32 division.  tests/test_gpu_preprocess.py checks all 2^24 (b, g, r) against the double formula and
+// against the reference's kernel.
+//
+// In the batched SIFT path the conversion is fused into the base blur (nm_pyramid.cu: the BGRA words are
+// staged by TMA and converted in shared memory), so no grey frame is ever written to HBM.
+#include "nm_common.cuh"
+#include "nm_pyramid.cuh"
+
+namespace {
+
+// 4 pixels per thread: one 16-byte load, one 16-byte store
+__global__ void __launch_bounds__(256) gray4_kernel(const uint4* __restrict__ bgra, float4* __restrict__ out, long long n4)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const uint4 p = __ldg(bgra + i);
+    out[i] = make_float4(nm_gray_from_bgra(p.x), nm_gray_from_bgra(p.y), nm_gray_from_bgra(p.z), nm_gray_from_bgra(p.w));
+}
+__global__ void __launch_bounds__(256) gray1_kernel(const unsigned* __restrict__ bgra, float* __restrict__ out, long long first,
+                                                    long long n)
+{
+    const long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = nm_gray_from_bgra(__ldg(bgra + i));
+}
+
+// cast.cu:7-21.  The reference indexes pos = j*cols + i with i up to the padded grid width and only tests
+// pos < cols*rows, so every element is written (some twice, with the same value): a flat loop is equivalent.
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src, unsigned char* __restrict__ dst, long long n,
+                                                   unsigned char max_val)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = src[i];
+    dst[i] = (max_val != 0 && v >= max_val) ? max_val : (unsigned char)(v);
+}
+
+// undistort.cu:6-47 (the stores to u/v between the steps round to fp32, as the local floats here do)
+__global__ void __launch_bounds__(256) undistort_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n,
+                                                        const float* __restrict__ distortion_coeffs,
+                                                        const float* __restrict__ camera_matrix, float* __restrict__ u,
+                                                        float* __restrict__ v)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float k1 = distortion_coeffs[0], k2 = distortion_coeffs[1], k3 = distortion_coeffs[2];
+    const float fx = camera_matrix[0], fy = camera_matrix[1], cx = camera_matrix[2], cy = camera_matrix[3];
+    float uu = x[i];
+    uu -= cx;
+    uu /= fx;
+    float vv = y[i];
+    vv -= cy;
+    vv /= fy;
+    const float r2 = powf(uu, 2) + powf(vv, 2);
+    const float kr_poly = 1 + k1 * r2 + k2 * powf(r2, 2) + k3 * powf(r2, 3);
+    uu *= kr_poly;
+    uu *= fx;
+    uu += cx;
+    vv *= kr_poly;
+    vv *= fy;
+    vv += cy;
+    u[i] = uu;
+    v[i] = vv;
+}
+
+// resample_2D<float> (resample.cu:104-117): the caller's texture decides filtering and addressing
+__global__ void __launch_bounds__(256) resample_kernel(float* __restrict__ result, cudaTextureObject_t tex, long long n,
+                                                       const float* __restrict__ x, const float* __restrict__ y)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float res = tex2D<float>(tex, x[i] + 0.5f, y[i] + 0.5f);
+    result[i] = res * 255.9999f;
+}
+
+} // namespace
+
+int nm_grayscale_launch(const void* bgra, float* out, long long n, cudaStream_t st)
+{
+    const bool vec = !(reinterpret_cast<uintptr_t>(bgra) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15);
+    const long long n4 = vec ? n / 4 : 0;
+    if (n4) {
+        gray4_kernel<<<(unsigned)nm_div_up64(n4, 256), 256, 0, st>>>(static_cast<const uint4*>(bgra), reinterpret_cast<float4*>(out), n4);
+        NM_LAUNCH_CHECK();
+    }
+    if (n4 * 4 < n) {
+        gray1_kernel<<<(unsigned)nm_div_up64(n - n4 * 4, 256), 256, 0, st>>>(static_cast<const unsigned*>(bgra), out, n4 * 4, n);
+        NM_LAUNCH_CHECK();
+    }
+    return NM_OK;
+}
+
+extern "C" int nm_grayscale_bgra_f32(const void* bgra, float* output, int width, int height, nm_stream_t stream)
+{
+    if (width < 0 || height < 0) return NM_ERR_INVALID;
+    const long long n = (long long)width * height;
+    if (n == 0) return NM_OK;
+    if (!bgra || !output || (reinterpret_cast<uintptr_t>(bgra) & 3)) return NM_ERR_INVALID;
+    return nm_grayscale_launch(bgra, output, n, (cudaStream_t)stream);
+}
+
+extern "C" int nm_cast_f32_u8(const float* src, int cols, int rows, unsigned char* dst, unsigned char max_val,
+                              nm_stream_t stream)
+{
+    if (cols < 0 || rows < 0) return NM_ERR_INVALID;
+    const long long n = (long long)cols * rows;
+    if (n == 0) return NM_OK;
+    if (!src || !dst) return NM_ERR_INVALID;
+    cast_kernel<<<(unsigned)nm_div_up64(n, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n, max_val);
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+extern "C" int nm_undistort_map_f32(const float* x, const float* y, int cols, int rows, const float* camera_matrix,
+                                    const float* distortion_coeffs, float* u, float* v, nm_stream_t stream)
+{
+    if (cols < 0 || rows < 0) return NM_ERR_INVALID;
+    const long long n = (long long)cols * rows;
+    if (n == 0) return NM_OK;
+    if (!x || !y || !camera_matrix || !distortion_coeffs || !u || !v) return NM_ERR_INVALID;
+    undistort_kernel<<<(unsigned)nm_div_up64(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, distortion_coeffs, camera_matrix, u, v);
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+extern "C" int nm_resample_tex_f32(unsigned long long tex, const float* x, const float* y, int cols, int rows,
+                                   float* result, nm_stream_t stream)
+{
+    if (cols < 0 || rows < 0) return NM_ERR_INVALID;
+    const long long n = (long long)cols * rows;
+    if (n == 0) return NM_OK;
+    if (!tex || !x || !y || !result) return NM_ERR_INVALID;
+    resample_kernel<<<(unsigned)nm_div_up64(n, 256), 256, 0, (cudaStream_t)stream>>>(result, (cudaTextureObject_t)tex, n, x, y);
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}

@@ -411,6 +411,16 @@ __global__ void __launch_bounds__(kThreads, 2) blur_strip_kernel(const NmBlurArg
             }
         } else more = false;
         mbar_wait(bar, phase);
+        if (a.src_bgra) {
+            // the staged words are BGRA pixels: grey values in place (zero fill outside the frame stays 0)
+            float4* w4 = reinterpret_cast<float4*>(s_in);
+            for (int i = tid; i < kCH * IP / 4; i += kThreads) {
+                const float4 q = w4[i];
+                w4[i] = make_float4(nm_gray_from_bgra(__float_as_uint(q.x)), nm_gray_from_bgra(__float_as_uint(q.y)),
+                                    nm_gray_from_bgra(__float_as_uint(q.z)), nm_gray_from_bgra(__float_as_uint(q.w)));
+            }
+            __syncthreads();
+        }
         strip_row_pass<R>(s_in, s_ring, t, tid, (c & 1) * kCH, pre ? kCH - 2 * R : 0, c * kCH - R, a.h);
         __syncthreads();                       // window consumed, ring rows visible
         if (tid == 0 && more) issue(nc, ntx, nf);
@@ -517,9 +527,35 @@ __global__ void blur_cols_generic(const NmBlurArgs a)
         a.dst2[(long long)f * a.dst2_fstride + (long long)(y >> 1) * a.dst2_pitch + (x >> 1)] = sum;
 }
 
+int sm_count()
+{
+    static int n_sms = 0;
+    if (n_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            n_sms = 0;
+    }
+    return n_sms;
+}
+
+// The strip-walking kernel is taken for TMA-describable sources with enough chunks: below ~8 chunks per CTA the
+// lead-in row pass of a piece that starts inside a strip costs more than the tile kernels' halo rows.
+// NM_BLUR_STRIP_MIN overrides the threshold (tests force 1); NM_BLUR_WALK / NM_BLUR_TILE disable it (tuning aids).
+bool strip_eligible(const NmBlurArgs& a, const NmBlurTma* tma)
+{
+    static const bool no_strip = getenv("NM_BLUR_TILE") != nullptr || getenv("NM_BLUR_WALK") != nullptr;
+    const int n_sms = sm_count();
+    if (no_strip || !tma || !tma->valid || !tma->valid_strip || n_sms <= 0 || a.radius < 1 || a.radius > 16) return false;
+    static const long long strip_min = getenv("NM_BLUR_STRIP_MIN") ? atoll(getenv("NM_BLUR_STRIP_MIN")) : 16LL * n_sms;
+    const long long strips = (long long)nm_div_up(a.w, kTW) * a.batch;
+    const long long total = strips * nm_div_up(a.h + 2 * a.radius, kCH);
+    return total >= strip_min && strips < (1LL << 31);
+}
+
 template <int R>
 int launch_tile(const NmBlurArgs& a, cudaStream_t stream, const NmBlurTma* tma)
 {
+    if (a.src_bgra && !strip_eligible(a, tma)) return NM_ERR_INVALID;     // only the strip kernel converts
     static bool configured = false;
     constexpr int smem = blur_smem_bytes(R);
     if (!configured) {
@@ -537,14 +573,10 @@ int launch_tile(const NmBlurArgs& a, cudaStream_t stream, const NmBlurTma* tma)
             NM_CUDA_TRY(cudaFuncSetAttribute(blur_walk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         }
         const long long n_tiles = (long long)grid.x * grid.y * grid.z;
-        static const bool no_walk = getenv("NM_BLUR_TILE") != nullptr;        // tuning aids
-        static const bool no_strip = no_walk || getenv("NM_BLUR_WALK") != nullptr;
+        static const bool no_walk = getenv("NM_BLUR_TILE") != nullptr;        // tuning aid
         const int chunks = nm_div_up(a.h + 2 * R, kCH);
         const long long total = (long long)grid.x * a.batch * chunks;
-        // below ~8 chunks per CTA the lead-in row pass of a range that starts inside a strip costs more
-        // than the tile kernels' halo rows; NM_BLUR_STRIP_MIN overrides the threshold (tests force 1)
-        static const long long strip_min = getenv("NM_BLUR_STRIP_MIN") ? atoll(getenv("NM_BLUR_STRIP_MIN")) : 16LL * n_sms;
-        if (!no_strip && tma->valid_strip && total >= strip_min && (long long)grid.x * a.batch < (1LL << 31)) {
+        if (strip_eligible(a, tma)) {
             static bool strip_configured = false;
             if (!strip_configured) {
                 NM_CUDA_TRY(cudaFuncSetAttribute(blur_strip_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -635,9 +667,12 @@ bool nm_tma_encode_3d(NmBlurTma* t, const float* base, const unsigned long long 
     return t->valid;
 }
 
+bool nm_blur_uses_strip(const NmBlurArgs& a, const NmBlurTma* tma) { return strip_eligible(a, tma); }
+
 bool nm_blur_make_tma(NmBlurTma* t, const float* src, int w, int h, int pitch, long long fstride,
-                      int batch, int radius)
+                      int batch, int radius, bool words_u32)
 {
+    const CUtensorMapDataType dtype = words_u32 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     t->valid = t->valid_strip = false;
     if (radius < 1 || radius > 16 || w <= 0 || h <= 0 || batch <= 0) return false;
     if ((reinterpret_cast<uintptr_t>(src) & 15) || (pitch & 3) || (batch > 1 && (fstride & 3))) return false;
@@ -647,13 +682,13 @@ bool nm_blur_make_tma(NmBlurTma* t, const float* src, int w, int h, int pitch, l
     const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)(batch > 1 ? fstride : (long long)pitch * h) * 4};
     const cuuint32_t box[3] = {(cuuint32_t)in_pitch(radius), (cuuint32_t)(kTH + 2 * radius), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&t->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(src), dims, strides, box, estr,
+    CUresult r = enc(&t->map, dtype, 3, const_cast<float*>(src), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     t->valid = (r == CUDA_SUCCESS);
     if (t->valid) {
         const cuuint32_t box_strip[3] = {(cuuint32_t)in_pitch(radius), (cuuint32_t)kCH, 1};
-        r = enc(&t->map_strip, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(src), dims, strides, box_strip, estr,
+        r = enc(&t->map_strip, dtype, 3, const_cast<float*>(src), dims, strides, box_strip, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         t->valid_strip = (r == CUDA_SUCCESS);

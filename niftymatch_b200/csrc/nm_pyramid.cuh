@@ -11,6 +11,7 @@ struct NmBlurArgs {
     float*       scratch;   // only for the generic (R > 16) path: [batch][h][w]
     long long    src_fstride, dst_fstride, dst2_fstride;   // floats between frames
     int          w, h, src_pitch, dst_pitch, dst2_pitch, batch, radius;
+    int          src_bgra;  // src holds BGRA words (uchar4), converted to grey while staged (strip kernel only)
 };
 
 // TMA descriptor of a blur source: 3-D tensor (x: w, y: h, frame: batch) with the row pitch
@@ -26,7 +27,12 @@ struct NmBlurTma {
 // aligned, radius outside the tiled kernel's range): the caller then uses the plain-load
 // kernel, which computes the same values.
 bool nm_blur_make_tma(NmBlurTma* t, const float* src, int w, int h, int pitch, long long fstride,
-                      int batch, int radius);
+                      int batch, int radius, bool words_u32 = false);
+// True when nm_blur_launch would take the strip-walking kernel for these arguments (the only kernel that
+// converts a BGRA source on the fly).
+bool nm_blur_uses_strip(const NmBlurArgs& a, const NmBlurTma* tma);
+// BGRA words -> grey floats, n pixels (nm_preprocess.cu).
+int nm_grayscale_launch(const void* bgra, float* out, long long n, cudaStream_t st);
 
 // Generic 3-D fp32 tiled descriptor (no swizzle, zero fill outside the tensor); false if it cannot be encoded.
 bool nm_tma_encode_3d(NmBlurTma* t, const float* base, const unsigned long long dims[3],

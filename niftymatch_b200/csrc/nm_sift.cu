@@ -246,7 +246,8 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
 // Detect + describe for the frames [first, first + n) of the workspace (frames_dev = the first of
 // those n frames).  All kernels index frames by block, so a range is the same launch sequence on
 // pointers advanced to the range's first frame.
-static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, int n, cudaStream_t st, bool timing)
+static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, int n, cudaStream_t st, bool timing,
+                          bool bgra = false)
 {
     const nm_sift_params& P = c->P;
     int launches = 0, rc;
@@ -299,7 +300,16 @@ static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, in
             a.dst = oc.levels; a.dst_pitch = oc.pitch; a.dst_fstride = fstride;
             a.taps = c->taps[0]; a.radius = c->radii[0]; a.w = oc.w; a.h = oc.h; a.batch = n;
             NmBlurTma base;
-            nm_blur_make_tma(&base, frames_dev, P.width, P.height, P.width, (long long)P.width * P.height, n, c->radii[0]);
+            nm_blur_make_tma(&base, frames_dev, P.width, P.height, P.width, (long long)P.width * P.height, n, c->radii[0], bgra);
+            a.src_bgra = bgra ? 1 : 0;
+            if (bgra && !nm_blur_uses_strip(a, &base)) {
+                // small launch: the tile kernels do not convert -- grey frames through the staging buffer first
+                float* gray = c->frames_stage + (long long)first * P.width * P.height;
+                if ((rc = nm_grayscale_launch(frames_dev, gray, (long long)n * P.width * P.height, st)) != NM_OK) return rc;
+                launches += 1;
+                a.src = gray; a.src_bgra = 0;
+                nm_blur_make_tma(&base, gray, P.width, P.height, P.width, (long long)P.width * P.height, n, c->radii[0]);
+            }
             if ((rc = nm_blur_launch(a, st, &base)) != NM_OK) return rc;
             ++launches;
         }
@@ -343,6 +353,13 @@ static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, in
     if (timing) cudaEventRecord(c->ev[5], st);
     c->last_launches = launches;
     return NM_OK;
+}
+
+extern "C" int nm_sift_run_bgra(nm_sift_ctx* c, const void* frames_bgra_dev, int n_frames, nm_stream_t stream)
+{
+    if (!c || !frames_bgra_dev || n_frames <= 0 || n_frames > c->B) return NM_ERR_INVALID;
+    if (reinterpret_cast<uintptr_t>(frames_bgra_dev) & 3) return NM_ERR_INVALID;
+    return sift_run_range(c, static_cast<const float*>(frames_bgra_dev), 0, n_frames, (cudaStream_t)stream, c->timing != 0, true);
 }
 
 extern "C" int nm_sift_run(nm_sift_ctx* c, const float* frames_dev, int n_frames, nm_stream_t stream)

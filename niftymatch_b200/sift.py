@@ -103,6 +103,14 @@ class SiftBatch:
         check(self.lib.nm_sift_run(self._ctx, C.c_void_p(frames.data_ptr()), n, _stream_ptr()), "nm_sift_run")
         self._n = n
 
+    def run_bgra(self, frames) -> None:
+        """frames: cuda uint8 tensor (n, height, width, 4), BGRA.  Grey conversion fused into the base blur."""
+        assert frames.is_cuda and frames.is_contiguous() and frames.element_size() == 1 and frames.shape[-1] == 4
+        n = frames.shape[0]
+        assert tuple(frames.shape[1:3]) == (self.params._height, self.params._width)
+        check(self.lib.nm_sift_run_bgra(self._ctx, C.c_void_p(frames.data_ptr()), n, _stream_ptr()), "nm_sift_run_bgra")
+        self._n = n
+
     def run_host(self, frames_host, want_desc=True, out=None):
         """End to end from HOST memory (numpy array or pinned torch tensor): H2D copy, run,
         D2H of counts / descriptors / coordinates.  Returns dict of numpy views."""
@@ -259,3 +267,36 @@ def descriptors(kpts, orient, grad, ow, oh, num_dogs, xper):
                                              n, ow, oh, num_dogs, xper, C.c_void_p(desc.data_ptr()), C.c_void_p(x.data_ptr()),
                                              C.c_void_p(y.data_ptr()), _stream_ptr()), "nm_descriptors_f32")
     return desc, x, y
+
+
+# ---- input preprocessing -----------------------------------------------------
+def grayscale(bgra):
+    """cuda_grayscale<float>: bgra (h, w, 4) uint8 cuda -> (h, w) float32."""
+    import torch
+    h, w = bgra.shape[:2]
+    out = torch.empty((h, w), dtype=torch.float32, device=bgra.device)
+    check(_lib.load().nm_grayscale_bgra_f32(C.c_void_p(bgra.data_ptr()), C.c_void_p(out.data_ptr()), w, h, _stream_ptr()),
+          "nm_grayscale_bgra_f32")
+    return out
+
+
+def cast_u8(src, max_val: int = 0):
+    """cuda_cast<float, unsigned char>."""
+    import torch
+    rows, cols = src.shape
+    out = torch.empty((rows, cols), dtype=torch.uint8, device=src.device)
+    check(_lib.load().nm_cast_f32_u8(C.c_void_p(src.data_ptr()), cols, rows, C.c_void_p(out.data_ptr()), max_val, _stream_ptr()),
+          "nm_cast_f32_u8")
+    return out
+
+
+def undistort_map(x, y, camera_matrix, distortion_coeffs):
+    """cuda_undistort: (u, v) for coordinate maps x, y (rows, cols); camera_matrix (fx, fy, cx, cy) and
+    distortion_coeffs (k1, k2, k3) are cuda float32 tensors."""
+    import torch
+    rows, cols = x.shape
+    u, v = torch.empty_like(x), torch.empty_like(y)
+    check(_lib.load().nm_undistort_map_f32(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), cols, rows,
+                                           C.c_void_p(camera_matrix.data_ptr()), C.c_void_p(distortion_coeffs.data_ptr()),
+                                           C.c_void_p(u.data_ptr()), C.c_void_p(v.data_ptr()), _stream_ptr()), "nm_undistort_map_f32")
+    return u, v

@@ -28,7 +28,7 @@ INC="-I$HERE/shim -I$REF/utils -I$REF/gpu/kernels -I$REF/gpu/utils -I$REF/gpu/si
 FLAGS="$ARCH -std=c++17 -O2 -DUSE_CUDA -Xcompiler -fPIC -w $INC"
 sed -e 's/#define CHUNK 16/#define CHUNK 4/' "$REF/gpu/kernels/match.cu" > "$TMP/match.cu"
 # orientation.cu is included textually by ref_driver.cu (see there)
-SRCS=(convolution downsample cudamath keypoint descriptor transpose)
+SRCS=(convolution downsample cudamath keypoint descriptor transpose bgra_2_gray cast undistort resample)
 pids=()
 for s in "${SRCS[@]}"; do
     $NVCC $FLAGS -c "$REF/gpu/kernels/$s.cu" -o "$TMP/$s.o" & pids+=($!)
@@ -39,6 +39,7 @@ for s in pyramidata siftdata siftfunctions; do
 done
 $NVCC $FLAGS -c "$REF/gpu/utils/cudatex2D.cu" -o "$TMP/cudatex2D.o" & pids+=($!)
 $NVCC $FLAGS -c "$HERE/ref_driver.cu" -o "$TMP/ref_driver.o" & pids+=($!)
+$NVCC $FLAGS -c "$HERE/ref_preprocess_driver.cu" -o "$TMP/ref_preprocess_driver.o" & pids+=($!)
 # ransac.cu (+ svd.cu) is included textually by ref_ransac_driver.cu (see there)
 $NVCC $FLAGS -c "$HERE/ref_ransac_driver.cu" -o "$TMP/ref_ransac_driver.o" & pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done

@@ -916,3 +916,48 @@ int orc_ransac_best(const int* inliers, int iterations)
     for (int i = 1; i < iterations; ++i) if (inliers[i] > inliers[best]) best = i;
     return best;
 }
+
+
+/* ========================================================================= */
+/* input preprocessing.                                 */
+/* ========================================================================= */
+
+/* grayscale (gpu/kernels/bgra_2_gray.cu:8-19): double literals, double sum, rounded to float on the store */
+void orc_grayscale_bgra(const unsigned char* bgra, float* out, long long n)
+{
+    for (long long i = 0; i < n; ++i)
+        out[i] = (float)(0.07 * bgra[4 * i] + 0.72 * bgra[4 * i + 1] + 0.21 * bgra[4 * i + 2]);
+}
+
+/* cast<float, unsigned char> (cast.cu:7-21).  (unsigned char)src of the device code: cvt.rzi.u32.f32 (saturating:
+ * negative and NaN -> 0, above 2^32-1 -> 0xffffffff) followed by the truncation to 8 bits. */
+void orc_cast_f32_u8(const float* src, long long n, unsigned char* dst, unsigned char max_val)
+{
+    for (long long i = 0; i < n; ++i) {
+        const float v = src[i];
+        if (max_val != 0 && v >= (float)max_val) { dst[i] = max_val; continue; }
+        unsigned u;
+        if (!(v > 0.f)) u = 0u;
+        else if (v >= 4294967296.f) u = 0xffffffffu;
+        else u = (unsigned)v;
+        dst[i] = (unsigned char)(u & 0xffu);
+    }
+}
+
+/* undistort (undistort.cu:6-47).  powf(a, 2) and powf(a, 3) are evaluated as repeated products here; the
+ * device powf is accurate to 2 ulp in general, parity is tolerance based (tests: 2e-6 relative). */
+void orc_undistort_map(const float* x, const float* y, long long n, const float* camera_matrix,
+                       const float* distortion_coeffs, float* u, float* v)
+{
+    const float k1 = distortion_coeffs[0], k2 = distortion_coeffs[1], k3 = distortion_coeffs[2];
+    const float fx = camera_matrix[0], fy = camera_matrix[1], cx = camera_matrix[2], cy = camera_matrix[3];
+    for (long long i = 0; i < n; ++i) {
+        float uu = x[i]; uu -= cx; uu /= fx;
+        float vv = y[i]; vv -= cy; vv /= fy;
+        const float r2 = uu * uu + vv * vv;
+        const float kr = 1 + k1 * r2 + k2 * (r2 * r2) + k3 * (r2 * r2 * r2);
+        uu *= kr; uu *= fx; uu += cx;
+        vv *= kr; vv *= fy; vv += cy;
+        u[i] = uu; v[i] = vv;
+    }
+}

@@ -160,6 +160,42 @@ def normalise_h(H):
     return H / nrm
 
 
+# ---- input preprocessing checkers -----------------------------------------------------------------
+def preprocess_inputs(seed=5):
+    """Small deterministic inputs of the rank-2 functions: a BGRA frame, a float image with values around and
+    beyond the byte range, coordinate maps with a camera model."""
+    rng = np.random.default_rng(seed)
+    h, w = 96, 160
+    bgra = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    fimg = (rng.random((h, w)) * 300 - 20).astype(np.float32)
+    fimg[0, :8] = [0.0, 0.999, 1.0, 254.999, 255.0, 255.5, 256.0, 1000.0]
+    fimg[1, :6] = [-0.5, -1.0, -300.0, 511.7, 65536.0, 3.0e9]
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    cam = np.array([140.0, 150.0, 79.5, 47.5], np.float32)        # fx, fy, cx, cy
+    dist = np.array([-0.21, 0.06, -0.004], np.float32)            # k1, k2, k3
+    gray8 = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    return dict(bgra=bgra, fimg=fimg, x=np.ascontiguousarray(xx), y=np.ascontiguousarray(yy), cam=cam, dist=dist, gray8=gray8)
+
+
+def all_bgr_words():
+    """Every (b, g, r) combination once, alpha = low byte of the index: 4096 x 4096 BGRA pixels."""
+    i = np.arange(1 << 24, dtype=np.uint32)
+    px = np.empty((1 << 24, 4), np.uint8)
+    px[:, 0] = i & 255
+    px[:, 1] = (i >> 8) & 255
+    px[:, 2] = (i >> 16) & 255
+    px[:, 3] = (i * 7) & 255
+    return px.reshape(4096, 4096, 4)
+
+
+def gray_double_formula(bgra):
+    """(float)(0.07*b + 0.72*g + 0.21*r) in double, the expression of bgra_2_gray.cu:16."""
+    b = bgra[..., 0].astype(np.float64)
+    g = bgra[..., 1].astype(np.float64)
+    r = bgra[..., 2].astype(np.float64)
+    return (0.07 * b + 0.72 * g + 0.21 * r).astype(np.float32)
+
+
 def load_oracle():
     if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(ROOT, "oracle", "nm_oracle.c")):
         subprocess.check_call(["make", "-C", ROOT, "oracle/libnm_oracle.so"], stdout=subprocess.DEVNULL)

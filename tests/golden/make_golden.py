@@ -114,6 +114,33 @@ def ransac(outdir):
     np.savez_compressed(os.path.join(outdir, "ransac_400.npz"), **out)
 
 
+def preprocess(outdir):
+    """The reference's cuda_grayscale<float>, cuda_cast<float, uchar>, cuda_undistort and resample_undistort."""
+    from tests._util import preprocess_inputs, _p
+    os.makedirs(outdir, exist_ok=True)
+    ref = load_reflib()
+    assert ref is not None, "oracle/_ref/libnmref.so missing"
+    d = preprocess_inputs()
+    h, w = d["fimg"].shape
+    out = dict(d)
+    gray = np.zeros((h, w), np.float32)
+    assert ref.lib.nmref_grayscale(_p(d["bgra"]), w, h, _p(gray)) == 0
+    out["gray"] = gray
+    for mv in (0, 200):
+        c = np.zeros((h, w), np.uint8)
+        assert ref.lib.nmref_cast(_p(d["fimg"]), w, h, _p(c), mv) == 0
+        out[f"cast_{mv}"] = c
+    u, v = np.zeros((h, w), np.float32), np.zeros((h, w), np.float32)
+    assert ref.lib.nmref_undistort(_p(d["x"]), _p(d["y"]), w, h, _p(d["cam"]), _p(d["dist"]), _p(u), _p(v)) == 0
+    out["u"], out["v"] = u, v
+    res = np.zeros((h, w), np.float32)
+    assert ref.lib.nmref_resample_undistort(_p(d["gray8"]), w, h, _p(u), _p(v), w, h, _p(res)) == 0
+    out["resampled"] = res
+    print("preprocess: gray", gray.min(), gray.max(), "cast", out["cast_0"][0, :8], out["cast_0"][1, :6], "u", u.min(), u.max(),
+          "resampled", res.min(), res.max())
+    np.savez_compressed(os.path.join(outdir, "preprocess_160x96.npz"), **out)
+
+
 def main(outdir):
     os.makedirs(outdir, exist_ok=True)
     ref, orc = load_reflib(), load_oracle()
@@ -177,7 +204,10 @@ if __name__ == "__main__":
         masked(out)
     elif len(sys.argv) > 2 and sys.argv[2] == "ransac":    # only the registration fixture
         ransac(out)
+    elif len(sys.argv) > 2 and sys.argv[2] == "preprocess":
+        preprocess(out)
     else:
         main(out)
         masked(out)
         ransac(out)
+        preprocess(out)

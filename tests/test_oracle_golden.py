@@ -184,3 +184,35 @@ def test_ransac_hypotheses_oracle_vs_reference_golden(oracle, kind):
     assert np.abs(normalise_h(H) - normalise_h(Hg)).max() < 5e-4
     assert np.abs(inl - ig).max() <= 2
     assert oracle.lib.orc_ransac_best(_p(inl), len(inl)) == int(ig.argmax())     # first maximum, same winner
+
+
+# ------------------------------------------------------------------ input preprocessing
+def test_preprocess_oracle_vs_reference_golden(oracle):
+    """cuda_grayscale<float>, cuda_cast<float, uchar> bitwise; cuda_undistort to 2e-6 relative (device powf)."""
+    g = np.load(os.path.join(GOLDEN, "preprocess_160x96.npz"))
+    h, w = g["fimg"].shape
+    gray = np.zeros((h, w), np.float32)
+    oracle.lib.orc_grayscale_bgra(_p(g["bgra"]), _p(gray), C.c_longlong(h * w))
+    assert np.array_equal(gray, g["gray"])
+    for mv in (0, 200):
+        c = np.zeros((h, w), np.uint8)
+        oracle.lib.orc_cast_f32_u8(_p(g["fimg"]), C.c_longlong(h * w), _p(c), C.c_ubyte(mv))
+        assert np.array_equal(c, g[f"cast_{mv}"]), mv
+    u, v = np.zeros((h, w), np.float32), np.zeros((h, w), np.float32)
+    oracle.lib.orc_undistort_map(_p(g["x"]), _p(g["y"]), C.c_longlong(h * w), _p(g["cam"]), _p(g["dist"]), _p(u), _p(v))
+    assert np.abs(u - g["u"]).max() <= 2e-6 * np.abs(g["u"]).max()
+    assert np.abs(v - g["v"]).max() <= 2e-6 * np.abs(g["v"]).max()
+
+
+def test_grey_value_identity_all_colours(oracle):
+    """The identity the CUDA kernel relies on (nm_preprocess.cu): the reference's double expression equals the
+    correctly rounded fp32 quotient (7b + 72g + 21r) / 100 for all 2^24 colours."""
+    from tests._util import all_bgr_words, gray_double_formula
+    px = all_bgr_words()
+    want = gray_double_formula(px)
+    out = np.zeros((4096, 4096), np.float32)
+    oracle.lib.orc_grayscale_bgra(_p(px), _p(out), C.c_longlong(1 << 24))
+    assert np.array_equal(out, want)
+    q = px.astype(np.int32)
+    n = (7 * q[..., 0] + 72 * q[..., 1] + 21 * q[..., 2]).astype(np.float32)
+    assert np.array_equal((n / np.float32(100)).astype(np.float32), want)
