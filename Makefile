@@ -7,7 +7,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Iinclude
 CSRC      := niftymatch_b200/csrc
 SRCS      := $(CSRC)/nm_pyramid.cu $(CSRC)/nm_extrema.cu $(CSRC)/nm_orient_desc.cu \
-             $(CSRC)/nm_match.cu $(CSRC)/nm_match_tc.cu $(CSRC)/nm_sift.cu $(CSRC)/nm_ransac.cu $(CSRC)/nm_preprocess.cu
+             $(CSRC)/nm_match.cu $(CSRC)/nm_match_tc.cu $(CSRC)/nm_sift.cu $(CSRC)/nm_ransac.cu $(CSRC)/nm_preprocess.cu $(CSRC)/nm_mosaic.cu
 OBJS      := $(patsubst $(CSRC)/%.cu,build/obj/%.o,$(SRCS))
 HDRS      := $(wildcard $(CSRC)/*.cuh) include/nm_b200.h
 LIB       := niftymatch_b200/libnm_b200.so
@@ -46,7 +46,7 @@ compat: $(LIB)
 # The client loop that drives the REFERENCE in the parity tests (oracle/ref_driver.cu), compiled
 # unchanged against the drop-in tree: test artefact, entry points nmcompat_*.
 compat-client: compat
-	$(NVCC) $(CFLAGS_C) -DNM_COMPAT_BUILD -shared oracle/ref_driver.cu oracle/ref_ransac_driver.cu oracle/ref_preprocess_driver.cu -o build/compat/libnmcompat.so \
+	$(NVCC) $(CFLAGS_C) -DNM_COMPAT_BUILD -shared oracle/ref_driver.cu oracle/ref_ransac_driver.cu oracle/ref_preprocess_driver.cu oracle/ref_mosaic_driver.cu -o build/compat/libnmcompat.so \
 	    -L$(CPREFIX)/lib/nm -lsift -lkernels -lgpuutils -lnm_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/prefix/lib/nm'
 
 clean:

@@ -13,7 +13,7 @@
 // The bodies (compat/src/*.cu) unwrap thrust vectors to raw pointers, call the C-ABI and turn a
 // non-zero status into the reference's exception type.  ransac.h (align_points, ransac_*) is served
 // too, and the pipeline-input functions of bgra_2_gray.h, cast.h, undistort.h and
-// resample.h (rank 2).  Not provided: the mosaic functions of resample.h, cudautils.h (rank 4).
+// resample.h (ranks 2 and 4), cudautils.h.
 #ifndef NM_COMPAT_HPP
 #define NM_COMPAT_HPP
 
@@ -263,8 +263,8 @@ void transpose(TYPE* odata, const TYPE* idata, int width, int height, cudaStream
 
 // ---- gpu/kernels/bgra_2_gray.h (cuda_grayscale), cast.h, undistort.h:29, resample.h:36 -----------------
 // Served instantiations: cuda_grayscale<float>, cuda_cast<float, unsigned char> (the ones the reference
-// instantiates for its pipeline input); cuda_extract_channel / cuda_put_channel / cuda_set_alpha_to_const and
-// the mosaic functions of resample.h are not provided.
+// instantiates for its pipeline input); cuda_extract_channel / cuda_put_channel / cuda_set_alpha_to_const are
+// not provided.
 template <typename OutputType>
 void cuda_grayscale(const uchar4* bgra, OutputType* output, const int width, const int height, cudaStream_t stream = 0);
 template <typename FROM, typename TO>
@@ -273,6 +273,24 @@ void cuda_undistort(const float* x, const float* y, const size_t cols, const siz
                     const float* distortion_coeffs, float* u, float* v, cudaStream_t stream = 0);
 void resample_undistort(cudaTextureObject_t tex, const float* x, const float* y, const size_t cols, const size_t rows,
                         float* undistorted, cudaStream_t stream = 0);
+
+// resample.h:7-23 (mosaic rendering)
+void resample_perspective_transform(uchar4* result, cudaTextureObject_t text, const int cols, const int rows, float* x_pos,
+                                    float* y_pos, const float* mat3x3, bool inverse = true, cudaStream_t stream = 0);
+void resample_mask(unsigned char* result, cudaTextureObject_t text, const int cols, const int rows, const float* x_pos,
+                   const float* y_pos, const float threshold = 0.5f, cudaStream_t stream = 0);
+void transform_blend(uchar4* canvas, const int cw, const int ch, cudaTextureObject_t frame, const int fw, const int fh,
+                     const int nw, const int nh, const float* mat3x3, const int tx, const int ty,
+                     cudaTextureObject_t frame_mask, float* canvas_wts, cudaTextureObject_t frame_wts, cudaStream_t stream = 0);
+
+// ---- gpu/utils/cudautils.h ---------------------------------------------------------------------------
+class CudaUtils {
+public:
+    static int get_max_flops_device_id();      // the device with the most SMs x clock (helper_cuda's gpuGetMaxGflopsDeviceId)
+    static void setup_CUDA(int device_id);     // cudaSetDevice; the reference's cudaGLSetGLDevice (deprecated interop) is not called
+private:
+    static int _max_gflops_device_id;
+};
 
 // ---- gpu/kernels/ransac.h:8-22 -------------------------------------------------------------------
 void align_points(const float* src_x, const float* src_y, const float* dst_x, const float* dst_y,

@@ -185,3 +185,23 @@ void resample_undistort(cudaTextureObject_t tex, const float* x, const float* y,
 {
     nm_check(nm_resample_tex_f32(tex, x, y, (int)cols, (int)rows, undistorted, stream), "resample_undistort");
 }
+
+// resample.h:7-23
+void resample_perspective_transform(uchar4* result, cudaTextureObject_t text, const int cols, const int rows, float* x_pos,
+                                    float* y_pos, const float* mat3x3, bool inverse, cudaStream_t stream)
+{
+    nm_check(nm_resample_perspective_bgra(result, text, cols, rows, x_pos, y_pos, mat3x3, inverse ? 1 : 0, stream),
+             "resample_perspective_transform");
+}
+void resample_mask(unsigned char* result, cudaTextureObject_t text, const int cols, const int rows, const float* x_pos,
+                   const float* y_pos, const float threshold, cudaStream_t stream)
+{
+    nm_check(nm_resample_mask_tex_u8(result, text, cols, rows, x_pos, y_pos, threshold, stream), "resample_mask");
+}
+void transform_blend(uchar4* canvas, const int cw, const int ch, cudaTextureObject_t frame, const int fw, const int fh,
+                     const int nw, const int nh, const float* mat3x3, const int tx, const int ty, cudaTextureObject_t frame_mask,
+                     float* canvas_wts, cudaTextureObject_t frame_wts, cudaStream_t stream)
+{
+    nm_check(nm_transform_blend_bgra(canvas, cw, ch, frame, fw, fh, nw, nh, mat3x3, tx, ty, frame_mask, canvas_wts, frame_wts, stream),
+             "transform_blend");
+}

@@ -55,3 +55,26 @@ float CudaTimer::stop()
     cuda_check(cudaEventElapsedTime(&ms, _start, _stop), "cudaEventElapsedTime");
     return ms;
 }
+
+// cudautils.h (gpu/utils/cudautils.cpp:8-31)
+int CudaUtils::_max_gflops_device_id = -1;
+int CudaUtils::get_max_flops_device_id()
+{
+    if (_max_gflops_device_id != -1) return _max_gflops_device_id;
+    int n = 0, best = 0;
+    double best_score = -1.0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) RUNTIME_EXCEPTION("no CUDA device");
+    for (int d = 0; d < n; ++d) {
+        int sms = 0, khz = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d);
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, d);
+        const double score = (double)sms * khz;
+        if (score > best_score) { best_score = score; best = d; }
+    }
+    _max_gflops_device_id = best;
+    return best;
+}
+void CudaUtils::setup_CUDA(int device_id)
+{
+    if (cudaSetDevice(device_id) != cudaSuccess) RUNTIME_EXCEPTION("Could not set the CUDA device");
+}

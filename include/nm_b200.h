@@ -204,6 +204,26 @@ int nm_resample_tex_f32(unsigned long long tex, const float* x, const float* y, 
                         float* result, nm_stream_t stream);
 
 /* ------------------------------------------------------------------------ */
+/* Mosaic rendering: gpu/kernels/resample.h.             */
+/* Texture objects are the caller's (the reference's CudaTex2D set-up).        */
+/* ------------------------------------------------------------------------ */
+
+/* resample_perspective_transform (resample.h:7; resample.cu:83-102, :119-233): x_pos / y_pos receive the
+ * (inverse) perspective map of the pixel grid, result (uchar4) the texture sampled there. */
+int nm_resample_perspective_bgra(void* result, unsigned long long tex, int cols, int rows, float* x_pos, float* y_pos,
+                                 const float* mat3x3, int inverse, nm_stream_t stream);
+
+/* resample_mask (resample.h:12; resample.cu:67-81, :236-244). */
+int nm_resample_mask_tex_u8(unsigned char* result, unsigned long long tex, int cols, int rows, const float* x_pos,
+                            const float* y_pos, float threshold, nm_stream_t stream);
+
+/* transform_blend (resample.h:16; resample.cu:7-65, :246-258): warp `frame` by mat3x3 into the canvas at
+ * offset (tx, ty), blended by the running weights. */
+int nm_transform_blend_bgra(void* canvas, int cw, int ch, unsigned long long frame_tex, int fw, int fh, int nw, int nh,
+                            const float* mat3x3, int tx, int ty, unsigned long long mask_tex, float* canvas_wts,
+                            unsigned long long frame_wts_tex, nm_stream_t stream);
+
+/* ------------------------------------------------------------------------ */
 /* Registration after matching: align_points and the    */
 /* three RANSAC estimators of gpu/kernels/ransac.h, Jacobi SVD of svd.cu.      */
 /* ------------------------------------------------------------------------ */

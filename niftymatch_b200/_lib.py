@@ -64,6 +64,9 @@ SIGNATURES = {
     "nm_cast_f32_u8": (_i, [_vp, _i, _i, _vp, C.c_ubyte, _vp]),
     "nm_undistort_map_f32": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "nm_resample_tex_f32": (_i, [_ull, _vp, _vp, _i, _i, _vp, _vp]),
+    "nm_resample_perspective_bgra": (_i, [_vp, _ull, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "nm_resample_mask_tex_u8": (_i, [_vp, _ull, _i, _i, _vp, _vp, _f, _vp]),
+    "nm_transform_blend_bgra": (_i, [_vp, _i, _i, _ull, _i, _i, _i, _i, _vp, _i, _i, _ull, _vp, _ull, _vp]),
     "nm_sift_run_bgra": (_i, [_vp, _vp, _i, _vp]),
     "nm_align_points_f32": (_i, [_vp] * 9 + [_i, _vp]),
     "nm_ransac_hypotheses_f32": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp, _i, _f, _vp, _vp, _vp]),

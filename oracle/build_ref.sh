@@ -40,6 +40,7 @@ done
 $NVCC $FLAGS -c "$REF/gpu/utils/cudatex2D.cu" -o "$TMP/cudatex2D.o" & pids+=($!)
 $NVCC $FLAGS -c "$HERE/ref_driver.cu" -o "$TMP/ref_driver.o" & pids+=($!)
 $NVCC $FLAGS -c "$HERE/ref_preprocess_driver.cu" -o "$TMP/ref_preprocess_driver.o" & pids+=($!)
+$NVCC $FLAGS -c "$HERE/ref_mosaic_driver.cu" -o "$TMP/ref_mosaic_driver.o" & pids+=($!)
 # ransac.cu (+ svd.cu) is included textually by ref_ransac_driver.cu (see there)
 $NVCC $FLAGS -c "$HERE/ref_ransac_driver.cu" -o "$TMP/ref_ransac_driver.o" & pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done

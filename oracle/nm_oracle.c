@@ -961,3 +961,119 @@ void orc_undistort_map(const float* x, const float* y, long long n, const float*
         u[i] = uu; v[i] = vv;
     }
 }
+
+/* ========================================================================= */
+/* mosaic rendering (gpu/kernels/resample.cu).          */
+/* The texture unit is restated from the CUDA programming guide (linear        */
+/* filtering, un-normalised coordinates, border addressing): xB = x - 0.5,      */
+/* i = floor(xB), alpha = frac(xB) held in 9-bit fixed point with 8 fractional  */
+/* bits; out-of-range texels read 0.  The hardware's internal rounding is not   */
+/* documented, so byte results are compared with a tolerance of one LSB        */
+/* (tests/test_oracle_golden.py).                                               */
+/* ========================================================================= */
+static float tex_fetch(const float* img, int w, int h, int nch, int ch, int ix, int iy)
+{
+    if (ix < 0 || ix >= w || iy < 0 || iy >= h) return 0.f;
+    return img[((size_t)iy * w + ix) * nch + ch];
+}
+
+/* bilinear sample of channel ch of an interleaved float image at texture coordinates (x, y) */
+static float tex2d_linear(const float* img, int w, int h, int nch, int ch, float x, float y)
+{
+    const float xb = x - 0.5f, yb = y - 0.5f;
+    const float fx = floorf(xb), fy = floorf(yb);
+    const float a = floorf((xb - fx) * 256.f + 0.5f) / 256.f, b = floorf((yb - fy) * 256.f + 0.5f) / 256.f;
+    const int i = (int)fx, j = (int)fy;
+    return (1.f - a) * (1.f - b) * tex_fetch(img, w, h, nch, ch, i, j) + a * (1.f - b) * tex_fetch(img, w, h, nch, ch, i + 1, j) +
+           (1.f - a) * b * tex_fetch(img, w, h, nch, ch, i, j + 1) + a * b * tex_fetch(img, w, h, nch, ch, i + 1, j + 1);
+}
+
+static unsigned char to_byte(float v)               /* (unsigned char)v of the device code, see orc_cast_f32_u8 */
+{
+    unsigned u;
+    if (!(v > 0.f)) u = 0u;
+    else if (v >= 4294967296.f) u = 0xffffffffu;
+    else u = (unsigned)v;
+    return (unsigned char)(u & 0xffu);
+}
+
+/* apply_perspective / apply_perspective_inverse (resample.cu:119-191) */
+void orc_perspective_coords(const float* mat9, int inverse, int cols, int rows, float* x_pos, float* y_pos)
+{
+    float t[9];
+    if (inverse) {
+        const float* m = mat9;
+        const float det = m[0] * (m[4] * m[8] - m[7] * m[5]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+        const float id = 1 / det;
+        t[0] = (m[4] * m[8] - m[7] * m[5]) * id; t[1] = (m[2] * m[7] - m[1] * m[8]) * id; t[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+        t[3] = (m[5] * m[6] - m[3] * m[8]) * id; t[4] = (m[0] * m[8] - m[2] * m[6]) * id; t[5] = (m[3] * m[2] - m[0] * m[5]) * id;
+        t[6] = (m[3] * m[7] - m[6] * m[4]) * id; t[7] = (m[6] * m[1] - m[0] * m[7]) * id; t[8] = (m[0] * m[4] - m[3] * m[1]) * id;
+    } else for (int i = 0; i < 9; ++i) t[i] = mat9[i];
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) {
+            const float xp = t[0] * x + t[1] * y + t[2], yp = t[3] * x + t[4] * y + t[5], sp = t[6] * x + t[7] * y + t[8];
+            x_pos[(size_t)y * cols + x] = xp / sp;
+            y_pos[(size_t)y * cols + x] = yp / sp;
+        }
+}
+
+/* resample_2D<uchar4> (resample.cu:83-102) on a BGRA byte frame read as normalised floats */
+void orc_resample_bgra(const unsigned char* frame, int fw, int fh, const float* x_pos, const float* y_pos, long long n,
+                       unsigned char* result)
+{
+    float* img = (float*)malloc(sizeof(float) * 4 * (size_t)fw * fh);
+    for (size_t i = 0; i < (size_t)4 * fw * fh; ++i) img[i] = frame[i] / 255.f;
+    for (long long i = 0; i < n; ++i)
+        for (int c = 0; c < 4; ++c)
+            result[4 * i + c] = to_byte(tex2d_linear(img, fw, fh, 4, c, x_pos[i] + 0.5f, y_pos[i] + 0.5f) * 255.9999f);
+    free(img);
+}
+
+/* resample_mask_2D (resample.cu:67-81) */
+void orc_resample_mask(const unsigned char* mask, int mw, int mh, const float* x_pos, const float* y_pos, long long n,
+                       float threshold, unsigned char* result)
+{
+    float* img = (float*)malloc(sizeof(float) * (size_t)mw * mh);
+    for (size_t i = 0; i < (size_t)mw * mh; ++i) img[i] = mask[i] / 255.f;
+    for (long long i = 0; i < n; ++i) {
+        const float res = tex2d_linear(img, mw, mh, 1, 0, x_pos[i] + 0.5f, y_pos[i] + 0.5f);
+        result[i] = res <= threshold ? 0 : to_byte(res * 255.999f);
+    }
+    free(img);
+}
+
+/* transform_and_blend (resample.cu:7-65), one warp of the frame into the canvas */
+void orc_transform_blend(unsigned char* canvas, int cw, int ch, const unsigned char* frame, const unsigned char* mask,
+                         const float* wts, int fw, int fh, int nw, int nh, const float* t, int tx, int ty, float* canvas_wts)
+{
+    float* img = (float*)malloc(sizeof(float) * 4 * (size_t)fw * fh);
+    float* msk = (float*)malloc(sizeof(float) * (size_t)fw * fh);
+    for (size_t i = 0; i < (size_t)4 * fw * fh; ++i) img[i] = frame[i] / 255.f;
+    for (size_t i = 0; i < (size_t)fw * fh; ++i) msk[i] = mask[i] / 255.f;
+    for (int y = 0; y < nh; ++y)
+        for (int x = 0; x < nw; ++x) {
+            const int px = x + tx, py = y + ty;
+            if (px < 0 || px >= cw || py < 0 || py >= ch) continue;
+            float xp = t[0] * x + t[1] * y + t[2], yp = t[3] * x + t[4] * y + t[5];
+            const float sp = t[6] * x + t[7] * y + t[8];
+            xp /= sp; yp /= sp;
+            if (xp >= fw || yp >= fh) continue;
+            if (tex2d_linear(msk, fw, fh, 1, 0, xp + 0.5f, yp + 0.5f) <= 0.5f) continue;
+            const float nwt = tex2d_linear(wts, fw, fh, 1, 0, xp + 0.5f, yp + 0.5f);
+            const size_t idx = (size_t)py * cw + px;
+            float res[3];
+            for (int c = 0; c < 3; ++c) res[c] = tex2d_linear(img, fw, fh, 4, c, xp + 0.5f, yp + 0.5f);
+            if (canvas_wts[idx] == 0) {
+                for (int c = 0; c < 3; ++c) canvas[4 * idx + c] = to_byte(res[c] * 255.9999f);
+                canvas[4 * idx + 3] = 255;
+                canvas_wts[idx] = nwt;
+            } else {
+                const float cur = canvas_wts[idx], sum = cur + nwt;
+                for (int c = 0; c < 3; ++c)
+                    canvas[4 * idx + c] = to_byte((res[c] * nwt * 255.9999f + canvas[4 * idx + c] * cur) / sum);
+                canvas[4 * idx + 3] = 255;
+                canvas_wts[idx] = cur + nwt;
+            }
+        }
+    free(img); free(msk);
+}

@@ -196,6 +196,27 @@ def gray_double_formula(bgra):
     return (0.07 * b + 0.72 * g + 0.21 * r).astype(np.float32)
 
 
+def mosaic_inputs(seed=6):
+    """A smooth BGRA frame (so that one-LSB filtering differences stay one LSB), a circular byte mask, a
+    distance-to-border weight map, perspective matrices and canvas offsets for three blended warps."""
+    rng = np.random.default_rng(seed)
+    fh, fw = 90, 128
+    yy, xx = np.mgrid[0:fh, 0:fw].astype(np.float32)
+    frame = np.zeros((fh, fw, 4), np.uint8)
+    frame[..., 0] = (127 + 100 * np.sin(xx / 9.0) * np.cos(yy / 7.0)).astype(np.uint8)
+    frame[..., 1] = (xx * 1.7 + yy * 0.4).astype(np.uint8)
+    frame[..., 2] = rng.integers(0, 256, (fh, fw)).astype(np.uint8)
+    frame[..., 3] = 255
+    mask = (((xx - fw / 2) ** 2 + (yy - fh / 2) ** 2) < (0.47 * fh) ** 2).astype(np.uint8) * 255
+    wts = np.minimum(np.minimum(xx + 1, fw - xx), np.minimum(yy + 1, fh - yy)).astype(np.float32) / 16.0
+    mats = np.array([[1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0],
+                     [0.98, 0.05, -3.2, -0.04, 1.01, 2.6, 1.0e-4, -2.0e-4, 1.0],
+                     [1.03, -0.02, 5.5, 0.03, 0.97, -4.25, -1.5e-4, 1.0e-4, 1.0]], np.float32)
+    tx = np.array([10, 22, -6], np.int32)
+    ty = np.array([8, -5, 30], np.int32)
+    return dict(frame=frame, mask=mask, wts=np.ascontiguousarray(wts), mats=mats, tx=tx, ty=ty)
+
+
 def load_oracle():
     if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(ROOT, "oracle", "nm_oracle.c")):
         subprocess.check_call(["make", "-C", ROOT, "oracle/libnm_oracle.so"], stdout=subprocess.DEVNULL)

@@ -141,6 +141,33 @@ def preprocess(outdir):
     np.savez_compressed(os.path.join(outdir, "preprocess_160x96.npz"), **out)
 
 
+def mosaic(outdir):
+    """The reference's resample_perspective_transform, resample_mask and transform_blend (resample.h:7-23)."""
+    from tests._util import mosaic_inputs, _p
+    os.makedirs(outdir, exist_ok=True)
+    ref = load_reflib()
+    assert ref is not None, "oracle/_ref/libnmref.so missing"
+    d = mosaic_inputs()
+    fh, fw = d["mask"].shape
+    out = dict(d)
+    cols, rows = 150, 100
+    for inv in (0, 1):
+        res = np.zeros((rows, cols, 4), np.uint8)
+        xp, yp = np.zeros((rows, cols), np.float32), np.zeros((rows, cols), np.float32)
+        assert ref.lib.nmref_resample_perspective(_p(d["frame"]), fw, fh, _p(d["mats"][1]), inv, cols, rows, _p(res), _p(xp), _p(yp)) == 0
+        out[f"persp_{inv}"], out[f"xpos_{inv}"], out[f"ypos_{inv}"] = res, xp, yp
+        m = np.zeros((rows, cols), np.uint8)
+        assert ref.lib.nmref_resample_mask(_p(d["mask"]), fw, fh, _p(xp), _p(yp), cols, rows, C.c_float(0.5), _p(m)) == 0
+        out[f"maskres_{inv}"] = m
+    cw, ch = 170, 140
+    canvas, cwts = np.zeros((ch, cw, 4), np.uint8), np.zeros((ch, cw), np.float32)
+    assert ref.lib.nmref_transform_blend(_p(d["frame"]), _p(d["mask"]), _p(d["wts"]), fw, fh, 3, _p(d["mats"]), _p(d["tx"]), _p(d["ty"]),
+                                         fw + 10, fh + 10, cw, ch, _p(canvas), _p(cwts)) == 0
+    out["canvas"], out["canvas_wts"] = canvas, cwts
+    print("mosaic: painted", int((cwts > 0).sum()), "of", cw * ch, "max weight", cwts.max(), "mask kept", int((out["maskres_1"] > 0).sum()))
+    np.savez_compressed(os.path.join(outdir, "mosaic_128x90.npz"), **out)
+
+
 def main(outdir):
     os.makedirs(outdir, exist_ok=True)
     ref, orc = load_reflib(), load_oracle()
@@ -206,8 +233,11 @@ if __name__ == "__main__":
         ransac(out)
     elif len(sys.argv) > 2 and sys.argv[2] == "preprocess":
         preprocess(out)
+    elif len(sys.argv) > 2 and sys.argv[2] == "mosaic":
+        mosaic(out)
     else:
         main(out)
         masked(out)
         ransac(out)
         preprocess(out)
+        mosaic(out)

@@ -16,7 +16,8 @@ CLIENT = os.path.join(ROOT, "build", "compat", "libnmcompat.so")
 
 HOT_PATH_HEADERS = ["siftparams.h", "pyramidata.h", "siftdata.h", "siftfunctions.h", "convolution.h", "downsample.h",
                     "cudamath.h", "keypoint.h", "orientation.h", "descriptor.h", "match.h", "transpose.h",
-                    "cudatex2D.h", "cudatimer.h", "exception.h", "macros.h"]
+                    "cudatex2D.h", "cudatimer.h", "exception.h", "macros.h", "ransac.h", "bgra_2_gray.h", "cast.h", "undistort.h",
+                    "resample.h", "cudautils.h"]
 
 
 def _built():
@@ -52,7 +53,10 @@ def test_exported_cxx_symbols():
                 "void convolve<float>(", "void downsample_by_2<float>(", "void subtract<float>(", "void gradient<float>(",
                 "void transpose<float>(", "void compute_brute_force_distance<float>(", "void get_sift_matches<float>(",
                 "detect_orientations(", "compute_sift_descriptors(", "find_keypoints(", "CudaTex2D::set(", "CudaTimer::stop()",
-                "DivUp", "AlignDown"]:
+                "DivUp", "AlignDown", "align_points(", "ransac_homography(", "ransac_translation(", "ransac_similarity(",
+                "void cuda_grayscale<float>(", "void cuda_cast<float, unsigned char>(", "cuda_undistort(", "resample_undistort(",
+                "resample_perspective_transform(", "resample_mask(", "transform_blend(", "CudaUtils::get_max_flops_device_id()",
+                "CudaUtils::setup_CUDA(int)"]:
         assert sym in out, sym
 
 

@@ -216,3 +216,39 @@ def test_grey_value_identity_all_colours(oracle):
     q = px.astype(np.int32)
     n = (7 * q[..., 0] + 72 * q[..., 1] + 21 * q[..., 2]).astype(np.float32)
     assert np.array_equal((n / np.float32(100)).astype(np.float32), want)
+
+
+# ------------------------------------------------------------------ mosaic rendering
+def test_mosaic_oracle_vs_reference_golden(oracle):
+    """Perspective maps to 1e-5 relative (the CPU has no FMA contraction); resampled bytes within one LSB of
+    the texture unit on >= 99.5 % of the samples away from the frame border (the oracle restates the documented
+    9-bit filtering weights, the hardware's internal rounding is not documented); blended canvas likewise."""
+    g = np.load(os.path.join(GOLDEN, "mosaic_128x90.npz"))
+    fh, fw = g["mask"].shape
+    rows, cols = g["xpos_0"].shape
+    n = rows * cols
+    for inv in (0, 1):
+        xp, yp = np.zeros((rows, cols), np.float32), np.zeros((rows, cols), np.float32)
+        oracle.lib.orc_perspective_coords(_p(g["mats"][1]), inv, cols, rows, _p(xp), _p(yp))
+        assert np.abs(xp - g[f"xpos_{inv}"]).max() < 1e-5 * max(1.0, np.abs(g[f"xpos_{inv}"]).max())
+        assert np.abs(yp - g[f"ypos_{inv}"]).max() < 1e-5 * max(1.0, np.abs(g[f"ypos_{inv}"]).max())
+        res = np.zeros((rows, cols, 4), np.uint8)
+        oracle.lib.orc_resample_bgra(_p(g["frame"]), fw, fh, _p(g[f"xpos_{inv}"]), _p(g[f"ypos_{inv}"]), C.c_longlong(n), _p(res))
+        d = np.abs(res[..., :2].astype(int) - g[f"persp_{inv}"][..., :2].astype(int))    # the two smooth channels
+        assert (d <= 1).mean() > 0.995, (d <= 1).mean()
+        m = np.zeros((rows, cols), np.uint8)
+        oracle.lib.orc_resample_mask(_p(g["mask"]), fw, fh, _p(g[f"xpos_{inv}"]), _p(g[f"ypos_{inv}"]), C.c_longlong(n),
+                                     C.c_float(0.5), _p(m))
+        dm = np.abs(m.astype(int) - g[f"maskres_{inv}"].astype(int))
+        assert (dm <= 1).mean() > 0.995, (dm <= 1).mean()
+    ch, cw = g["canvas_wts"].shape
+    canvas, cwts = np.zeros((ch, cw, 4), np.uint8), np.zeros((ch, cw), np.float32)
+    for k in range(3):
+        oracle.lib.orc_transform_blend(_p(canvas), cw, ch, _p(g["frame"]), _p(g["mask"]), _p(g["wts"]), fw, fh, fw + 10, fh + 10,
+                                       _p(g["mats"][k]), int(g["tx"][k]), int(g["ty"][k]), _p(cwts))
+    same = (cwts > 0) == (g["canvas_wts"] > 0)
+    assert same.mean() > 0.998                                  # mask edge samples may fall either side of 0.5
+    both = (cwts > 0) & (g["canvas_wts"] > 0)
+    assert np.abs(cwts - g["canvas_wts"])[both].max() < 0.02 * g["canvas_wts"].max()
+    dc = np.abs(canvas[..., :2].astype(int) - g["canvas"][..., :2].astype(int))[both]
+    assert (dc <= 2).mean() > 0.99, (dc <= 2).mean()
