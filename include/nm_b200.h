@@ -259,6 +259,16 @@ int nm_ransac_f32(int kind, const float* src_x, const float* src_y, const float*
                   float* homography, int* status, nm_stream_t stream);
 
 
+/* nm_ransac_f32 for n_pairs frame pairs in ONE launch sequence (a video stream registers every frame to its
+ * successor): pair p reads its correspondences at src_x + p*pair_stride (likewise src_y, dst_x, dst_y),
+ * counts[p] of them (device ints, clamped to max_pts; NULL = max_pts for every pair), draws with the seed
+ * `seed + p`, and writes homographies[p*9..] and status[p*3..].  Pair p's result equals nm_ransac_f32 on that
+ * pair with seed + p.  The hypotheses of all pairs share the grid, so the latency of the per-thread SVD chain is
+ * paid once per batch, not once per pair. */
+int nm_ransac_batch_f32(int kind, const float* src_x, const float* src_y, const float* dst_x, const float* dst_y,
+                        long long pair_stride, const int* counts, int max_pts, int n_pairs, float inlier_threshold,
+                        int iterations, unsigned long long seed, float* homographies, int* status, nm_stream_t stream);
+
 /* ------------------------------------------------------------------------ */
 /* Batched SIFT detect+describe: the client loop of the reference             */
 /* (compute_dog/_gradients/_keypoints/_orientations/_descriptors,             */

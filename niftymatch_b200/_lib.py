@@ -71,6 +71,7 @@ SIGNATURES = {
     "nm_align_points_f32": (_i, [_vp] * 9 + [_i, _vp]),
     "nm_ransac_hypotheses_f32": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp, _i, _f, _vp, _vp, _vp]),
     "nm_ransac_f32": (_i, [_i, _vp, _vp, _vp, _vp, _i, _f, _i, _ull, _vp, _vp, _vp]),
+    "nm_ransac_batch_f32": (_i, [_i, _vp, _vp, _vp, _vp, C.c_longlong, _vp, _i, _i, _f, _i, _ull, _vp, _vp, _vp]),
     "nm_match_set_engine": (_i, [_i]),
     "nm_match_get_engine": (_i, []),
     "nm_sift_create": (_i, [C.POINTER(_vp), C.POINTER(SiftParamsC), _i, _i]),

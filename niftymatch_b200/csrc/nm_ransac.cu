@@ -232,13 +232,32 @@ __global__ void align_kernel(const float* __restrict__ src_x, const float* __res
     c_dst_y[i] = ok ? dst_y[m] : -1.f;
 }
 
-// Ordered list of the indices with src_x >= 0 (the host loop of ransac.cu:533-538); one CTA.
-// state[0] = number of valid correspondences.
-__global__ void __launch_bounds__(1024) valid_list_kernel(const float* __restrict__ src_x, int n, int* __restrict__ list,
-                                                          int* __restrict__ state)
+// ---- batched estimator: every kernel indexes a PAIR of frames by a grid dimension ------------------------
+// Pair p reads its correspondences at (sx, sy, dx, dy) + p * stride, n(p) = counts ? min(counts[p], max_pts) :
+// max_pts of them; per-pair workspace slices: valid[p * max_pts], state[p * 4], rand[p * draws], H[p * it * 9],
+// inliers / skip [p * it].  A single estimate is the batch of one.
+struct Pairs {
+    const float *sx, *sy, *dx, *dy;
+    long long stride;
+    const int* counts;
+    int max_pts;
+};
+__device__ __forceinline__ int pair_n(const Pairs& P, int p)
+{
+    if (P.counts == nullptr) return P.max_pts;
+    const int c = P.counts[p];
+    return c < 0 ? 0 : (c < P.max_pts ? c : P.max_pts);
+}
+
+// Ordered list of the indices with src_x >= 0 (the host loop of ransac.cu:533-538); one CTA per pair.
+// state[p * 4] = number of valid correspondences.
+__global__ void __launch_bounds__(1024) valid_list_kernel(const Pairs P, int* __restrict__ list_all, int* __restrict__ state_all)
 {
     __shared__ int warp_tot[32];
     __shared__ int base;
+    const int p = blockIdx.x, n = pair_n(P, p);
+    const float* __restrict__ src_x = P.sx + (long long)p * P.stride;
+    int* __restrict__ list = list_all + (long long)p * P.max_pts;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) base = 0;
     __syncthreads();
@@ -259,7 +278,7 @@ __global__ void __launch_bounds__(1024) valid_list_kernel(const float* __restric
         }
         __syncthreads();
     }
-    if (tid == 0) state[0] = base;
+    if (tid == 0) state_all[p * 4] = base;
 }
 
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x)
@@ -270,43 +289,48 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x)
     return x ^ (x >> 31);
 }
 
-// rand_list[d] = valid[u(seed, d) mod-free in [0, n_valid)], d < draws (the host loop of ransac.cu:551-555)
-__global__ void draw_kernel(const int* __restrict__ valid, const int* __restrict__ state, int min_pts,
-                            unsigned long long seed, int draws, int* __restrict__ rand_list)
+// rand_list[d] = valid[u(seed + p, d) scaled to [0, n_valid)], d < draws (the host loop of ransac.cu:551-555)
+__global__ void draw_kernel(const int* __restrict__ valid_all, const int* __restrict__ state_all, int max_pts, int min_pts,
+                            unsigned long long seed, int draws, int* __restrict__ rand_all)
 {
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
     if (d >= draws) return;
-    const int nv = state[0];
+    int* rand_list = rand_all + (long long)p * draws;
+    const int nv = state_all[p * 4];
     if (nv < min_pts) { rand_list[d] = 0; return; }
-    const unsigned r = (unsigned)(splitmix64(seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(d + 1))) >> 32);
-    rand_list[d] = valid[(int)(((unsigned long long)r * (unsigned)nv) >> 32)];
+    const unsigned r = (unsigned)(splitmix64((seed + (unsigned long long)p) ^ (0xD1B54A32D192ED03ull * (unsigned long long)(d + 1))) >> 32);
+    rand_list[d] = valid_all[(long long)p * max_pts + (int)(((unsigned long long)r * (unsigned)nv) >> 32)];
 }
 
-// One thread per iteration: the hypothesis (translation_kernel / similarity_transformation_kernel /
-// homography_kernel, ransac.cu:437-520, without their scoring loop).  skip[it] = 1 for an iteration with a
+// One thread per (pair, iteration): the hypothesis (translation_kernel / similarity_transformation_kernel /
+// homography_kernel, ransac.cu:437-520, without their scoring loop).  skip = 1 for an iteration with a
 // repeated index: H stays 0 and it scores 0, as in the reference (zero-filled buffers, early return).
 // CTAs of kHypThreads = 32: a hypothesis is one long dependent chain (5-9 Jacobi sweeps of 36 rotations), so
 // the hypotheses are spread over as many SMs as possible instead of packed 128 or 256 to a CTA.
 template <int KIND>
-__global__ void __launch_bounds__(kHypThreads) hypothesis_kernel(const float* __restrict__ sx, const float* __restrict__ sy,
-                                                         const float* __restrict__ dx, const float* __restrict__ dy,
-                                                         const int* __restrict__ rand_list, int iterations,
-                                                         const int* __restrict__ state, int min_pts,
-                                                         float* __restrict__ H_all, int* __restrict__ inliers,
-                                                         unsigned char* __restrict__ skip)
+__global__ void __launch_bounds__(kHypThreads) hypothesis_kernel(const Pairs P, const int* __restrict__ rand_all, int iterations,
+                                                                 const int* __restrict__ state_all, int min_pts,
+                                                                 float* __restrict__ H_all, int* __restrict__ inliers,
+                                                                 unsigned char* __restrict__ skip)
 {
     constexpr int M = KIND == 0 ? 1 : KIND == 1 ? 2 : 4;
     __shared__ float ws[KIND == 0 ? 1 : (81 + 81 + 9) * kHypThreads];
     const SMat X{ws + threadIdx.x}, V{ws + 81 * kHypThreads + threadIdx.x}, err{ws + 162 * kHypThreads + threadIdx.x};
-    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    const int it = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
     if (it >= iterations) return;
+    const long long off = (long long)p * P.stride;
+    const float* __restrict__ sx = P.sx + off;
+    const float* __restrict__ sy = P.sy + off;
+    const float* __restrict__ dx = P.dx + off;
+    const float* __restrict__ dy = P.dy + off;
+    const int* __restrict__ rand_list = rand_all + (long long)p * iterations * M;
     float H[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) H[i] = 0.f;
     int r[M];
 #pragma unroll
     for (int i = 0; i < M; ++i) r[i] = rand_list[it * M + i];
-    bool dup = state != nullptr && state[0] < min_pts;      // not enough correspondences: nothing is estimated
+    bool dup = state_all != nullptr && state_all[p * 4] < min_pts;      // not enough correspondences: nothing is estimated
 #pragma unroll
     for (int a = 0; a < M; ++a)
 #pragma unroll
@@ -325,29 +349,33 @@ __global__ void __launch_bounds__(kHypThreads) hypothesis_kernel(const float* __
         } else if (KIND == 1) similarity2(src, dst, H, X, V, err);
         else homography4(src, dst, H, X, V, err);
     }
+    const long long o = (long long)p * iterations + it;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) H_all[(long long)it * 9 + i] = H[i];
-    inliers[it] = 0;
-    skip[it] = dup ? 1 : 0;
+    for (int i = 0; i < 9; ++i) H_all[o * 9 + i] = H[i];
+    inliers[o] = 0;
+    skip[o] = dup ? 1 : 0;
 }
 
-// eval_transformation (ransac.cu:61-82) for 128 hypotheses x one block of up to 256 correspondences (two IEEE
-// divisions per pair make the loop long: short blocks give the grid enough CTAs to fill the SMs).
+// eval_transformation (ransac.cu:61-82) for 128 hypotheses x one block of up to 256 correspondences of one pair
+// (two IEEE divisions per evaluation make the loop long: short blocks give the grid enough CTAs to fill the SMs).
 constexpr int kScoreThreads = 128, kScorePts = 256;
-__global__ void __launch_bounds__(kScoreThreads) score_kernel(const float* __restrict__ sx, const float* __restrict__ sy,
-                                                              const float* __restrict__ dx, const float* __restrict__ dy, int n,
-                                                              const float* __restrict__ H_all, const unsigned char* __restrict__ skip,
-                                                              int iterations, float thr, int* __restrict__ inliers)
+__global__ void __launch_bounds__(kScoreThreads) score_kernel(const Pairs P, const float* __restrict__ H_all,
+                                                              const unsigned char* __restrict__ skip, int iterations, float thr,
+                                                              int* __restrict__ inliers)
 {
     __shared__ float4 pts[kScorePts];
+    const int p = blockIdx.z, n = pair_n(P, p);
     const int p0 = blockIdx.y * kScorePts, np = min(kScorePts, n - p0);
-    for (int i = threadIdx.x; i < np; i += kScoreThreads) pts[i] = make_float4(sx[p0 + i], sy[p0 + i], dx[p0 + i], dy[p0 + i]);
+    if (np <= 0) return;
+    const long long off = (long long)p * P.stride + p0;
+    for (int i = threadIdx.x; i < np; i += kScoreThreads) pts[i] = make_float4(P.sx[off + i], P.sy[off + i], P.dx[off + i], P.dy[off + i]);
     __syncthreads();
     const int it = blockIdx.x * kScoreThreads + threadIdx.x;
-    if (it >= iterations || skip[it]) return;
+    const long long o = (long long)p * iterations + it;
+    if (it >= iterations || skip[o]) return;
     float H[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) H[i] = H_all[(long long)it * 9 + i];
+    for (int i = 0; i < 9; ++i) H[i] = H_all[o * 9 + i];
     int cnt = 0;
     for (int i = 0; i < np; ++i) {
         const float4 q = pts[i];
@@ -361,22 +389,24 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const float* __res
             if (d2 < thr) ++cnt;
         }
     }
-    if (cnt) atomicAdd(inliers + it, cnt);
+    if (cnt) atomicAdd(inliers + o, cnt);
 }
 
-// thrust::max_element (first maximum, ransac.cu:566-570) + the 9-float copy; one CTA.
-// status[0] = 1 when a model was written, 0 when there were too few correspondences (the reference returns
-// false and leaves `homography` untouched); status[1] = inlier count of the chosen hypothesis, status[2] = its index.
-__global__ void __launch_bounds__(256) select_kernel(const int* __restrict__ inliers, const float* __restrict__ H_all, int iterations,
-                                                     const int* __restrict__ state, int min_pts, float* __restrict__ H_out,
-                                                     int* __restrict__ status)
+// thrust::max_element (first maximum, ransac.cu:566-570) + the 9-float copy; one CTA per pair.
+// status[p*3 + 0] = 1 when a model was written, 0 when there were too few correspondences (the reference returns
+// false and leaves `homography` untouched); [1] = inlier count of the chosen hypothesis, [2] = its index.
+__global__ void __launch_bounds__(256) select_kernel(const int* __restrict__ inliers_all, const float* __restrict__ H_all, int iterations,
+                                                     const int* __restrict__ state_all, int min_pts, float* __restrict__ H_out_all,
+                                                     int* __restrict__ status_all)
 {
     __shared__ long long best[256];
-    const int tid = threadIdx.x;
-    if (state[0] < min_pts) {
+    const int tid = threadIdx.x, p = blockIdx.x;
+    int* status = status_all + p * 3;
+    if (state_all[p * 4] < min_pts) {
         if (tid == 0) { status[0] = 0; status[1] = 0; status[2] = -1; }
         return;
     }
+    const int* inliers = inliers_all + (long long)p * iterations;
     // key = count in the high word, ~index in the low word: a larger key is a larger count, then a smaller index
     long long key = -1;
     for (int i = tid; i < iterations; i += 256) {
@@ -390,26 +420,57 @@ __global__ void __launch_bounds__(256) select_kernel(const int* __restrict__ inl
         __syncthreads();
     }
     const int idx = 0x7fffffff - (int)(best[0] & 0xffffffffll);
-    if (tid < 9) H_out[tid] = H_all[(long long)idx * 9 + tid];
+    if (tid < 9) H_out_all[p * 9 + tid] = H_all[((long long)p * iterations + idx) * 9 + tid];
     if (tid == 0) { status[0] = 1; status[1] = (int)(best[0] >> 32); status[2] = idx; }
 }
 
 int min_points(int kind) { return kind == 2 ? 4 : 2; }        // ransac.cu:541, :606, :656 (translation also asks for 2)
 int sample_size(int kind) { return kind == 0 ? 1 : kind == 1 ? 2 : 4; }
 
-int launch_hypotheses(int kind, const float* sx, const float* sy, const float* dx, const float* dy, int n,
-                      const int* rand_list, int iterations, float thr, const int* state, float* H_all, int* inliers,
-                      unsigned char* skip, cudaStream_t st)
+int launch_hypotheses(int kind, const Pairs& P, int n_pairs, const int* rand_list, int iterations, float thr, const int* state,
+                      float* H_all, int* inliers, unsigned char* skip, cudaStream_t st)
 {
-    const int grid = nm_div_up(iterations, kHypThreads), mp = min_points(kind);
-    if (kind == 0) hypothesis_kernel<0><<<grid, kHypThreads, 0, st>>>(sx, sy, dx, dy, rand_list, iterations, state, mp, H_all, inliers, skip);
-    else if (kind == 1) hypothesis_kernel<1><<<grid, kHypThreads, 0, st>>>(sx, sy, dx, dy, rand_list, iterations, state, mp, H_all, inliers, skip);
-    else hypothesis_kernel<2><<<grid, kHypThreads, 0, st>>>(sx, sy, dx, dy, rand_list, iterations, state, mp, H_all, inliers, skip);
+    const dim3 grid(nm_div_up(iterations, kHypThreads), n_pairs);
+    const int mp = min_points(kind);
+    if (kind == 0) hypothesis_kernel<0><<<grid, kHypThreads, 0, st>>>(P, rand_list, iterations, state, mp, H_all, inliers, skip);
+    else if (kind == 1) hypothesis_kernel<1><<<grid, kHypThreads, 0, st>>>(P, rand_list, iterations, state, mp, H_all, inliers, skip);
+    else hypothesis_kernel<2><<<grid, kHypThreads, 0, st>>>(P, rand_list, iterations, state, mp, H_all, inliers, skip);
     NM_LAUNCH_CHECK();
-    dim3 sg(nm_div_up(iterations, kScoreThreads), nm_div_up(n, kScorePts));
-    score_kernel<<<sg, kScoreThreads, 0, st>>>(sx, sy, dx, dy, n, H_all, skip, iterations, thr, inliers);
+    const dim3 sg(nm_div_up(iterations, kScoreThreads), nm_div_up(P.max_pts, kScorePts), n_pairs);
+    score_kernel<<<sg, kScoreThreads, 0, st>>>(P, H_all, skip, iterations, thr, inliers);
     NM_LAUNCH_CHECK();
     return NM_OK;
+}
+
+int ransac_batch(int kind, const Pairs& P, int n_pairs, float thr, int iterations, unsigned long long seed, float* homographies,
+                 int* status, cudaStream_t st)
+{
+    const int m = sample_size(kind), mp = min_points(kind);
+    const long long draws = (long long)iterations * m;
+    if (draws >= (1LL << 31) || (long long)n_pairs * iterations >= (1LL << 31) || n_pairs > 65535) return NM_ERR_INVALID;
+    // one stream-ordered block: valid lists | states | rand lists | homographies | inliers | skip flags
+    const size_t np = (size_t)n_pairs;
+    const size_t o_valid = 0, o_state = o_valid + sizeof(int) * np * (size_t)P.max_pts, o_rand = o_state + 16 * np,
+                 o_H = o_rand + sizeof(int) * np * (size_t)draws, o_inl = o_H + sizeof(float) * 9 * np * (size_t)iterations,
+                 o_skip = o_inl + sizeof(int) * np * (size_t)iterations, total = o_skip + np * (size_t)iterations;
+    char* ws = nullptr;
+    NM_CUDA_TRY(cudaMallocAsync(&ws, total, st));
+    int* valid = reinterpret_cast<int*>(ws + o_valid);
+    int* state = reinterpret_cast<int*>(ws + o_state);
+    int* rand_list = reinterpret_cast<int*>(ws + o_rand);
+    float* H_all = reinterpret_cast<float*>(ws + o_H);
+    int* inl = reinterpret_cast<int*>(ws + o_inl);
+    unsigned char* skip = reinterpret_cast<unsigned char*>(ws + o_skip);
+    valid_list_kernel<<<n_pairs, 1024, 0, st>>>(P, valid, state);
+    draw_kernel<<<dim3(nm_div_up((int)draws, 256), n_pairs), 256, 0, st>>>(valid, state, P.max_pts, mp, seed, (int)draws, rand_list);
+    int rc = cudaGetLastError() == cudaSuccess ? NM_OK : NM_ERR_CUDA_BASE;
+    if (rc == NM_OK) rc = launch_hypotheses(kind, P, n_pairs, rand_list, iterations, thr, state, H_all, inl, skip, st);
+    if (rc == NM_OK) {
+        select_kernel<<<n_pairs, 256, 0, st>>>(inl, H_all, iterations, state, mp, homographies, status);
+        rc = cudaGetLastError() == cudaSuccess ? NM_OK : NM_ERR_CUDA_BASE;
+    }
+    NM_CUDA_TRY(cudaFreeAsync(ws, st));
+    return rc;
 }
 
 } // namespace
@@ -436,8 +497,8 @@ extern "C" int nm_ransac_hypotheses_f32(int kind, const float* src_x, const floa
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* skip = nullptr;
     NM_CUDA_TRY(cudaMallocAsync(&skip, (size_t)iterations, st));
-    const int rc = launch_hypotheses(kind, src_x, src_y, dst_x, dst_y, num_pts, rand_list, iterations, inlier_threshold,
-                                     nullptr, homographies, inliers, skip, st);
+    const Pairs P{src_x, src_y, dst_x, dst_y, 0, nullptr, num_pts};
+    const int rc = launch_hypotheses(kind, P, 1, rand_list, iterations, inlier_threshold, nullptr, homographies, inliers, skip, st);
     NM_CUDA_TRY(cudaFreeAsync(skip, st));
     return rc;
 }
@@ -448,32 +509,16 @@ extern "C" int nm_ransac_f32(int kind, const float* src_x, const float* src_y, c
 {
     if (kind < 0 || kind > 2 || num_pts <= 0 || iterations <= 0) return NM_ERR_INVALID;
     if (!src_x || !src_y || !dst_x || !dst_y || !homography || !status) return NM_ERR_INVALID;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int m = sample_size(kind), mp = min_points(kind);
-    const long long draws = (long long)iterations * m;
-    if (draws >= (1LL << 31)) return NM_ERR_INVALID;
-    // one stream-ordered block: valid list | state | rand list | homographies | inliers | skip flags
-    const size_t o_valid = 0, o_state = o_valid + sizeof(int) * (size_t)num_pts, o_rand = o_state + 16,
-                 o_H = o_rand + sizeof(int) * (size_t)draws, o_inl = o_H + sizeof(float) * 9 * (size_t)iterations,
-                 o_skip = o_inl + sizeof(int) * (size_t)iterations, total = o_skip + (size_t)iterations;
-    char* ws = nullptr;
-    NM_CUDA_TRY(cudaMallocAsync(&ws, total, st));
-    int* valid = reinterpret_cast<int*>(ws + o_valid);
-    int* state = reinterpret_cast<int*>(ws + o_state);
-    int* rand_list = reinterpret_cast<int*>(ws + o_rand);
-    float* H_all = reinterpret_cast<float*>(ws + o_H);
-    int* inl = reinterpret_cast<int*>(ws + o_inl);
-    unsigned char* skip = reinterpret_cast<unsigned char*>(ws + o_skip);
-    valid_list_kernel<<<1, 1024, 0, st>>>(src_x, num_pts, valid, state);
-    draw_kernel<<<nm_div_up((int)draws, 256), 256, 0, st>>>(valid, state, mp, seed, (int)draws, rand_list);
-    int rc = cudaGetLastError() == cudaSuccess ? NM_OK : NM_ERR_CUDA_BASE;
-    if (rc == NM_OK)
-        rc = launch_hypotheses(kind, src_x, src_y, dst_x, dst_y, num_pts, rand_list, iterations, inlier_threshold, state,
-                               H_all, inl, skip, st);
-    if (rc == NM_OK) {
-        select_kernel<<<1, 256, 0, st>>>(inl, H_all, iterations, state, mp, homography, status);
-        rc = cudaGetLastError() == cudaSuccess ? NM_OK : NM_ERR_CUDA_BASE;
-    }
-    NM_CUDA_TRY(cudaFreeAsync(ws, st));
-    return rc;
+    const Pairs P{src_x, src_y, dst_x, dst_y, 0, nullptr, num_pts};
+    return ransac_batch(kind, P, 1, inlier_threshold, iterations, seed, homography, status, (cudaStream_t)stream);
+}
+
+extern "C" int nm_ransac_batch_f32(int kind, const float* src_x, const float* src_y, const float* dst_x, const float* dst_y,
+                                   long long pair_stride, const int* counts, int max_pts, int n_pairs, float inlier_threshold,
+                                   int iterations, unsigned long long seed, float* homographies, int* status, nm_stream_t stream)
+{
+    if (kind < 0 || kind > 2 || max_pts <= 0 || n_pairs <= 0 || iterations <= 0 || pair_stride < 0) return NM_ERR_INVALID;
+    if (!src_x || !src_y || !dst_x || !dst_y || !homographies || !status) return NM_ERR_INVALID;
+    const Pairs P{src_x, src_y, dst_x, dst_y, pair_stride, counts, max_pts};
+    return ransac_batch(kind, P, n_pairs, inlier_threshold, iterations, seed, homographies, status, (cudaStream_t)stream);
 }

@@ -75,3 +75,43 @@ def match_stream(sift_batch, frames, ambiguity: float = 0.8, world: int = 1, ran
                     out[t - 1] = torch.full((prev[1].shape[0],), -1, dtype=torch.int32, device=frames.device)
             prev = (t, d)
     return out
+
+
+def register_stream(sift_batch, frames, kind: int = 2, ambiguity: float = 0.8, inlier_threshold: float = 4.0,
+                    iterations: int = 1024, seed: int = 0, world: int = 1, rank: int = 0, chunk: int = 16):
+    """BASELINE.json configs[4] with its consumer: SIFT on this rank's frames of a stream, every frame matched to
+    its successor, correspondences aligned (align_points) and ONE batched RANSAC over all the rank's pairs.
+    Returns (pairs, homographies (n_pairs, 9) cuda, status (n_pairs, 3) cuda); pair t -> t+1 maps frame t's
+    coordinates to frame t+1's.  Pair t uses the seed `seed + t` (independent of the sharding)."""
+    import torch
+    from .match import match as _match
+    from .ransac import align_points, ransac_batch
+    n = frames.shape[0]
+    lo, hi, pairs = stream_pairs(n, world, rank)
+    cap = sift_batch.capacity
+    dev = frames.device
+    npairs = len(pairs)
+    c = [torch.full((max(npairs, 1), cap), -1.0, dtype=torch.float32, device=dev) for _ in range(4)]
+    counts = torch.zeros(max(npairs, 1), dtype=torch.int32, device=dev)
+    prev = None
+    for c0 in range(lo, hi, chunk):
+        c1 = min(hi, c0 + chunk)
+        sift_batch.run(frames[c0:c1].contiguous())
+        r = sift_batch.results()
+        cnt = r["counts"][: c1 - c0].tolist()
+        for i in range(c1 - c0):
+            t = c0 + i
+            cur = (t, r["desc"][i, : cnt[i]].clone(), r["x"][i, : cnt[i]].clone(), r["y"][i, : cnt[i]].clone())
+            if prev is not None and prev[0] == t - 1 and prev[1].shape[0] and cur[1].shape[0]:
+                m = _match(prev[1], cur[1], ambiguity)
+                al = align_points(prev[2], prev[3], cur[2], cur[3], m)
+                k = t - 1 - lo
+                for a, b in zip(c, al):
+                    a[k, : b.shape[0]] = b
+                counts[k] = prev[1].shape[0]
+            prev = cur
+    if npairs == 0:
+        return pairs, torch.zeros((0, 9), device=dev), torch.zeros((0, 3), dtype=torch.int32, device=dev)
+    # one seed per PAIR INDEX of the whole stream, so a sharded run reproduces the single-rank run
+    H, st = ransac_batch(kind, *c, counts, inlier_threshold, iterations, seed + lo)
+    return pairs, H, st

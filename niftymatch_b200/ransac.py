@@ -50,3 +50,17 @@ def ransac(kind, src_x, src_y, dst_x, dst_y, inlier_threshold, iterations, seed=
                                     iterations, seed & 0xFFFFFFFFFFFFFFFF, _p(homography), _p(status), _stream_ptr()),
           "nm_ransac_f32")
     return homography, status
+
+
+def ransac_batch(kind, src_x, src_y, dst_x, dst_y, counts, inlier_threshold, iterations, seed=0):
+    """nm_ransac_batch_f32: src_x ... dst_y are (n_pairs, max_pts) cuda float32 (contiguous), counts (n_pairs,) cuda
+    int32 or None.  Returns homographies (n_pairs, 9) and status (n_pairs, 3); pair p uses seed + p."""
+    import torch
+    n_pairs, max_pts = src_x.shape
+    H = torch.zeros((n_pairs, 9), dtype=torch.float32, device=src_x.device)
+    status = torch.zeros((n_pairs, 3), dtype=torch.int32, device=src_x.device)
+    check(_lib.load().nm_ransac_batch_f32(kind, _p(src_x), _p(src_y), _p(dst_x), _p(dst_y), max_pts,
+                                          _p(counts) if counts is not None else None, max_pts, n_pairs, inlier_threshold,
+                                          iterations, seed & 0xFFFFFFFFFFFFFFFF, _p(H), _p(status), _stream_ptr()),
+          "nm_ransac_batch_f32")
+    return H, status

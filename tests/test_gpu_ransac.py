@@ -191,6 +191,74 @@ def test_sift_match_ransac_chain(nm):
     sb.close()
 
 
+def test_batched_ransac_equals_single_calls(nm):
+    """nm_ransac_batch_f32: pair p == nm_ransac_f32 on that pair with seed + p, for ragged counts, a pair with too
+    few valid correspondences and an empty pair."""
+    max_pts, n_pairs = 700, 6
+    arrs = [np.full((n_pairs, max_pts), -1.0, np.float32) for _ in range(4)]
+    counts = np.array([700, 523, 64, 3, 0, 300], np.int32)
+    for p in range(n_pairs):
+        sc = ransac_scene(n=max_pts, seed=30 + p)
+        for a, v in zip(arrs, sc[:4]):
+            a[p, : counts[p]] = v[: counts[p]]
+    arrs[0][3, :3] = [5.0, -1.0, 7.0]                    # pair 3: two valid correspondences only
+    d = [_cu(a) for a in arrs]
+    for kind in (0, 1, 2):
+        H, st = nm.ransac_batch(kind, *d, _cu(counts), 3.0, 300, seed=77)
+        H, st = H.cpu().numpy(), st.cpu().numpy()
+        for p in range(n_pairs):
+            if counts[p] == 0:
+                assert st[p].tolist() == [0, 0, -1] and (H[p] == 0).all()
+                continue
+            one = [x[p, : counts[p]].contiguous() for x in d]
+            H1, st1 = nm.ransac(kind, *one, 3.0, 300, seed=77 + p)
+            assert st[p].tolist() == st1.cpu().tolist(), (kind, p)
+            assert np.array_equal(H[p], H1.cpu().numpy()), (kind, p)
+        assert st[3][0] == (0 if kind == 2 else 1)        # two valid points: enough for translation / similarity only
+        assert st[0][0] == 1 and (kind != 2 or st[0][1] > 100)
+    # counts = NULL: every pair uses max_pts (the -1 padding is ignored by the valid-index rule)
+    H2, st2 = nm.ransac_batch(2, *d, None, 3.0, 300, seed=77)
+    assert np.array_equal(st2.cpu().numpy()[[0, 1, 2, 5]], st[[0, 1, 2, 5]]) and np.array_equal(H2.cpu().numpy()[0], H[0])
+
+
+def test_register_stream_recovers_the_motion_and_shards(nm):
+    """BASELINE.json configs[4] with its consumer: frames cut from one scene at known offsets; SIFT, consecutive
+    matching, align_points and one batched RANSAC recover the shifts; two ranks (one overlap frame) reproduce the
+    single-rank homographies bit for bit."""
+    from niftymatch_b200 import synth
+    w, h = 512, 384
+    base = synth.scene(w + 64, h + 64, synth.SEED_BASE + 9)
+    offs = [(8, 8), (12, 10), (18, 9), (20, 16), (27, 20), (30, 26), (38, 30)]      # window origin of frame t
+    frames = np.stack([base[oy: oy + h, ox: ox + w] for ox, oy in offs])
+    P = nm.SiftParams(w, h)
+    P._peak_threshold = 2.0
+    sb = nm.SiftBatch(P, 4, 8192)
+    fr = _cu(frames)
+    pairs, H, st = nm.register_stream(sb, fr, kind=nm.TRANSLATION, inlier_threshold=1.0, iterations=256, seed=5, chunk=4)
+    assert pairs == [(t, t + 1) for t in range(6)]
+    H, st = H.cpu().numpy(), st.cpu().numpy()
+    for t in range(6):
+        sx, sy = offs[t][0] - offs[t + 1][0], offs[t][1] - offs[t + 1][1]          # a point moves by -(window motion)
+        assert st[t][0] == 1 and st[t][1] > 30, st[t]
+        assert abs(H[t][2] - sx) < 0.5 and abs(H[t][5] - sy) < 0.5, (t, H[t], sx, sy)
+    Hh, sth = nm.register_stream(sb, fr, kind=nm.HOMOGRAPHY, inlier_threshold=1.0, iterations=512, seed=5, chunk=4)[1:]
+    Hh = Hh.cpu().numpy()
+    for t in range(6):
+        sx, sy = offs[t][0] - offs[t + 1][0], offs[t][1] - offs[t + 1][1]
+        g = Hh[t] / Hh[t][8]
+        assert abs(g[2] - sx) < 1.0 and abs(g[5] - sy) < 1.0 and abs(g[0] - 1) < 1e-2 and abs(g[4] - 1) < 1e-2, (t, g)
+    got = {}
+    for rank in range(2):
+        pr, Hr, sr = nm.register_stream(sb, fr, kind=nm.HOMOGRAPHY, inlier_threshold=1.0, iterations=512, seed=5, world=2,
+                                        rank=rank, chunk=4)
+        for k, (t, _) in enumerate(pr):
+            got[t] = (Hr[k].cpu().numpy(), sr[k].cpu().numpy())
+    assert sorted(got) == list(range(6))
+    for t in range(6):
+        assert np.array_equal(got[t][0], Hh[t]) and np.array_equal(got[t][1], sth.cpu().numpy()[t]), t
+    sb.close()
+
+
 def test_dropin_ransac_header(nm):
     """ransac.h of the drop-in layer (compat/include/nm/ransac.h) through the same client code that drives the
     reference (oracle/ref_ransac_driver.cu built with -DNM_COMPAT_BUILD)."""

@@ -36,19 +36,41 @@ for kind, rl in ransac_rand_lists(sx).items():
         P = lambda v: v.ctypes.data_as(C.c_void_p)
         ok = ref.lib.nmref_ransac(kind, P(sx), P(sy), P(dx), P(dy), len(sx), C.c_float(4.0), 2000, P(H9))
         print("   reference full", ok, (H9 / max(abs(H9[8]), 1e-30)).round(5).tolist())
-# timing
-n = 8192
-sx, sy, dx, dy, _ = ransac_scene(n=n, seed=9)
-a = [cu(v) for v in (sx, sy, dx, dy)]
-for kind in (0, 1, 2):
-    for it in (1024, 4096):
-        for _ in range(5):
-            nm.ransac(kind, *a, 4.0, it, 1)
+def timing():
+    # timing
+    n = 8192
+    sx, sy, dx, dy, _ = ransac_scene(n=n, seed=9)
+    a = [cu(v) for v in (sx, sy, dx, dy)]
+    for kind in (0, 1, 2):
+        for it in (1024, 4096):
+            for _ in range(5):
+                nm.ransac(kind, *a, 4.0, it, 1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                nm.ransac(kind, *a, 4.0, it, 1)
+            e1.record()
+            torch.cuda.synchronize()
+            print(f"nm_ransac_f32 kind {kind} n {n} iterations {it}: {e0.elapsed_time(e1) / 10 * 1e3:.1f} us")
+
+    # batched: 64 frame pairs in one launch sequence
+    npairs = 64
+    arrs = [torch.stack([cu(ransac_scene(n=n, seed=100 + p)[k]) for p in range(npairs)]).contiguous() for k in range(4)]
+    for kind in (0, 2):
+        for _ in range(3):
+            nm.ransac_batch(kind, *arrs, None, 4.0, 1024, 1)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(10):
-            nm.ransac(kind, *a, 4.0, it, 1)
+        for _ in range(5):
+            nm.ransac_batch(kind, *arrs, None, 4.0, 1024, 1)
         e1.record()
         torch.cuda.synchronize()
-        print(f"nm_ransac_f32 kind {kind} n {n} iterations {it}: {e0.elapsed_time(e1) / 10 * 1e3:.1f} us")
+        ms = e0.elapsed_time(e1) / 5
+        print(f"nm_ransac_batch_f32 kind {kind}: {npairs} pairs x {n} correspondences x 1024 hypotheses: {ms * 1e3:.0f} us = {ms * 1e3 / npairs:.1f} us per pair")
+
+
+for rep in range(2):
+    print("timing pass", rep)
+    timing()
