@@ -700,10 +700,11 @@ int orc_sift_batch(const float* frames, int n_frames, int w, int h, const float*
 /* the one-sided Jacobi SVD of gpu/kernels/svd.cu (the reference's port of    */
 /* GSL's gsl_linalg_SV_decomp_jacobi).  Restated from the published           */
 /* algorithm (Hestenes / Nash plane rotations with GSL's error-estimate       */
-/* skip rule) in the order of operations of the reference; fp32 throughout.   */
-/* Parity of the homographies is tolerance based (the CPU evaluates a*b+c*d   */
-/* without the GPU's FMA contractions; the null vector is determined up to     */
-/* rounding), see tests/test_oracle_golden.py.                                 */
+/* skip rule) in the order of operations of the reference; fp32 throughout,   */
+/* with explicit fmaf where the reference's GPU build contracts a*b+c*d (the   */
+/* forms were established against tests/golden/ransac_400.npz): translation    */
+/* and homography hypotheses are bitwise the reference's, similarity within    */
+/* one ulp of one element, see tests/test_oracle_golden.py.                    */
 /* ========================================================================= */
 
 /* establish_correspondences (ransac.cu:29-48) */
@@ -729,8 +730,8 @@ static float col_norm(const float* A, int rows, int cols, int col)
         const float x = A[i * cols + col];
         if (x != 0.f) {
             const float ax = fabsf(x);
-            if (scale < ax) { ssq = 1.f + ssq * (scale / ax) * (scale / ax); scale = ax; }
-            else ssq += (ax / scale) * (ax / scale);
+            if (scale < ax) { ssq = fmaf(ssq * (scale / ax), scale / ax, 1.f); scale = ax; }
+            else ssq = fmaf(ax / scale, ax / scale, ssq);
         }
     }
     return scale * sqrtf(ssq);
@@ -743,7 +744,7 @@ static float hyp(float x, float y)
     const float mn = xa < ya ? xa : ya, mx = xa < ya ? ya : xa;
     if (mn == 0.f) return mx;
     const float u = mn / mx;
-    return mx * sqrtf(1.f + u * u);
+    return mx * sqrtf(fmaf(u, u, 1.f));
 }
 
 /* linalg_SV_decomp_jacobi (svd.cu:197-360): A (M x N, overwritten), Q (N x N) = right vectors.
@@ -762,10 +763,10 @@ static int jacobi_sv(float* A, int M, int N, float* Q)
         for (int j = 0; j < N - 1; ++j)
             for (int k = j + 1; k < N; ++k) {
                 float p = 0.f;
-                for (int i = 0; i < M; ++i) p += A[i * N + j] * A[i * N + k];   /* ddot :123-131 */
+                for (int i = 0; i < M; ++i) p = fmaf(A[i * N + j], A[i * N + k], p);   /* ddot :123-131 */
                 p *= 2.0f;                                     /* :259 */
                 const float a = col_norm(A, M, N, j), b = col_norm(A, M, N, k);
-                const float q = a * a - b * b;
+                const float q = fmaf(a, a, -(b * b));
                 const float v = hyp(p, q);
                 const float ea = S[j], eb = S[k];
                 const int sorted = a >= b;
@@ -780,15 +781,15 @@ static int jacobi_sv(float* A, int M, int N, float* Q)
                 }
                 for (int i = 0; i < M; ++i) {                  /* :296-302 */
                     const float Aik = A[i * N + k], Aij = A[i * N + j];
-                    A[i * N + j] = Aij * c + Aik * s;
-                    A[i * N + k] = -Aij * s + Aik * c;
+                    A[i * N + j] = fmaf(Aik, s, Aij * c);
+                    A[i * N + k] = fmaf(Aik, c, -Aij * s);
                 }
-                S[j] = fabsf(c) * ea + fabsf(s) * eb;          /* :304-305 */
-                S[k] = fabsf(s) * ea + fabsf(c) * eb;
+                S[j] = fmaf(fabsf(c), ea, fabsf(s) * eb);      /* :304-305 */
+                S[k] = fmaf(fabsf(s), ea, fabsf(c) * eb);
                 for (int i = 0; i < N; ++i) {                  /* :308-314 */
                     const float Qij = Q[i * N + j], Qik = Q[i * N + k];
-                    Q[i * N + j] = Qij * c + Qik * s;
-                    Q[i * N + k] = -Qij * s + Qik * c;
+                    Q[i * N + j] = fmaf(Qij, c, Qik * s);
+                    Q[i * N + k] = fmaf(Qik, c, -Qij * s);
                 }
             }
         ++sweep;
@@ -799,15 +800,19 @@ static int jacobi_sv(float* A, int M, int N, float* Q)
 /* inv(dst_transform) * H * src_transform, expanded (ransac.cu:201-212 = :424-434) */
 static void denormalise(const float H[9], float s1, float s2, float tx1, float ty1, float tx2, float ty2, float R[9])
 {
-    R[0] = s1 * tx2 * H[6] + s1 * H[0] / s2;
-    R[1] = s1 * tx2 * H[7] + s1 * H[1] / s2;
-    R[2] = tx2 * (H[8] - s1 * ty1 * H[7] - s1 * tx1 * H[6]) + (H[2] - s1 * ty1 * H[1] - s1 * tx1 * H[0]) / s2;
-    R[3] = s1 * ty2 * H[6] + s1 * H[3] / s2;
-    R[4] = s1 * ty2 * H[7] + s1 * H[4] / s2;
-    R[5] = ty2 * (H[8] - s1 * ty1 * H[7] - s1 * tx1 * H[6]) + (H[5] - s1 * ty1 * H[4] - s1 * tx1 * H[3]) / s2;
+    /* the GPU build contracts a*b + c*d to fma(a, b, c*d) and x - a*b to fma(-a, b, x) (established on the
+     * vectors the reference produced, tests/golden/ransac_400.npz) */
+    const float sty = s1 * ty1, stx = s1 * tx1;
+    const float w8 = fmaf(-stx, H[6], fmaf(-sty, H[7], H[8]));
+    R[0] = fmaf(s1 * tx2, H[6], s1 * H[0] / s2);
+    R[1] = fmaf(s1 * tx2, H[7], s1 * H[1] / s2);
+    R[2] = fmaf(tx2, w8, fmaf(-stx, H[0], fmaf(-sty, H[1], H[2])) / s2);
+    R[3] = fmaf(s1 * ty2, H[6], s1 * H[3] / s2);
+    R[4] = fmaf(s1 * ty2, H[7], s1 * H[4] / s2);
+    R[5] = fmaf(ty2, w8, fmaf(-stx, H[3], fmaf(-sty, H[4], H[5])) / s2);
     R[6] = s1 * H[6];
     R[7] = s1 * H[7];
-    R[8] = H[8] - s1 * ty1 * H[7] - s1 * tx1 * H[6];
+    R[8] = w8;
 }
 
 /* compute_homography_2 (ransac.cu:84-214): normalised 4-point DLT, null vector by Jacobi SVD */
@@ -817,8 +822,8 @@ static void homography4(const float sx[4], const float sy[4], const float dx[4],
     const float dmx = (dx[0] + dx[1] + dx[2] + dx[3]) * 0.25f, dmy = (dy[0] + dy[1] + dy[2] + dy[3]) * 0.25f;
     float sv = 0.f, dv = 0.f;
     for (int i = 0; i < 4; ++i) {
-        sv += (sx[i] - smx) * (sx[i] - smx) + (sy[i] - smy) * (sy[i] - smy);
-        dv += (dx[i] - dmx) * (dx[i] - dmx) + (dy[i] - dmy) * (dy[i] - dmy);
+        sv += fmaf(sx[i] - smx, sx[i] - smx, (sy[i] - smy) * (sy[i] - smy));
+        dv += fmaf(dx[i] - dmx, dx[i] - dmx, (dy[i] - dmy) * (dy[i] - dmy));
     }
     sv *= 0.25f; dv *= 0.25f;
     const float s1 = sqrtf(2.0f) / sqrtf(sv), s2 = sqrtf(2.0f) / sqrtf(dv);      /* :117-118 */
@@ -848,8 +853,8 @@ static void similarity2(const float sx[2], const float sy[2], const float dx[2],
     const float dmx = (dx[0] + dx[1]) * 0.5f, dmy = (dy[0] + dy[1]) * 0.5f;
     float sv = 0.f, dv = 0.f;
     for (int i = 0; i < 2; ++i) {
-        sv += (sx[i] - smx) * (sx[i] - smx) + (sy[i] - smy) * (sy[i] - smy);
-        dv += (dx[i] - dmx) * (dx[i] - dmx) + (dy[i] - dmy) * (dy[i] - dmy);
+        sv += fmaf(sx[i] - smx, sx[i] - smx, (sy[i] - smy) * (sy[i] - smy));
+        dv += fmaf(dx[i] - dmx, dx[i] - dmx, (dy[i] - dmy) * (dy[i] - dmy));
     }
     sv = (float)((double)sv * 0.5); dv = (float)((double)dv * 0.5);               /* :336-337 (double literal) */
     const float r2 = sqrtf(2.0f);
@@ -874,11 +879,11 @@ static int count_inliers(const float* sx, const float* sy, const float* dx, cons
     int inl = 0;
     for (int i = 0; i < n; ++i)
         if (sx[i] >= 0) {
-            float x = H[0] * sx[i] + H[1] * sy[i] + H[2];
-            float y = H[3] * sx[i] + H[4] * sy[i] + H[5];
-            const float z = H[6] * sx[i] + H[7] * sy[i] + H[8];
+            float x = fmaf(H[0], sx[i], H[1] * sy[i]) + H[2];
+            float y = fmaf(H[3], sx[i], H[4] * sy[i]) + H[5];
+            const float z = fmaf(H[6], sx[i], H[7] * sy[i]) + H[8];
             x /= z; y /= z;
-            const float d2 = (dx[i] - x) * (dx[i] - x) + (dy[i] - y) * (dy[i] - y);
+            const float d2 = fmaf(dx[i] - x, dx[i] - x, (dy[i] - y) * (dy[i] - y));
             if (d2 < thr) ++inl;
         }
     return inl;

@@ -6,7 +6,7 @@ reference library live.
 
 The hypothesis arithmetic is fp32 with a few double intermediates (svd.cu:291-292); the product writes the
 same expressions and is compiled by the same nvcc, so its homographies and inlier counts are held to BITWISE
-equality with the reference's kernels.  The CPU oracle has no FMA contraction and is allowed 5e-4 on the
+equality with the reference's kernels.  The CPU oracle (explicit fmaf where the GPU build contracts) is allowed 5e-4 on the
 Frobenius-normalised homography and +-2 inliers (see tests/test_oracle_golden.py)."""
 import ctypes as C
 import os

@@ -169,21 +169,22 @@ def test_align_points_oracle_vs_reference_golden(oracle):
 @pytest.mark.parametrize("kind", [0, 1, 2])
 def test_ransac_hypotheses_oracle_vs_reference_golden(oracle, kind):
     """The reference's hypothesis kernels (ransac.cu:437-520, Jacobi SVD of svd.cu) on the fixture's index lists.
-    Translation is exact.  Similarity / homography: the CPU evaluates a*b+c*d without the GPU's FMA
-    contractions and the null vector of the DLT system is determined up to rounding, so the normalised
-    homography is compared to 5e-4 and the inlier counts to +-2 (measured: 1e-4, 1)."""
+    The oracle writes the fused multiply-adds where the reference's GPU build contracts them (forms established
+    against these vectors): translation and homography are BITWISE, homographies and inlier counts alike; the
+    similarity estimator is bitwise on 97 % of the hypotheses and one ulp off in one translation element on the
+    rest (tolerance 1e-6 on the Frobenius-normalised matrix), inlier counts identical."""
     from tests._util import checker_ransac_hypotheses, normalise_h
     g = np.load(os.path.join(GOLDEN, "ransac_400.npz"))
     H, inl = checker_ransac_hypotheses(oracle.lib, "orc", kind, g["src_x"], g["src_y"], g["dst_x"], g["dst_y"],
                                        g[f"rand_{kind}"], float(g["thr"]))
     Hg, ig = g[f"H_{kind}"], g[f"inliers_{kind}"]
-    assert np.array_equal((H == 0).all(axis=1), (Hg == 0).all(axis=1))
-    if kind == 0:
-        assert np.array_equal(H, Hg) and np.array_equal(inl, ig)
-        return
-    assert np.abs(normalise_h(H) - normalise_h(Hg)).max() < 5e-4
-    assert np.abs(inl - ig).max() <= 2
+    assert np.array_equal(inl, ig)
     assert oracle.lib.orc_ransac_best(_p(inl), len(inl)) == int(ig.argmax())     # first maximum, same winner
+    if kind != 1:
+        assert np.array_equal(H, Hg)
+        return
+    assert (H == Hg).all(axis=1).mean() > 0.95
+    assert np.abs(normalise_h(H) - normalise_h(Hg)).max() < 1e-6
 
 
 # ------------------------------------------------------------------ input preprocessing (SURVEY.md 8f rank 2)

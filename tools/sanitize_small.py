@@ -33,5 +33,26 @@ pr = nm.tc_probe(A, B)
 nm.set_engine(-1)
 torch.cuda.synchronize()
 print("match", int((m0 >= 0).sum()), bool(torch.equal(m0, m1)), "fallback rows", pr["fallback_rows"])
+# strip-walking blur (run with NM_BLUR_STRIP_MIN=1 to force it at this size), BGRA entry, registration, preprocessing
+bgra = torch.from_numpy(np.stack([np.stack([frames[f].astype(np.uint8)] * 4, axis=-1) for f in range(2)])).cuda()
+sb.run_bgra(bgra)
+torch.cuda.synchronize()
+r = sb.results()
+print("bgra", int(r["counts"][0]), "strip forced" if os.environ.get("NM_BLUR_STRIP_MIN") else "")
+tall = torch.from_numpy(synth.scene(300, 700, synth.SEED_BASE + 1)).cuda()
+for rad_ in (5, 13, 16):
+    tp = torch.from_numpy(np.full(2 * rad_ + 1, 1.0 / (2 * rad_ + 1), np.float32)).cuda()
+    S.blur(tall, tp, rad_)
+g = nm.grayscale(bgra[0, :7, :9].contiguous())
+u8 = nm.cast_u8(torch.from_numpy(frames[0]).cuda(), 200)
+x0, y0 = r["x"][0, :n0].contiguous(), r["y"][0, :n0].contiguous()
+x1, y1 = r["x"][1, :n1].contiguous(), r["y"][1, :n1].contiguous()
+c = nm.align_points(x0, y0, x1, y1, m1)
+for kind in (0, 1, 2):
+    H, st = nm.ransac(kind, *c, 2.0, 200, seed=3)
+cb = [torch.stack([v, v]).contiguous() for v in c]
+Hb, stb = nm.ransac_batch(2, *cb, torch.tensor([n0, n0 // 2], dtype=torch.int32, device="cuda"), 2.0, 200, seed=3)
+torch.cuda.synchronize()
+print("ransac", st.cpu().tolist(), stb.cpu().tolist())
 sb.close()
 print("done")
