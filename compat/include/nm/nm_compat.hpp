@@ -262,11 +262,17 @@ template <typename TYPE>
 void transpose(TYPE* odata, const TYPE* idata, int width, int height, cudaStream_t stream = 0);
 
 // ---- gpu/kernels/bgra_2_gray.h (cuda_grayscale), cast.h, undistort.h:29, resample.h:36 -----------------
-// Served instantiations: cuda_grayscale<float>, cuda_cast<float, unsigned char> (the ones the reference
-// instantiates for its pipeline input); cuda_extract_channel / cuda_put_channel / cuda_set_alpha_to_const are
-// not provided.
+// Served instantiations: the ones the reference instantiates (<float>; cuda_cast<float, unsigned char>).
 template <typename OutputType>
 void cuda_grayscale(const uchar4* bgra, OutputType* output, const int width, const int height, cudaStream_t stream = 0);
+template <typename OutputType>
+void cuda_extract_channel(const uchar4* bgra, OutputType* output, const int width, const int height, const int channel,
+                          cudaStream_t stream = 0);
+template <typename InputType>
+void cuda_put_channel(uchar4* bgra, const InputType* input, const int width, const int height, const int channel,
+                      cudaStream_t stream = 0);
+void cuda_set_alpha_to_const(uchar4* bgra, const int width, const int height, const unsigned char val = 255,
+                             cudaStream_t stream = 0);
 template <typename FROM, typename TO>
 void cuda_cast(const FROM* src, const size_t cols, const size_t rows, TO* dst, TO max_val = 0, cudaStream_t stream = 0);
 void cuda_undistort(const float* x, const float* y, const size_t cols, const size_t rows, const float* camera_matrix,

@@ -205,3 +205,29 @@ void transform_blend(uchar4* canvas, const int cw, const int ch, cudaTextureObje
     nm_check(nm_transform_blend_bgra(canvas, cw, ch, frame, fw, fh, nw, nh, mat3x3, tx, ty, frame_mask, canvas_wts, frame_wts, stream),
              "transform_blend");
 }
+
+// bgra_2_gray.h: colour-channel helpers; downsample.h: the uchar4 instantiation (a 32-bit word copy, like float)
+template <>
+void cuda_extract_channel<float>(const uchar4* bgra, float* output, const int width, const int height, const int channel,
+                                 cudaStream_t stream)
+{
+    nm_check(nm_bgra_extract_channel_f32(bgra, output, width, height, channel, stream), "cuda_extract_channel");
+}
+template <>
+void cuda_put_channel<float>(uchar4* bgra, const float* input, const int width, const int height, const int channel,
+                             cudaStream_t stream)
+{
+    nm_check(nm_bgra_put_channel_f32(bgra, input, width, height, channel, stream), "cuda_put_channel");
+}
+void cuda_set_alpha_to_const(uchar4* bgra, const int width, const int height, const unsigned char val, cudaStream_t stream)
+{
+    nm_check(nm_bgra_set_alpha(bgra, width, height, val, stream), "cuda_set_alpha_to_const");
+}
+template <>
+void downsample_by_2<uchar4>(uchar4* result, const int result_width, const int result_height, const uchar4* source,
+                             const int source_width, const int source_height, cudaStream_t stream)
+{
+    nm_check(nm_downsample2_f32(reinterpret_cast<float*>(result), result_width, result_height,
+                                reinterpret_cast<const float*>(source), source_width, source_height, stream),
+             "downsample_by_2<uchar4>");
+}

@@ -188,6 +188,12 @@ int nm_match_tc_probe(const float* A, int nA, const float* B, int nB, float* rec
  * rounds it.  Device pointers; bgra 4-byte aligned. */
 int nm_grayscale_bgra_f32(const void* bgra, float* output, int width, int height, nm_stream_t stream);
 
+/* cuda_extract_channel<float> / cuda_put_channel<float> / cuda_set_alpha_to_const (bgra_2_gray.h; bgra_2_gray.cu:
+ * 33-112).  channel 0..3 = b, g, r, a; put_channel on channel 3 writes 255 like the reference. */
+int nm_bgra_extract_channel_f32(const void* bgra, float* output, int width, int height, int channel, nm_stream_t stream);
+int nm_bgra_put_channel_f32(void* bgra, const float* input, int width, int height, int channel, nm_stream_t stream);
+int nm_bgra_set_alpha(void* bgra, int width, int height, unsigned char val, nm_stream_t stream);
+
 /* cuda_cast<float, unsigned char> (gpu/kernels/cast.h; cast.cu:7-39): dst = (max_val != 0 && src >= max_val)
  * ? max_val : (unsigned char)src. */
 int nm_cast_f32_u8(const float* src, int cols, int rows, unsigned char* dst, unsigned char max_val,

@@ -61,6 +61,9 @@ SIGNATURES = {
     "nm_match_merge_top2": (_i, [_vp, _i, _i, _f, _vp, _vp]),
     "nm_match_tc_probe": (_i, [_vp, _i, _vp, _i, _vp, C.POINTER(_i), _vp, _vp, C.POINTER(_i), C.POINTER(_f), _vp]),
     "nm_grayscale_bgra_f32": (_i, [_vp, _vp, _i, _i, _vp]),
+    "nm_bgra_extract_channel_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "nm_bgra_put_channel_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "nm_bgra_set_alpha": (_i, [_vp, _i, _i, C.c_ubyte, _vp]),
     "nm_cast_f32_u8": (_i, [_vp, _i, _i, _vp, C.c_ubyte, _vp]),
     "nm_undistort_map_f32": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "nm_resample_tex_f32": (_i, [_ull, _vp, _vp, _i, _i, _vp, _vp]),

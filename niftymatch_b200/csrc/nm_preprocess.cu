@@ -84,6 +84,27 @@ __global__ void __launch_bounds__(256) resample_kernel(float* __restrict__ resul
     result[i] = res * 255.9999f;
 }
 
+// extract_channel / put_channel / set_alpha_to_const (bgra_2_gray.cu:33-112): one 32-bit word per pixel
+__global__ void __launch_bounds__(256) extract_channel_kernel(const unsigned* __restrict__ bgra, float* __restrict__ out, long long n,
+                                                              int channel)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)((__ldg(bgra + i) >> (8 * channel)) & 0xffu);
+}
+__global__ void __launch_bounds__(256) put_channel_kernel(unsigned* __restrict__ bgra, const float* __restrict__ in, long long n,
+                                                          int channel)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned v = channel == 3 ? 255u : (unsigned)(unsigned char)in[i];      // alpha is set to 255 (bgra_2_gray.cu:71)
+    bgra[i] = (bgra[i] & ~(0xffu << (8 * channel))) | (v << (8 * channel));
+}
+__global__ void __launch_bounds__(256) set_alpha_kernel(unsigned* __restrict__ bgra, long long n, unsigned val)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) bgra[i] = (bgra[i] & 0x00ffffffu) | (val << 24);
+}
+
 } // namespace
 
 int nm_grayscale_launch(const void* bgra, float* out, long long n, cudaStream_t st)
@@ -142,6 +163,40 @@ extern "C" int nm_resample_tex_f32(unsigned long long tex, const float* x, const
     if (n == 0) return NM_OK;
     if (!tex || !x || !y || !result) return NM_ERR_INVALID;
     resample_kernel<<<(unsigned)nm_div_up64(n, 256), 256, 0, (cudaStream_t)stream>>>(result, (cudaTextureObject_t)tex, n, x, y);
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+extern "C" int nm_bgra_extract_channel_f32(const void* bgra, float* output, int width, int height, int channel, nm_stream_t stream)
+{
+    if (width < 0 || height < 0) return NM_ERR_INVALID;
+    const long long n = (long long)width * height;
+    if (n == 0 || channel < 0 || channel > 3) return NM_OK;          // the reference writes nothing for other channel numbers
+    if (!bgra || !output || (reinterpret_cast<uintptr_t>(bgra) & 3)) return NM_ERR_INVALID;
+    extract_channel_kernel<<<(unsigned)nm_div_up64(n, 256), 256, 0, (cudaStream_t)stream>>>(static_cast<const unsigned*>(bgra), output, n,
+                                                                                           channel);
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+extern "C" int nm_bgra_put_channel_f32(void* bgra, const float* input, int width, int height, int channel, nm_stream_t stream)
+{
+    if (width < 0 || height < 0) return NM_ERR_INVALID;
+    const long long n = (long long)width * height;
+    if (n == 0 || channel < 0 || channel > 3) return NM_OK;
+    if (!bgra || !input || (reinterpret_cast<uintptr_t>(bgra) & 3)) return NM_ERR_INVALID;
+    put_channel_kernel<<<(unsigned)nm_div_up64(n, 256), 256, 0, (cudaStream_t)stream>>>(static_cast<unsigned*>(bgra), input, n, channel);
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+extern "C" int nm_bgra_set_alpha(void* bgra, int width, int height, unsigned char val, nm_stream_t stream)
+{
+    if (width < 0 || height < 0) return NM_ERR_INVALID;
+    const long long n = (long long)width * height;
+    if (n == 0) return NM_OK;
+    if (!bgra || (reinterpret_cast<uintptr_t>(bgra) & 3)) return NM_ERR_INVALID;
+    set_alpha_kernel<<<(unsigned)nm_div_up64(n, 256), 256, 0, (cudaStream_t)stream>>>(static_cast<unsigned*>(bgra), n, val);
     NM_LAUNCH_CHECK();
     return NM_OK;
 }

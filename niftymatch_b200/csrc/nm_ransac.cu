@@ -331,10 +331,13 @@ __global__ void __launch_bounds__(kHypThreads) hypothesis_kernel(const Pairs P, 
 #pragma unroll
     for (int i = 0; i < M; ++i) r[i] = rand_list[it * M + i];
     bool dup = state_all != nullptr && state_all[p * 4] < min_pts;      // not enough correspondences: nothing is estimated
+    const int n = pair_n(P, p);
 #pragma unroll
-    for (int a = 0; a < M; ++a)
+    for (int a = 0; a < M; ++a) {
+        dup |= (unsigned)r[a] >= (unsigned)n;                           // a caller's list with an index outside the arrays
 #pragma unroll
         for (int b = a + 1; b < M; ++b) dup |= r[a] == r[b];
+    }
     if (!dup) {
         float2 src[M], dst[M];
 #pragma unroll

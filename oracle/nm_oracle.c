@@ -1082,3 +1082,19 @@ void orc_transform_blend(unsigned char* canvas, int cw, int ch, const unsigned c
         }
     free(img); free(msk);
 }
+
+/* extract_channel / put_channel / set_alpha_to_const (bgra_2_gray.cu:33-112) */
+void orc_extract_channel(const unsigned char* bgra, float* out, long long n, int channel)
+{
+    if (channel < 0 || channel > 3) return;
+    for (long long i = 0; i < n; ++i) out[i] = (float)bgra[4 * i + channel];
+}
+void orc_put_channel(unsigned char* bgra, const float* in, long long n, int channel)
+{
+    if (channel < 0 || channel > 3) return;
+    for (long long i = 0; i < n; ++i) bgra[4 * i + channel] = channel == 3 ? 255 : to_byte(in[i]);
+}
+void orc_set_alpha(unsigned char* bgra, long long n, unsigned char val)
+{
+    for (long long i = 0; i < n; ++i) bgra[4 * i + 3] = val;
+}

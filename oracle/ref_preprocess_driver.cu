@@ -9,6 +9,7 @@
 #include "undistort.h"
 #include "resample.h"
 #include "cudatex2D.h"
+#include "downsample.h"
 #include <cuda_runtime.h>
 
 #ifndef NM_COMPAT_BUILD
@@ -42,6 +43,36 @@ int NMREF(grayscale)(const unsigned char* bgra, int w, int h, float* out)
     cuda_grayscale<float>(in.p, o.p, w, h, 0);
     const int rc = status();
     o.get(out);
+    return rc;
+}
+
+// extract every channel, write them back rotated (b <- g, g <- r, r <- b, a <- put(3) = 255), then
+// cuda_set_alpha_to_const(alpha): chan_out = 4 float planes, bgra_out = the rewritten frame
+int NMREF(channels)(const unsigned char* bgra, int w, int h, int alpha, float* chan_out, unsigned char* bgra_out)
+{
+    const size_t n = (size_t)w * h;
+    Dev<uchar4> px(n, reinterpret_cast<const uchar4*>(bgra));
+    Dev<float> ch(4 * n);
+    for (int c = 0; c < 4; ++c) cuda_extract_channel<float>(px.p, ch.p + c * n, w, h, c, 0);
+    int rc = status();
+    ch.get(chan_out);
+    cuda_put_channel<float>(px.p, ch.p + 1 * n, w, h, 0, 0);
+    cuda_put_channel<float>(px.p, ch.p + 2 * n, w, h, 1, 0);
+    cuda_put_channel<float>(px.p, ch.p + 0 * n, w, h, 2, 0);
+    cuda_put_channel<float>(px.p, ch.p + 0 * n, w, h, 3, 0);
+    if (alpha >= 0) cuda_set_alpha_to_const(px.p, w, h, (unsigned char)alpha, 0);
+    rc = rc ? rc : status();
+    px.get(reinterpret_cast<uchar4*>(bgra_out));
+    return rc;
+}
+
+int NMREF(downsample_bgra)(const unsigned char* bgra, int w, int h, unsigned char* out)
+{
+    const int rw = w / 2, rh = h / 2;
+    Dev<uchar4> px((size_t)w * h, reinterpret_cast<const uchar4*>(bgra)), o((size_t)rw * rh);
+    downsample_by_2<uchar4>(o.p, rw, rh, px.p, w, h, 0);
+    const int rc = status();
+    o.get(reinterpret_cast<uchar4*>(out));
     return rc;
 }
 

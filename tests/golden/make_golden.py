@@ -136,6 +136,13 @@ def preprocess(outdir):
     res = np.zeros((h, w), np.float32)
     assert ref.lib.nmref_resample_undistort(_p(d["gray8"]), w, h, _p(u), _p(v), w, h, _p(res)) == 0
     out["resampled"] = res
+    chans = np.zeros((4, h, w), np.float32)
+    rot = np.zeros((h, w, 4), np.uint8)
+    assert ref.lib.nmref_channels(_p(d["bgra"]), w, h, 77, _p(chans), _p(rot)) == 0
+    out["channels"], out["rotated_alpha77"] = chans, rot
+    half = np.zeros((h // 2, w // 2, 4), np.uint8)
+    assert ref.lib.nmref_downsample_bgra(_p(d["bgra"]), w, h, _p(half)) == 0
+    out["bgra_half"] = half
     print("preprocess: gray", gray.min(), gray.max(), "cast", out["cast_0"][0, :8], out["cast_0"][1, :6], "u", u.min(), u.max(),
           "resampled", res.min(), res.max())
     np.savez_compressed(os.path.join(outdir, "preprocess_160x96.npz"), **out)

@@ -56,7 +56,8 @@ def test_exported_cxx_symbols():
                 "DivUp", "AlignDown", "align_points(", "ransac_homography(", "ransac_translation(", "ransac_similarity(",
                 "void cuda_grayscale<float>(", "void cuda_cast<float, unsigned char>(", "cuda_undistort(", "resample_undistort(",
                 "resample_perspective_transform(", "resample_mask(", "transform_blend(", "CudaUtils::get_max_flops_device_id()",
-                "CudaUtils::setup_CUDA(int)"]:
+                "CudaUtils::setup_CUDA(int)", "void cuda_extract_channel<float>(", "void cuda_put_channel<float>(", "cuda_set_alpha_to_const(",
+                "void downsample_by_2<uchar4>("]:
         assert sym in out, sym
 
 

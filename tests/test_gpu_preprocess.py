@@ -141,6 +141,24 @@ def test_dropin_preprocess_headers(nm):
     assert np.array_equal(res, g["resampled"])          # same texture unit, same filtering arithmetic
 
 
+def test_channel_helpers_and_bgra_downsample_vs_reference_golden(nm):
+    """cuda_extract_channel / cuda_put_channel / cuda_set_alpha_to_const / downsample_by_2<uchar4> of the drop-in
+    headers, through the client code that drives the reference."""
+    client = os.path.abspath(os.path.join(os.path.dirname(GOLDEN), os.pardir, "build", "compat", "libnmcompat.so"))
+    if not os.path.exists(client):
+        pytest.skip("build/compat/libnmcompat.so not built")
+    cl = C.CDLL(client)
+    g = _gold()
+    h, w = g["fimg"].shape
+    chans, rot = np.zeros((4, h, w), np.float32), np.zeros((h, w, 4), np.uint8)
+    assert cl.nmcompat_channels(_p(g["bgra"]), w, h, 77, _p(chans), _p(rot)) == 0
+    assert np.array_equal(chans, g["channels"]) and np.array_equal(rot, g["rotated_alpha77"])
+    assert np.array_equal(chans, np.moveaxis(g["bgra"], 2, 0).astype(np.float32))
+    half = np.zeros((h // 2, w // 2, 4), np.uint8)
+    assert cl.nmcompat_downsample_bgra(_p(g["bgra"]), w, h, _p(half)) == 0
+    assert np.array_equal(half, g["bgra_half"]) and np.array_equal(half, g["bgra"][::2, ::2][: h // 2, : w // 2])
+
+
 def test_preprocess_bad_arguments(nm):
     lib = nm.load()
     t = torch.zeros(64, device="cuda")

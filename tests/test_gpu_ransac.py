@@ -159,6 +159,10 @@ def test_too_few_correspondences_and_bad_arguments(nm):
     assert lib.nm_ransac_f32(0, p, p, p, p, 50, 4.0, 0, 0, p, p, None) == -1
     assert lib.nm_ransac_f32(0, p, p, p, p, 50, 4.0, 10, 0, None, p, None) == -1
     assert lib.nm_ransac_hypotheses_f32(0, p, p, p, p, 50, None, 10, 4.0, p, p, None) == -1
+    # an index outside the arrays in a caller's list: that iteration is skipped (H = 0, 0 inliers), nothing is read
+    rl = torch.tensor([3, 9, 20, 7, 3, 9, 20, 50, -1, 9, 20, 7], dtype=torch.int32, device="cuda")
+    H, inl = nm.ransac_hypotheses(2, *a, rl, 4.0)
+    assert (H[1:] == 0).all().item() and inl[1:].tolist() == [0, 0]
 
 
 def test_sift_match_ransac_chain(nm):

@@ -205,6 +205,21 @@ def test_preprocess_oracle_vs_reference_golden(oracle):
     assert np.abs(v - g["v"]).max() <= 2e-6 * np.abs(g["v"]).max()
 
 
+def test_channel_helpers_oracle_vs_reference_golden(oracle):
+    g = np.load(os.path.join(GOLDEN, "preprocess_160x96.npz"))
+    h, w = g["fimg"].shape
+    n = C.c_longlong(h * w)
+    px = np.ascontiguousarray(g["bgra"]).copy()
+    ch = np.zeros((4, h, w), np.float32)
+    for c in range(4):
+        oracle.lib.orc_extract_channel(_p(px), _p(ch[c]), n, c)
+    assert np.array_equal(ch, g["channels"])
+    for dst, src in ((0, 1), (1, 2), (2, 0), (3, 0)):
+        oracle.lib.orc_put_channel(_p(px), _p(ch[src]), n, dst)
+    oracle.lib.orc_set_alpha(_p(px), n, C.c_ubyte(77))
+    assert np.array_equal(px, g["rotated_alpha77"])
+
+
 def test_grey_value_identity_all_colours(oracle):
     """The identity the CUDA kernel relies on (nm_preprocess.cu): the reference's double expression equals the
     correctly rounded fp32 quotient (7b + 72g + 21r) / 100 for all 2^24 colours."""
