@@ -15,7 +15,7 @@
 #include <vector>
 
 #define NM_MAX_CHUNKS 64
-#define NM_AUX_STREAMS 3      // nm_sift_run_host: stages rotate over the caller's stream and up to 3 more
+#define NM_AUX_STREAMS 4      // nm_sift_run_host: stages rotate over up to 4 internal compute streams forked from the caller's
 
 struct nm_sift_ctx {
     nm_sift_params P;
@@ -30,6 +30,13 @@ struct nm_sift_ctx {
     cudaStream_t s_in, s_out, s_aux[NM_AUX_STREAMS];   // nm_sift_run_host: H2D / D2H copy streams, extra compute streams
     cudaEvent_t ev_fork, ev_join[NM_AUX_STREAMS];
     cudaEvent_t ev_in[NM_MAX_CHUNKS], ev_done[NM_MAX_CHUNKS], ev_out;
+    // nm_sift_run_host: the ~47 launches of a pipeline stage replayed as one CUDA graph.  A stage's launch
+    // sequence depends only on (first frame, frame count, mask texture, descriptor mode): captured once per key.
+    struct StageGraph {
+        cudaGraphExec_t exec = nullptr;
+        int f0 = -1, n = 0, exact = 0, launches = 0;
+        unsigned long long mask = 0;
+    } stage_graph[NM_MAX_CHUNKS];
     float* taps[6];          // 0: base kernel, 1..5: level kernels (device)
     int    radii[6];
     int *seg_raw, *seg_cnt, *seg_off, *counts, *meta;
@@ -145,6 +152,7 @@ extern "C" int nm_sift_destroy(nm_sift_ctx* c)
     for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (auto* t : c->tma_sets) delete t;
     for (int i = 0; i < NM_MAX_CHUNKS; ++i) {
+        if (c->stage_graph[i].exec) cudaGraphExecDestroy(c->stage_graph[i].exec);
         if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
     }
@@ -434,18 +442,48 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
     static const int n_streams = [] {
         const char* e = getenv("NM_HOST_STREAMS");
         const int v = e ? atoi(e) : 4;
-        return v < 1 ? 1 : v > NM_AUX_STREAMS + 1 ? NM_AUX_STREAMS + 1 : v;
+        return v < 1 ? 1 : v > NM_AUX_STREAMS ? NM_AUX_STREAMS : v;
     }();
+    // NM_HOST_GRAPH=0: launch the stages kernel by kernel (tuning aid); with several stages the launches of a stage
+    // are replayed as one CUDA graph (11 stages x 47 launches per 64-frame call otherwise)
+    static const bool graphs_on = [] {
+        const char* e = getenv("NM_HOST_GRAPH");
+        return !(e && e[0] == '0');
+    }();
+    const bool use_graphs = graphs_on && n_chunks > 1 && !trace;
     NM_CUDA_TRY(cudaEventRecord(c->ev_fork, st));
-    for (int i = 0; i + 1 < n_streams; ++i) NM_CUDA_TRY(cudaStreamWaitEvent(c->s_aux[i], c->ev_fork, 0));
+    // every stage runs on an internal stream (the caller's may be the legacy default stream, which cannot be captured)
+    for (int i = 0; i < n_streams; ++i) NM_CUDA_TRY(cudaStreamWaitEvent(c->s_aux[i], c->ev_fork, 0));
     for (int k = 0; k < n_chunks; ++k) {
         const int f0 = bounds[k], n = bounds[k + 1] - bounds[k];
-        cudaStream_t sk = (k % n_streams) ? c->s_aux[k % n_streams - 1] : st;
+        cudaStream_t sk = c->s_aux[k % n_streams];
         NM_CUDA_TRY(cudaStreamWaitEvent(sk, c->ev_in[k], 0));
         if (trace) cudaEventRecord(tr_k0[k], sk);
-        int rc = sift_run_range(c, c->frames_stage + f0 * fpix, f0, n, sk, false);
-        if (rc != NM_OK) return rc;
-        launches += c->last_launches;
+        int rc;
+        if (use_graphs) {
+            nm_sift_ctx::StageGraph& g = c->stage_graph[k];
+            if (!g.exec || g.f0 != f0 || g.n != n || g.mask != c->mask_tex || g.exact != c->exact_desc) {
+                if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+                cudaGraph_t graph = nullptr;
+                NM_CUDA_TRY(cudaStreamBeginCapture(sk, cudaStreamCaptureModeThreadLocal));
+                rc = sift_run_range(c, c->frames_stage + f0 * fpix, f0, n, sk, false);
+                const cudaError_t ce = cudaStreamEndCapture(sk, &graph);
+                if (rc != NM_OK || ce != cudaSuccess) {
+                    if (graph) cudaGraphDestroy(graph);
+                    return rc != NM_OK ? rc : nm_cuda_err(ce);
+                }
+                const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ie != cudaSuccess) { g.exec = nullptr; return nm_cuda_err(ie); }
+                g.f0 = f0; g.n = n; g.mask = c->mask_tex; g.exact = c->exact_desc; g.launches = c->last_launches;
+            }
+            NM_CUDA_TRY(cudaGraphLaunch(g.exec, sk));
+            launches += g.launches;
+        } else {
+            rc = sift_run_range(c, c->frames_stage + f0 * fpix, f0, n, sk, false);
+            if (rc != NM_OK) return rc;
+            launches += c->last_launches;
+        }
         NM_CUDA_TRY(cudaMemcpyAsync(counts_host + f0, c->counts + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, sk));
         NM_CUDA_TRY(cudaEventRecord(c->ev_done[k], sk));
         if (trace) cudaEventRecord(tr_k1[k], sk);
@@ -459,7 +497,7 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
         if (rc != NM_OK) return rc;
     }
     // the caller's stream is complete when all compute streams and the result copies are
-    for (int i = 0; i + 1 < n_streams; ++i) {
+    for (int i = 0; i < n_streams; ++i) {
         NM_CUDA_TRY(cudaEventRecord(c->ev_join[i], c->s_aux[i]));
         NM_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join[i], 0));
     }
