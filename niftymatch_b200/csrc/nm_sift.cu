@@ -386,18 +386,19 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
     if (!c || !frames_host || !counts_host || n_frames <= 0 || n_frames > c->B) return NM_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t fpix = (size_t)c->P.width * c->P.height;
-    // Pipeline stages: the uploads pace the pipeline (1080p: 6.7 frames/ms over PCIe against 7.1 frames/ms
-    // of kernels at full batch), so the end-to-end time is (all uploads) + (what the kernels still have to
-    // do when the last frame lands).  Small stages keep that tail short; their under-filled launches
-    // (octaves 2+ are a fraction of a wave) are covered by running up to four stages concurrently on
-    // separate streams.  Measured at 64 x 1080p: 6-frame stages on 4 streams 12.5 ms, 8 on 2: 12.8,
-    // 14-frame stages with small edge stages on 2 (previous schedule): 13.9.
-    // NM_HOST_CHUNK=<n> / NM_HOST_STREAMS=<1..4> override (tuning aid).
+    // Pipeline stages: the uploads pace the pipeline (1080p: 6.7 frames/ms over PCIe against 7.5 frames/ms of
+    // kernels at full batch), so the end-to-end time is (all uploads) + (what the kernels still have to do when
+    // the last frame lands).  Small stages keep that tail short; their under-filled launches (octaves 2+ are a
+    // fraction of a wave) are covered by running up to four stages concurrently on separate streams, and their
+    // launch cost by replaying each stage as one CUDA graph.  Measured at 64 x 1080p, 4 streams, graphs:
+    // stages of 3 frames 11.45 ms, 4: 11.67, 5: 11.60, 6: 11.73, 8: 12.16 (uploads alone: 9.58 ms);
+    // without graphs 6-frame stages were best at 12.33.
+    // NM_HOST_CHUNK=<n> / NM_HOST_STREAMS=<1..4> / NM_HOST_GRAPH=0 override (tuning aids).
     static const int forced = [] {
         const char* e = getenv("NM_HOST_CHUNK");
         return e ? atoi(e) : 0;
     }();
-    const int stage = forced > 0 ? forced : 6;
+    const int stage = forced > 0 ? forced : 3;
     int bounds[NM_MAX_CHUNKS + 1];
     int n_chunks = 0;
     bounds[0] = 0;
@@ -437,8 +438,8 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
         NM_CUDA_TRY(cudaEventRecord(c->ev_in[k], c->s_in));
         if (trace) cudaEventRecord(tr_in[k], c->s_in);
     }
-    // stages alternate between the caller's stream and a second one (forked from it): the launch-bound
-    // tail of one stage (small octaves, orientation) overlaps the big blur kernels of the next
+    // stages rotate over the internal compute streams: the launch-bound tail of one stage (small octaves,
+    // orientation) overlaps the big blur kernels of the next
     static const int n_streams = [] {
         const char* e = getenv("NM_HOST_STREAMS");
         const int v = e ? atoi(e) : 4;

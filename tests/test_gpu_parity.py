@@ -410,7 +410,7 @@ def test_masked_detector_batched_vs_reference_and_oracle(nm, oracle):
 
 def test_run_host_pipeline_equals_device_run(nm):
     """nm_sift_run_host splits a batch into stages of a few frames that run concurrently on several
-    streams (H2D, kernels and D2H overlapped).  20 frames = 4 stages: counts, descriptors and coordinates
+    streams (H2D, kernels and D2H overlapped).  20 frames = 7 stages (each replayed as a CUDA graph on the second call): counts, descriptors and coordinates
     must be bitwise those of the single whole-batch nm_sift_run on device-resident frames."""
     n = 20
     frames = np.stack([synth.scene(256, 192, synth.SEED_BASE + (i % 5), shift=(0.5 * (i // 5), 0.25 * (i // 5)))
