@@ -56,6 +56,18 @@ def test_preprocess_vs_reference_golden(nm):
         assert np.array_equal(nm.cast_u8(_cu(g["fimg"]), mv).cpu().numpy(), g[f"cast_{mv}"]), mv
     u, v = nm.undistort_map(_cu(g["x"]), _cu(g["y"]), _cu(g["cam"]), _cu(g["dist"]))
     assert np.array_equal(u.cpu().numpy(), g["u"]) and np.array_equal(v.cpu().numpy(), g["v"])
+    # pointers that are not 16-byte aligned and a length that is not a multiple of 4: the one-element kernels
+    n = g["fimg"].size - 3
+    f1 = _cu(g["fimg"]).flatten()[1: 1 + n].view(1, n)
+    assert f1.data_ptr() % 16 == 4
+    assert np.array_equal(nm.cast_u8(f1, 200).cpu().numpy().ravel(), g["cast_200"].ravel()[1: 1 + n])
+    x1, y1 = _cu(g["x"]).flatten()[1: 1 + n].view(1, n), _cu(g["y"]).flatten()[1: 1 + n].view(1, n)
+    u1, v1 = nm.undistort_map(x1, y1, _cu(g["cam"]), _cu(g["dist"]))
+    assert np.array_equal(u1.cpu().numpy().ravel(), g["u"].ravel()[1: 1 + n])
+    assert np.array_equal(v1.cpu().numpy().ravel(), g["v"].ravel()[1: 1 + n])
+    # aligned start, ragged tail (quads + 1..3 single elements)
+    f2 = _cu(g["fimg"]).flatten()[: n].view(1, n)
+    assert np.array_equal(nm.cast_u8(f2, 0).cpu().numpy().ravel(), g["cast_0"].ravel()[: n])
 
 
 def test_preprocess_vs_oracle(nm, oracle):
