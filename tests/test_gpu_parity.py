@@ -436,6 +436,41 @@ def test_run_host_pipeline_equals_device_run(nm):
     sb.close()
 
 
+def test_run_host_graphs_follow_the_context_state(nm):
+    """The stage graphs of nm_sift_run_host are keyed by (frames, mask texture, descriptor mode): changing the mask or
+    the descriptor mode between calls re-captures them, and the results equal the kernel-by-kernel nm_sift_run."""
+    n, w, h = 12, 256, 192
+    frames = np.stack([synth.scene(w, h, synth.SEED_BASE + 20 + i) for i in range(n)])
+    yy, xx = np.mgrid[0:h, 0:w]
+    mask = (((xx - w / 2) ** 2 + (yy - h / 2) ** 2) < (0.4 * h) ** 2).astype(np.float32)
+    sb = nm.SiftBatch(nm.SiftParams(w, h), n, 2048)
+    pinned = torch.from_numpy(frames).pin_memory()
+    dev = torch.from_numpy(frames).cuda()
+
+    def both():
+        out = sb.run_host(pinned)
+        c_host, d_host = out["counts"].numpy().copy(), out["desc"].numpy().copy()
+        sb.run(dev)
+        torch.cuda.synchronize()
+        r = sb.results()
+        c_dev, d_dev = r["counts"].cpu().numpy(), r["desc"].cpu().numpy()
+        assert np.array_equal(c_host, c_dev)
+        for f in range(n):
+            assert np.array_equal(d_host[f, : c_dev[f]], d_dev[f, : c_dev[f]]), f
+        return c_dev.copy()
+
+    plain = both()
+    sb.set_mask(mask)
+    masked = both()
+    assert (masked < plain).all() and (masked > 0).all()
+    sb.set_exact_descriptor(True)
+    both()
+    sb.set_exact_descriptor(False)
+    sb.set_mask(None)
+    assert np.array_equal(both(), plain)
+    sb.close()
+
+
 def test_4k_six_octave_pyramid_and_extrema_vs_oracle(nm, oracle):
     """BASELINE.json configs[2]: 3840x2160, octave count forced to 6 (the default would be 7):
     Gaussian levels bitwise, keypoints bitwise, against the CPU oracle."""
