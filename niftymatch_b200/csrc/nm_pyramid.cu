@@ -419,6 +419,8 @@ __global__ void __launch_bounds__(kThreads, 2) blur_strip_kernel(const NmBlurArg
                 w4[i] = make_float4(nm_gray_from_bgra(__float_as_uint(q.x)), nm_gray_from_bgra(__float_as_uint(q.y)),
                                     nm_gray_from_bgra(__float_as_uint(q.z)), nm_gray_from_bgra(__float_as_uint(q.w)));
             }
+            // these generic-proxy writes are followed by the next chunk's TMA write to the same bytes (async proxy)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
         }
         strip_row_pass<R>(s_in, s_ring, t, tid, (c & 1) * kCH, pre ? kCH - 2 * R : 0, c * kCH - R, a.h);
