@@ -76,7 +76,6 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -283,6 +282,13 @@ def main():
     for _ in range(args.steps):
         sb.run(frames_dev)
     e1.record(stream)
+    if rank == 0:
+        # the timed region lasts ~0.1 s, about one nvidia-smi period: keep the SAME load running (untimed, after the
+        # closing event) until the sampler has seen it at least three times, so the clocks line is always "under load"
+        t_lim = time.perf_counter() + 4.0
+        while len(sampler.lines) < 3 and time.perf_counter() < t_lim:
+            sb.run(frames_dev)
+            torch.cuda.synchronize()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
