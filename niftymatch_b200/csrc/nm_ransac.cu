@@ -19,8 +19,12 @@
 //    memory; here a CTA stages a block of correspondences in shared memory once and each of its threads
 //    scores one hypothesis against it (grid = hypothesis blocks x correspondence blocks, integer atomics,
 //    so the counts are exact and order independent);
+//  * nm_ransac_batch_f32 estimates many frame pairs in one launch sequence (every kernel indexes the pair by a
+//    grid dimension): a hypothesis is a long dependent chain (5-9 Jacobi sweeps of 36 rotations, ~1 ms), so
+//    one pair at a time leaves the GPU idle; 64 pairs cost 43 us each;
 //  * nm_ransac_hypotheses_f32 takes the caller's index list: that is the entry the parity tests drive with
-//    the list they also hand to the reference's own kernels.
+//    the list they also hand to the reference's own kernels (homographies and inlier counts are bitwise the
+//    reference's on the same lists, tests/test_gpu_ransac.py).
 #include "nm_common.cuh"
 
 namespace {
