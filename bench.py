@@ -315,6 +315,37 @@ def main():
     e2e = {"value": BATCH * world / e2e_ms * 1e3, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms}
 
+    # ---- auxiliary: registration of 64 frame pairs (batched homography RANSAC), rank 0 only ----
+    registration = None
+    if rank == 0 and not args.no_match:
+        try:
+            rng = np.random.default_rng(7)
+            n_pairs, n_pts, iters = 64, 8192, 1024
+            sx = (rng.random((n_pairs, n_pts)) * 1900).astype(np.float32)
+            sy = (rng.random((n_pairs, n_pts)) * 1060).astype(np.float32)
+            dx = (1.01 * sx + 0.02 * sy + 5.0 + rng.normal(0, 0.3, sx.shape)).astype(np.float32)
+            dy = (-0.02 * sx + 0.99 * sy - 3.0 + rng.normal(0, 0.3, sx.shape)).astype(np.float32)
+            bad = rng.random(sx.shape) < 0.3
+            dx[bad] = (rng.random(int(bad.sum())) * 1900).astype(np.float32)
+            pts = [torch.from_numpy(a).cuda() for a in (sx, sy, dx, dy)]
+            for _ in range(3):
+                Hr, st_r = nm.ransac_batch(nm.HOMOGRAPHY, *pts, None, 4.0, iters, seed=1)
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            for _ in range(5):
+                Hr, st_r = nm.ransac_batch(nm.HOMOGRAPHY, *pts, None, 4.0, iters, seed=1)
+            r1.record(stream)
+            torch.cuda.synchronize()
+            rms = r0.elapsed_time(r1) / 5
+            registration = {"metric": "ransac_homography_pairs_per_s", "value": n_pairs / rms * 1e3, "unit": "pairs/s",
+                            "ms_per_batch": rms, "config": {"workload": "64 frame pairs x 8192 correspondences (30 % outliers) x "
+                                                            "1024 hypotheses, nm_ransac_batch_f32, no host round trip"},
+                            "median_inliers": float(st_r[:, 1].float().median().item())}
+            del pts
+        except Exception as exc:                                 # auxiliary line: never fail the bench over it
+            registration = {"error": repr(exc)}
+
     # ---- auxiliary: 100k x 100k matching, database sharded over the ranks --------------------
     match = None
     if not args.no_match:
@@ -390,7 +421,7 @@ def main():
                        "l2": "inputs (531 MB per step) larger than L2", "parallelism": f"frames sharded x{world}"},
             "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps * world),
             "launches_per_step": launches_per_step, "clocks": clocks, "stages_ms": stage,
-            "roofline": roofline, "cpu_baseline": cb, "match": match,
+            "roofline": roofline, "cpu_baseline": cb, "match": match, "registration": registration,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
