@@ -324,7 +324,11 @@ int nm_sift_results(nm_sift_ctx* ctx, const float** desc, const float** x, const
 /* Pyramid level `level` (0..5) of `octave` for `frame`: pointer, pitch (floats), w, h. */
 int nm_sift_level(nm_sift_ctx* ctx, int frame, int octave, int level, const float** ptr,
                   int* pitch, int* w, int* h);
-/* Gradient map (float2) of DoG level `level` (0..2) of `octave` for `frame`. */
+/* Gradient map (float2) of DoG level `level` (0..2) of `octave` for `frame`.  By default only the 8-row x
+ * 32-column blocks that an orientation / descriptor window of an emitted keypoint reads are computed (the
+ * reference's compute_gradients, siftfunctions.cu:53-63, fills whole maps; their other pixels are never read
+ * by compute_orientations / compute_descriptors); call nm_sift_set_dense_gradients(ctx, 1) before a run
+ * whose whole maps are to be read. */
 int nm_sift_grad(nm_sift_ctx* ctx, int frame, int octave, int level, const float** ptr2,
                  int* pitch, int* w, int* h);
 /* Number of kernels the last nm_sift_run enqueued (for launch accounting). */
@@ -337,6 +341,10 @@ int nm_sift_enable_timing(nm_sift_ctx* ctx, int enable);
  * 1 = the reference's mixed fp64/fp32 expression shapes (validation mode). */
 int nm_sift_set_exact_descriptor(nm_sift_ctx* ctx, int exact);
 int nm_sift_stage_ms(nm_sift_ctx* ctx, float* ms6);
+/* {pyramid, extrema, compaction, gradient maps, orientation, descriptor, total} of the last timed run. */
+int nm_sift_stage_ms7(nm_sift_ctx* ctx, float* ms7);
+/* 1 = gradient maps of every pixel (see nm_sift_grad); 0 (default) = only where keypoint windows read. */
+int nm_sift_set_dense_gradients(nm_sift_ctx* ctx, int dense);
 
 #ifdef __cplusplus
 }

@@ -89,6 +89,8 @@ SIGNATURES = {
     "nm_sift_last_launches": (_i, [_vp]),
     "nm_sift_enable_timing": (_i, [_vp, _i]),
     "nm_sift_stage_ms": (_i, [_vp, _vp]),
+    "nm_sift_stage_ms7": (_i, [_vp, _vp]),
+    "nm_sift_set_dense_gradients": (_i, [_vp, _i]),
     "nm_sift_set_exact_descriptor": (_i, [_vp, _i]),
 }
 

@@ -21,6 +21,7 @@
 #include "nm_sift_internal.cuh"
 #include "nm_pyramid.cuh"
 #include "nm_refine.cuh"
+#include "nm_kpgeom.cuh"
 #include <cstdlib>
 
 namespace {
@@ -205,6 +206,246 @@ __global__ void __launch_bounds__(256, 4) extrema_grad_kernel(const NmOctave oc,
     }
 }
 
+// ------------------------- split pipeline: extrema without gradients -------------------------
+// DoG values formed on the fly from the staged Gaussian levels (cudamath.cu:34: next - this).
+struct SmemLevelFetch {
+    const float (*lv)[EX_ROWS][EX_P];      // [6]
+    int l, r, c;                           // detection level (0..2), window row / column of the centre
+    __device__ __forceinline__ float dogv(int k, int dx, int dy) const
+    {
+        return __fsub_rn(lv[k + 1][r + dy][c + dx], lv[k][r + dy][c + dx]);
+    }
+    __device__ __forceinline__ float cur(int dx, int dy) const { return dogv(l + 1, dx, dy); }
+    __device__ __forceinline__ float down(int dx, int dy) const { return dogv(l, dx, dy); }
+    __device__ __forceinline__ float up(int dx, int dy) const { return dogv(l + 2, dx, dy); }
+};
+
+constexpr int EX2_MAXC = EX_TW * EX_TH * 3;                     // every pixel of every level a candidate: cannot overflow
+constexpr int EX2_SMEM = 2 * (int)EX_TILE_BYTES + EX2_MAXC * (int)sizeof(unsigned short) + 2 * 3 * EX_TH * 4 + 64;
+
+// Persistent CTAs walk the 32 x 32 tiles of a launch (x fastest, so the CTAs in flight work on neighbouring
+// tiles and the halo columns / rows they share are L2 hits).  The six-level window of the NEXT tile is
+// fetched by TMA into the other half of a double buffer while the current one is processed: the window is
+// read-only (the DoG differences are formed in registers), so no thread ever waits for a load at CTA start
+// (13.8 % of the stall samples of the fused round-1 kernel) and the DoG pass with its barrier is gone.
+// Per tile: (1) the separable 26-neighbour test for 4 pixels x 3 levels per thread, the Gaussian levels carried
+// in registers from one DoG level to the next; extremum candidates (about 0.2 % of the pixels) go to a list in
+// shared memory; (2) the list is refined by consecutive threads (a warp refines 32 candidates at once instead of
+// one 32-pixel row with a single live lane); accepted pixels set bits in a shared-memory copy of the tile's
+// bitmap rows; (3) 96 threads store the rows.  Gradient maps are not produced here (gradmap_kernel).
+__global__ void __launch_bounds__(256, 2) extrema_kernel(const NmOctave oc, const NmDetectParams dp,
+                                                         const __grid_constant__ CUtensorMap tmap,
+                                                         int tiles_x, int tiles_y, int n_tiles)
+{
+    extern __shared__ __align__(128) unsigned char ex_smem[];
+    float (*s_win)[6][EX_ROWS][EX_P] = reinterpret_cast<float (*)[6][EX_ROWS][EX_P]>(ex_smem);      // [2]
+    unsigned short* s_cand = reinterpret_cast<unsigned short*>(ex_smem + 2 * EX_TILE_BYTES);
+    unsigned (*s_bits)[3][EX_TH] = reinterpret_cast<unsigned (*)[3][EX_TH]>(ex_smem + 2 * EX_TILE_BYTES + EX2_MAXC * 2);   // [2]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(ex_smem + 2 * EX_TILE_BYTES + EX2_MAXC * 2 + 2 * 3 * EX_TH * 4);        // [2]
+    int* s_ncand = reinterpret_cast<int*>(s_bar + 2);                                                                      // [2]
+    const int tid = threadIdx.y * 32 + threadIdx.x, lane = threadIdx.x;
+    const long long bm_words = (long long)oc.h * oc.wpr;
+    const int nrb = (oc.h + NM_NEED_ROWS - 1) / NM_NEED_ROWS;
+
+    auto issue = [&](int tile, int buf) {
+        const int tx = tile % tiles_x, q = tile / tiles_x, ty = q % tiles_y, f = q / tiles_y;
+        const uint32_t bar = ex_smem_u32(&s_bar[buf]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(EX_TILE_BYTES) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(ex_smem_u32(&s_win[buf][0][0][0])), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(tx * EX_TW - EX_HL),
+              "r"(ty * EX_TH - 1), "r"(f * 6), "r"(bar) : "memory");
+    };
+
+    int tile = blockIdx.x;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ex_smem_u32(&s_bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ex_smem_u32(&s_bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_ncand[0] = s_ncand[1] = 0;
+        if (tile < n_tiles) issue(tile, 0);
+    }
+    if (tid < 2 * 3 * EX_TH) (&s_bits[0][0][0])[tid] = 0u;
+    __syncthreads();
+
+    const float t = __fmul_rn(0.8f, dp.peak);
+    for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
+        const int buf = it & 1;
+        const int tx = tile % tiles_x, q = tile / tiles_x, ty = q % tiles_y, f = q / tiles_y;
+        const int x0 = tx * EX_TW, y0 = ty * EX_TH;
+        // the other buffer was last read before the closing barrier of the previous iteration
+        if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, buf ^ 1);
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "LAB_WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra LAB_DONE_%=;\n"
+            "bra LAB_WAIT_%=;\n"
+            "LAB_DONE_%=:\n"
+            "}\n" ::"r"(ex_smem_u32(&s_bar[buf])), "r"((it >> 1) & 1) : "memory");
+        const float (*L)[EX_ROWS][EX_P] = s_win[buf];
+
+        // ---- (1) separable 26-neighbour test, same comparisons as keypoint.cu:19-105 / :195-196 ----
+        unsigned extmask = 0;                      // bit l * 4 + j
+        {
+            const int c = lane + EX_HL, rbase = threadIdx.y * (EX_TH / 8);     // window row of the first pixel's upper neighbour
+            float lo[6][3];                        // Gaussian level k at the thread's 6 rows x 3 columns
+#pragma unroll
+            for (int rr = 0; rr < 6; ++rr) {
+                lo[rr][0] = L[0][rbase + rr][c - 1]; lo[rr][1] = L[0][rbase + rr][c]; lo[rr][2] = L[0][rbase + rr][c + 1];
+            }
+            float m9x[3][4], m9n[3][4];            // ring over k % 3: 3x3 maxima / minima, centre included
+            float m8x[4], m8n[4], cv[4];           // DoG level k - 1 (centre excluded) and its centre values
+            float p8x[4], p8n[4], pcv[4];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                float hx[6], hn[6], gxm[6], gnm[6], ctr[6];
+#pragma unroll
+                for (int rr = 0; rr < 6; ++rr) {
+                    const float u0 = L[k + 1][rbase + rr][c - 1], u1 = L[k + 1][rbase + rr][c], u2 = L[k + 1][rbase + rr][c + 1];
+                    const float a = __fsub_rn(u0, lo[rr][0]), b = __fsub_rn(u1, lo[rr][1]), d = __fsub_rn(u2, lo[rr][2]);
+                    lo[rr][0] = u0; lo[rr][1] = u1; lo[rr][2] = u2;
+                    hx[rr] = fmaxf(fmaxf(a, b), d);
+                    hn[rr] = fminf(fminf(a, b), d);
+                    gxm[rr] = fmaxf(a, d);
+                    gnm[rr] = fminf(a, d);
+                    ctr[rr] = b;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    m9x[k % 3][j] = fmaxf(fmaxf(hx[j], hx[j + 1]), hx[j + 2]);
+                    m9n[k % 3][j] = fminf(fminf(hn[j], hn[j + 1]), hn[j + 2]);
+                    p8x[j] = m8x[j]; p8n[j] = m8n[j]; pcv[j] = cv[j];
+                    m8x[j] = fmaxf(fmaxf(hx[j], gxm[j + 1]), hx[j + 2]);
+                    m8n[j] = fminf(fminf(hn[j], gnm[j + 1]), hn[j + 2]);
+                    cv[j] = ctr[j + 1];
+                }
+                if (k >= 2) {
+                    const int l = k - 2;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float mx = fmaxf(fmaxf(m9x[(k - 2) % 3][j], p8x[j]), m9x[k % 3][j]);
+                        const float mn = fminf(fminf(m9n[(k - 2) % 3][j], p8n[j]), m9n[k % 3][j]);
+                        const float c0 = pcv[j];
+                        if ((c0 <= t && c0 < mn) || (c0 >= t && c0 > mx)) extmask |= 1u << (l * 4 + j);
+                    }
+                }
+            }
+            // interior pixels only (keypoint.cu:191)
+            const int gx = x0 + lane;
+            if (!(gx >= 1 && gx <= oc.w - 2)) extmask = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int gy = y0 + rbase + j;
+                if (!(gy >= 1 && gy <= oc.h - 2)) extmask &= ~(0x111u << j);
+            }
+        }
+        if (extmask) {
+            const int n = __popc(extmask);
+            int pos = atomicAdd(&s_ncand[buf], n);
+            while (extmask) {
+                const int b = __ffs(extmask) - 1;
+                extmask &= extmask - 1;
+                // level (2 bits) | tile row (5 bits) | tile column (5 bits)
+                s_cand[pos++] = (unsigned short)(((b >> 2) << 10) | ((threadIdx.y * (EX_TH / 8) + (b & 3)) << 5) | lane);
+            }
+        }
+        // this tile's blocks of the gradient-need map start clear (marked by emit_kernel, read by gradmap_kernel)
+        if (tid < 3 * (EX_TH / NM_NEED_ROWS)) {
+            const int l = tid / (EX_TH / NM_NEED_ROWS), rb = ty * (EX_TH / NM_NEED_ROWS) + tid % (EX_TH / NM_NEED_ROWS);
+            if (rb < nrb) oc.need[(((long long)f * 3 + l) * nrb + rb) * oc.wpr + tx] = 0;
+        }
+        __syncthreads();
+
+        // ---- (2) refinement of the listed candidates (keypoint.cu:108-180, 214) ----
+        const int ncand = s_ncand[buf];
+        for (int i = tid; i < ncand; i += 256) {
+            const unsigned e = s_cand[i];
+            const int l = e >> 10, ly = (e >> 5) & 31, lx = e & 31;
+            const int gx = x0 + lx, gy = y0 + ly;
+            const bool masked_out = dp.mask != 0 &&
+                tex2D<float>((cudaTextureObject_t)dp.mask, (gx + 0.5f) * oc.xper, (gy + 0.5f) * oc.xper) < 1.f;
+            if (!masked_out) {
+                SmemLevelFetch ft{L, l, ly + 1, lx + EX_HL};
+                float4 out;
+                if (nm_refine(ft, gx, gy, dp.peak, dp.edge, oc.xper, dp.sigma_0, dp.num_dogs, l, out))
+                    atomicOr(&s_bits[buf][l][ly], 1u << lx);
+            }
+        }
+        __syncthreads();
+
+        // ---- (3) one 32-bit word per tile row and level; reset this parity's state for the tile after next ----
+        if (tid < 3 * EX_TH) {
+            const int l = tid / EX_TH, ly = tid % EX_TH, gy = y0 + ly;
+            const unsigned m = s_bits[buf][l][ly];
+            s_bits[buf][l][ly] = 0u;
+            if (gy < oc.h) oc.bitmap[((long long)f * 3 + l) * bm_words + (long long)gy * oc.wpr + tx] = m;
+        }
+        if (tid == 255) s_ncand[buf] = 0;
+    }
+}
+
+// Gradient maps of levels 1..3 (compute_gradients, siftfunctions.cu:53-63 -> cudamath.cu:38-54; border
+// pixels = (0, 0)), restricted to the 8-row x 32-column blocks that an orientation or descriptor window
+// touches (need map, marked by emit_kernel).  One warp per block: lane = column, 8 rows; the four
+// neighbours come straight from global memory (the rows are L1 / L2 hits of the neighbouring lanes and
+// rows).  `dense` != 0 computes every block (tests and tools that read whole maps).
+struct NmGradTasks {
+    long long first[NM_MAX_OCTAVES];       // first task of octave o; tasks of an octave = batch * 3 * nrb * wpr
+    long long total;
+};
+
+__global__ void __launch_bounds__(256, 3) gradmap_kernel(const NmOctaveTable tab, const NmGradTasks tasks, int dense)
+{
+    const long long task = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (task >= tasks.total) return;
+    int o = 0;
+    long long base = 0;
+#pragma unroll
+    for (int k = 1; k < NM_MAX_OCTAVES; ++k)
+        if (k < tab.n_oct && task >= tasks.first[k]) { o = k; base = tasks.first[k]; }
+    const NmOctave& oc = tab.o[o];
+    const int nrb = (oc.h + NM_NEED_ROWS - 1) / NM_NEED_ROWS;
+    long long r = task - base;
+    const int cb = (int)(r % oc.wpr); r /= oc.wpr;
+    const int rb = (int)(r % nrb); r /= nrb;                  // r = frame * 3 + level
+    if (!dense && oc.need[(r * nrb + rb) * oc.wpr + cb] == 0) return;
+    const int l = (int)(r % 3);
+    const long long f = r / 3;
+    const int w = oc.w, h = oc.h, pitch = oc.pitch;
+    const int x = cb * 32 + lane, y0 = rb * NM_NEED_ROWS;
+    if (x >= w) return;
+    const float* __restrict__ p = oc.levels + (f * 6 + l + 1) * oc.level_elems + (long long)y0 * pitch + x;
+    float2* __restrict__ q = oc.grad + (f * 3 + l) * oc.level_elems + (long long)y0 * pitch + x;
+    const bool intx = x >= 1 && x <= w - 2;
+    // all 26 loads of the block in flight before the first gradient is evaluated
+    float ctr[NM_NEED_ROWS + 2], lf[NM_NEED_ROWS], rt[NM_NEED_ROWS];
+#pragma unroll
+    for (int j = -1; j <= NM_NEED_ROWS; ++j) {
+        const int y = y0 + j;
+        ctr[j + 1] = (intx && y >= 0 && y < h) ? __ldg(p + j * pitch) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < NM_NEED_ROWS; ++j) {
+        const int y = y0 + j;
+        const bool interior = intx && y >= 1 && y <= h - 2;
+        lf[j] = interior ? __ldg(p + j * pitch - 1) : 0.f;
+        rt[j] = interior ? __ldg(p + j * pitch + 1) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < NM_NEED_ROWS; ++j) {
+        const int y = y0 + j;
+        if (y < h) {
+            const bool interior = intx && y >= 1 && y <= h - 2;
+            float2 g = make_float2(0.f, 0.f);
+            if (interior) g = nm_gradient_at(rt[j], lf[j], ctr[j + 2], ctr[j]);
+            q[j * pitch] = g;
+        }
+    }
+}
+
 // One block per (segment, frame): exclusive prefix of the word popcounts + segment total.
 // Coalesced: the block walks the bitmap in spans of 1024 words (4 consecutive words per thread, one
 // 16-byte load), scans the span with warp shuffles, and carries the running total across spans.
@@ -298,8 +539,36 @@ struct GlobalDogFetch {
     __device__ __forceinline__ float up(int dx, int dy) const { return dogv(l + 2, dx, dy); }
 };
 
+// The blocks of the level's gradient map that the keypoint's orientation window (orientation.cu:43-53) and
+// descriptor window (descriptor.cu:57-65, diagonal 16 x 16 chunks :94-97) read: same geometry routines as
+// orient_kernel / describe_kernel (nm_kpgeom.cuh), so the marked set is a superset of the samples.
+__device__ __forceinline__ void mark_rect(unsigned char* need, int wpr, int x0, int x1, int y0, int y1)
+{
+    if (x0 > x1 || y0 > y1) return;
+    for (int rb = y0 / NM_NEED_ROWS; rb <= y1 / NM_NEED_ROWS; ++rb)
+        for (int cb = x0 >> 5; cb <= (x1 >> 5); ++cb) need[(long long)rb * wpr + cb] = 1;
+}
+__device__ __forceinline__ void mark_gradient_need(const NmOctave& oc, int f, const float4 kp)
+{
+    const KpGeom g = kp_geom(kp, oc.xper);
+    if (g.level < 0 || g.level > 2) return;
+    const int nrb = (oc.h + NM_NEED_ROWS - 1) / NM_NEED_ROWS;
+    unsigned char* need = oc.need + ((long long)f * 3 + g.level) * nrb * oc.wpr;
+    float sigma_w;
+    const int W = kp_orient_radius(g, sigma_w);
+    mark_rect(need, oc.wpr, g.xi + max(-W, -g.xi), g.xi + min(W, oc.w - 1 - g.xi),
+              g.yi + max(-W, -g.yi), g.yi + min(W, oc.h - 1 - g.yi));
+    if (g.xi < 0 || g.xi >= oc.w || g.yi < 0 || g.yi >= oc.h) return;     // descriptor.cu:49
+    const KpDescWindow d = kp_desc_window(g, oc.w, oc.h);
+    for (int c = 0; c < d.chunks; ++c)
+        mark_rect(need, oc.wpr, g.xi + d.xmin + 16 * c, g.xi + min(d.xmin + 16 * c + 15, d.xmax),
+                  g.yi + d.ymin + 16 * c, g.yi + min(d.ymin + 16 * c + 15, d.ymax));
+}
+
+// Ordered compaction, step 3: every set bit of the bitmaps gets its slot (segment offset + word prefix + bits
+// below it = copy_if order) and the slot receives the pixel (x, y, level) as integers.  One thread per word.
 __global__ void __launch_bounds__(256) emit_kernel(const NmOctave oc, int octave_index, int n_oct,
-                                                   const NmDetectParams dp, const int* __restrict__ seg_cnt,
+                                                   const int* __restrict__ seg_cnt,
                                                    const int* __restrict__ seg_off, int capacity,
                                                    float4* __restrict__ kpts, int* __restrict__ meta)
 {
@@ -316,15 +585,31 @@ __global__ void __launch_bounds__(256) emit_kernel(const NmOctave oc, int octave
         const int b = __ffs(bits) - 1;
         bits &= bits - 1;
         if (pos >= capacity) break;
-        const int x = xw * 32 + b;
-        GlobalDogFetch ft{oc.levels + (long long)f * 6 * oc.level_elems + (long long)y * oc.pitch + x,
-                          oc.level_elems, oc.pitch, l};
-        float4 out = make_float4(-1.f, -1.f, -1.f, -1.f);
-        nm_refine(ft, x, y, dp.peak, dp.edge, oc.xper, dp.sigma_0, dp.num_dogs, l, out);
-        kpts[(long long)f * capacity + pos] = out;
+        kpts[(long long)f * capacity + pos] = make_float4(__int_as_float(xw * 32 + b), __int_as_float(y), __int_as_float(l), -1.f);
         meta[(long long)f * capacity + pos] = octave_index;
         ++pos;
     }
+}
+
+// Step 4: one thread per emitted keypoint re-runs the (deterministic) refinement of its pixel from the Gaussian
+// levels and writes the float4 payload (keypoint.cu:172-175) over the slot; it also marks the blocks of the
+// gradient maps that the keypoint's windows read.  Dense threads: a warp refines 32 keypoints, where the
+// per-word kernel above would run the ~400-instruction refinement (double pow) with one live lane.
+__global__ void __launch_bounds__(256) kprefine_kernel(const NmOctaveTable tab, const NmDetectParams dp, int capacity,
+                                                       const int* __restrict__ counts, float4* __restrict__ kpts,
+                                                       const int* __restrict__ meta, int mark)
+{
+    const int j = blockIdx.x * 256 + threadIdx.x, f = blockIdx.y;
+    if (j >= counts[f]) return;
+    const long long kidx = (long long)f * capacity + j;
+    const float4 slot = kpts[kidx];
+    const int x = __float_as_int(slot.x), y = __float_as_int(slot.y), l = __float_as_int(slot.z);
+    const NmOctave& oc = tab.o[meta[kidx]];
+    GlobalDogFetch ft{oc.levels + (long long)f * 6 * oc.level_elems + (long long)y * oc.pitch + x, oc.level_elems, oc.pitch, l};
+    float4 out = make_float4(-1.f, -1.f, -1.f, -1.f);
+    nm_refine(ft, x, y, dp.peak, dp.edge, oc.xper, dp.sigma_0, dp.num_dogs, l, out);
+    kpts[kidx] = out;
+    if (mark && oc.need != nullptr && out.w >= 0.f) mark_gradient_need(oc, f, out);
 }
 
 // ------------------------- compat: dense per-pixel maps -------------------------
@@ -440,17 +725,60 @@ bool nm_extrema_make_tma(NmBlurTma* t, const NmOctave& oc, int batch)
     return nm_tma_encode_3d(t, oc.levels, dims, strides, box);
 }
 
+// Split pipeline (default): extrema_kernel here, gradmap_kernel after the compaction.  The fused round-1 kernel
+// stays as the path for levels TMA cannot describe and behind NM_EXTREMA_FUSED=1 (A/B measurements); it writes
+// dense gradient maps itself.  Returns through *fused which one ran.
+static bool extrema_use_fused(const NmBlurTma* tma)
+{
+    static const bool forced = getenv("NM_EXTREMA_FUSED") != nullptr;
+    return forced || !(tma && tma->valid) || getenv("NM_EXTREMA_NO_TMA") != nullptr;
+}
+
+bool nm_extrema_is_fused(const NmBlurTma* tma) { return extrema_use_fused(tma); }
+
 int nm_extrema_launch(const NmOctave& oc, int, int, const NmDetectParams& dp, int batch, cudaStream_t stream,
-                      const NmBlurTma* tma)
+                      const NmBlurTma* tma, bool fused)
 {
     dim3 block(32, 8), grid(nm_div_up(oc.w, EX_TW), nm_div_up(oc.h, EX_TH), batch);
-    static const bool no_tma = getenv("NM_EXTREMA_NO_TMA") != nullptr;     // development aid
-    if (tma && tma->valid && !no_tma) {
+    if (!fused) {
+        if (extrema_use_fused(tma) && !(tma && tma->valid)) return NM_ERR_INVALID;
+        static int configured_dev = -1, n_sms = 0, ctas_per_sm = 2;
+        int dev = 0;
+        NM_CUDA_TRY(cudaGetDevice(&dev));
+        if (configured_dev != dev) {
+            NM_CUDA_TRY(cudaFuncSetAttribute(extrema_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EX2_SMEM));
+            NM_CUDA_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+            NM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, extrema_kernel, 256, EX2_SMEM));
+            if (ctas_per_sm < 1) ctas_per_sm = 1;
+            configured_dev = dev;
+        }
+        const long long n_tiles = (long long)grid.x * grid.y * grid.z;
+        if (n_tiles >= (1LL << 31)) return NM_ERR_OVERFLOW;
+        const int ctas = (int)(n_tiles < (long long)n_sms * ctas_per_sm ? n_tiles : (long long)n_sms * ctas_per_sm);
+        extrema_kernel<<<ctas, block, EX2_SMEM, stream>>>(oc, dp, tma->map, (int)grid.x, (int)grid.y, (int)n_tiles);
+    } else if (tma && tma->valid && getenv("NM_EXTREMA_NO_TMA") == nullptr) {
         extrema_grad_kernel<true><<<grid, block, 0, stream>>>(oc, dp, tma->map);
     } else {
         CUtensorMap none{};
         extrema_grad_kernel<false><<<grid, block, 0, stream>>>(oc, dp, none);
     }
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+int nm_gradmap_launch(const NmOctaveTable& tab, int batch, int dense, cudaStream_t stream)
+{
+    NmGradTasks tasks;
+    long long total = 0;
+    for (int o = 0; o < tab.n_oct; ++o) {
+        tasks.first[o] = total;
+        total += (long long)batch * 3 * nm_div_up(tab.o[o].h, NM_NEED_ROWS) * tab.o[o].wpr;
+    }
+    for (int o = tab.n_oct; o < NM_MAX_OCTAVES; ++o) tasks.first[o] = total;
+    tasks.total = total;
+    const long long blocks = nm_div_up64(total, 8);
+    if (blocks >= (1LL << 31)) return NM_ERR_OVERFLOW;
+    gradmap_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tab, tasks, dense);
     NM_LAUNCH_CHECK();
     return NM_OK;
 }
@@ -471,12 +799,21 @@ int nm_plan_launch(const int* seg_raw, int* seg_cnt, int* seg_off, int* counts, 
     return NM_OK;
 }
 
-int nm_emit_launch(const NmOctave& oc, int octave_index, int n_oct, const NmDetectParams& dp, int batch,
+int nm_emit_launch(const NmOctave& oc, int octave_index, int n_oct, int batch,
                    const int* seg_cnt, const int* seg_off, int capacity, float4* kpts, int* meta,
                    cudaStream_t stream)
 {
     dim3 grid(nm_div_up(oc.h * oc.wpr, 256), 3, batch);
-    emit_kernel<<<grid, 256, 0, stream>>>(oc, octave_index, n_oct, dp, seg_cnt, seg_off, capacity, kpts, meta);
+    emit_kernel<<<grid, 256, 0, stream>>>(oc, octave_index, n_oct, seg_cnt, seg_off, capacity, kpts, meta);
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+int nm_kprefine_launch(const NmOctaveTable& tab, const NmDetectParams& dp, int batch, int capacity, const int* counts,
+                       float4* kpts, const int* meta, int mark, cudaStream_t stream)
+{
+    dim3 grid(nm_div_up(capacity, 256), batch);
+    kprefine_kernel<<<grid, 256, 0, stream>>>(tab, dp, capacity, counts, kpts, meta, mark);
     NM_LAUNCH_CHECK();
     return NM_OK;
 }

@@ -13,29 +13,13 @@
 // orientation window, first-two-peaks-in-bin-order, first orientation only, diagonal-only
 // 16x16 chunks of the descriptor window, no normalisation (SURVEY.md Q5,Q6,Q10,Q12,Q16).
 #include "nm_sift_internal.cuh"
+#include "nm_kpgeom.cuh"
 
 namespace {
 
 constexpr int OR_WARPS = 8;      // warps per block, orientation
 constexpr int NBINS = 36;
 constexpr int OR_HP = 32;        // lane pitch of the private histograms (bank == lane)
-
-struct KpGeom {
-    float x, y, s;
-    int xi, yi, level;
-};
-
-__device__ __forceinline__ KpGeom kp_geom(const float4 kp, float xper)
-{
-    KpGeom g;
-    g.x = __fdiv_rn(kp.x, xper);                                  // orientation.cu:19-21
-    g.y = __fdiv_rn(kp.y, xper);
-    g.s = __fdiv_rn(kp.z, xper);
-    g.xi = __double2int_rz(__dadd_rn((double)g.x, 0.5));          // :23-24
-    g.yi = __double2int_rz(__dadd_rn((double)g.y, 0.5));
-    g.level = (int)kp.w;
-    return g;
-}
 
 __global__ void __launch_bounds__(OR_WARPS * 32) orient_kernel(const NmOctaveTable tab, int capacity,
                                                                const int* __restrict__ counts,
@@ -55,9 +39,8 @@ __global__ void __launch_bounds__(OR_WARPS * 32) orient_kernel(const NmOctaveTab
     if (!(kp.w < 0.f)) {                                          // orientation.cu:17
         const NmOctave& oc = tab.o[meta[kidx]];
         const KpGeom g = kp_geom(kp, oc.xper);
-        const float sigma_w = __fmul_rn(1.5f, g.s);               // :26, gauss_factor = 1.5 (siftfunctions.cu:150)
-        int W = max((int)floorf(__fmul_rn(3.0f, sigma_w)), 1);    // :27
-        W = min(W, 10);                                           // :29-30 (22x22 block)
+        float sigma_w;                                            // :26-30 (window clamped by the 22x22 block)
+        const int W = kp_orient_radius(g, sigma_w);
         const float2* __restrict__ G = oc.grad + ((long long)f * 3 + g.level) * oc.level_elems +
                                        (long long)g.yi * oc.pitch + g.xi;      // at the keypoint; offsets below are 32-bit
         const int pitch = oc.pitch;
@@ -229,12 +212,9 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
     for (int b = 0; b < DE_BINS * DE_COPIES / 32; ++b) hist[b * 32 + lane] = 0.f;
     __syncwarp();
 
-    const float SBP = (float)__dadd_rn((double)__fmul_rn(3.0f, g.s), 1.e-07);            // :54
-    const int W = (int)floor(__fma_rn(__dmul_rn(__dmul_rn((double)SBP, 1.4142135623730951), 5.0), 0.5, 0.5));  // :55
-    const int xmin = max(-W, -g.xi), xmax = min(W, oc.w - 1 - g.xi);                     // :57-60
-    const int ymin = max(-W, -g.yi), ymax = min(W, oc.h - 1 - g.yi);
-    const int max_dims = max(xmax - xmin, ymax - ymin);
-    const int chunks = (int)ceilf(__fdiv_rn(__fadd_rn((float)max_dims, 1.f), 16.f));     // :65
+    const KpDescWindow dw = kp_desc_window(g, oc.w, oc.h);                               // :54-65
+    const float SBP = dw.SBP;
+    const int xmin = dw.xmin, xmax = dw.xmax, ymin = dw.ymin, ymax = dw.ymax, chunks = dw.chunks;
     const float th0 = orient[kidx].x;                                                    // :89; in [0, 2 pi] or -1 (no peak),
                                                                                          // so gradient angle - th0 is in (-2 pi, 2 pi + 1]
     const float st0f = sinf(th0), ct0f = cosf(th0);                                      // :90-91 (float overloads)
@@ -412,7 +392,7 @@ static int compat_table(NmOctaveTable& tab, const float* grad2, int ow, int oh, 
 {
     tab.n_oct = 1;
     NmOctave& oc = tab.o[0];
-    oc.levels = nullptr; oc.bitmap = nullptr; oc.wprefix = nullptr;
+    oc.levels = nullptr; oc.bitmap = nullptr; oc.wprefix = nullptr; oc.need = nullptr;
     oc.grad = reinterpret_cast<float2*>(const_cast<float*>(grad2));
     oc.w = ow; oc.h = oh; oc.pitch = ow; oc.wpr = nm_div_up(ow, 32);
     oc.level_elems = (long long)ow * oh;

@@ -46,12 +46,13 @@ struct nm_sift_ctx {
     float* frames_stage;     // device staging for nm_sift_run_host: [B][h][w]
     float* scratch;          // generic-radius blur scratch (lazily allocated)
     int exact_desc;
+    int dense_grad;          // 1: gradient maps computed everywhere (tests / tools that read them), 0: only where keypoint windows read
     unsigned long long mask_tex;   // detector mask (0 = none); mask_arr/mask_own: texture made by nm_sift_set_mask_image
     cudaArray_t mask_arr;
     cudaTextureObject_t mask_own;
     int last_launches;
     int timing;
-    cudaEvent_t ev[6];
+    cudaEvent_t ev[7];
     std::vector<void*> allocs;
 };
 
@@ -149,7 +150,7 @@ extern "C" int nm_sift_destroy(nm_sift_ctx* c)
     if (!c) return NM_OK;
     release_own_mask(c);
     for (void* p : c->allocs) cudaFree(p);
-    for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 7; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (auto* t : c->tma_sets) delete t;
     for (int i = 0; i < NM_MAX_CHUNKS; ++i) {
         if (c->stage_graph[i].exec) cudaGraphExecDestroy(c->stage_graph[i].exec);
@@ -182,9 +183,9 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
     nm_sift_ctx* c = new (std::nothrow) nm_sift_ctx();
     if (!c) return NM_ERR_ALLOC;
     c->P = P; c->B = max_batch; c->capacity = capacity; c->n_oct = P.num_octaves;
-    c->scratch = nullptr; c->exact_desc = 0; c->last_launches = 0; c->timing = 0;
+    c->scratch = nullptr; c->exact_desc = 0; c->dense_grad = 0; c->last_launches = 0; c->timing = 0;
     c->mask_tex = 0; c->mask_arr = nullptr; c->mask_own = 0;
-    for (int i = 0; i < 6; ++i) c->ev[i] = nullptr;
+    for (int i = 0; i < 7; ++i) c->ev[i] = nullptr;
     c->s_in = c->s_out = nullptr; c->ev_out = c->ev_fork = nullptr;
     for (int i = 0; i < NM_AUX_STREAMS; ++i) { c->s_aux[i] = nullptr; c->ev_join[i] = nullptr; }
     for (int i = 0; i < NM_MAX_CHUNKS; ++i) c->ev_in[i] = c->ev_done[i] = nullptr;
@@ -212,6 +213,7 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
         if (rc == NM_OK) rc = dev_alloc(c, &oc.grad, B * 3 * (size_t)oc.level_elems);
         if (rc == NM_OK) rc = dev_alloc(c, &oc.bitmap, B * 3 * nwords);
         if (rc == NM_OK) rc = dev_alloc(c, &oc.wprefix, B * 3 * nwords);
+        if (rc == NM_OK) rc = dev_alloc(c, &oc.need, B * 3 * (size_t)nm_div_up(oc.h, 8) * oc.wpr);
     }
     const size_t S = (size_t)c->n_oct * 3, cap = (size_t)capacity;
     if (rc == NM_OK) rc = dev_alloc(c, &c->seg_raw, B * S);
@@ -231,7 +233,7 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
         cudaMemset(c->counts, 0, B * sizeof(int));
         cudaMemset(c->seg_cnt, 0, B * S * sizeof(int));
     }
-    for (int i = 0; i < 6 && rc == NM_OK; ++i)
+    for (int i = 0; i < 7 && rc == NM_OK; ++i)
         if (cudaEventCreate(&c->ev[i]) != cudaSuccess) rc = NM_ERR_ALLOC;
     if (rc == NM_OK && (cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) != cudaSuccess ||
                         cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) != cudaSuccess ||
@@ -269,6 +271,7 @@ static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, in
         oc.grad += (long long)first * 3 * oc.level_elems;
         oc.bitmap += (long long)first * 3 * nwords;
         oc.wprefix += (long long)first * 3 * nwords;
+        oc.need += (long long)first * 3 * nm_div_up(oc.h, 8) * oc.wpr;
     }
     const long long S = (long long)c->n_oct * 3, cap = c->capacity;
     int* seg_raw = c->seg_raw + first * S;
@@ -336,29 +339,40 @@ static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, in
         }
     }
     if (timing) cudaEventRecord(c->ev[1], st);
-    // ---- DoG + extrema + refinement + gradients ----------------------------------
+    // ---- DoG + extrema + refinement (+ dense gradient maps in the fused fallback) ----------
+    bool fused = false;
+    for (int o = 0; o < c->n_oct; ++o) fused = fused || nm_extrema_is_fused(&ts->ex[o]);
+    if (fused) for (int o = 0; o < c->n_oct; ++o) tab.o[o].need = nullptr;      // emit_kernel does not mark
     for (int o = 0; o < c->n_oct; ++o) {
-        if ((rc = nm_extrema_launch(tab.o[o], o, c->n_oct, dp, n, st, &ts->ex[o])) != NM_OK) return rc;
+        if ((rc = nm_extrema_launch(tab.o[o], o, c->n_oct, dp, n, st, &ts->ex[o], fused)) != NM_OK) return rc;
         ++launches;
     }
     if (timing) cudaEventRecord(c->ev[2], st);
-    // ---- ordered compaction --------------------------------------------------------
+    // ---- ordered compaction (emit also marks the gradient blocks the keypoint windows read) ----
     if ((rc = nm_rank_launch(tab, n, seg_raw, st)) != NM_OK) return rc;
     if ((rc = nm_plan_launch(seg_raw, seg_cnt, seg_off, counts, c->n_oct, n, c->capacity, st)) != NM_OK) return rc;
     launches += 2;
     for (int o = 0; o < c->n_oct; ++o) {
-        if ((rc = nm_emit_launch(tab.o[o], o, c->n_oct, dp, n, seg_cnt, seg_off, c->capacity, kpts, meta, st)) != NM_OK) return rc;
+        if ((rc = nm_emit_launch(tab.o[o], o, c->n_oct, n, seg_cnt, seg_off, c->capacity, kpts, meta, st)) != NM_OK) return rc;
         ++launches;
     }
+    if ((rc = nm_kprefine_launch(tab, dp, n, c->capacity, counts, kpts, meta, fused ? 0 : 1, st)) != NM_OK) return rc;
+    ++launches;
     if (timing) cudaEventRecord(c->ev[3], st);
+    // ---- gradient maps of the marked blocks ----------------------------------------------
+    if (!fused) {
+        if ((rc = nm_gradmap_launch(tab, n, c->dense_grad, st)) != NM_OK) return rc;
+        ++launches;
+    }
+    if (timing) cudaEventRecord(c->ev[4], st);
     // ---- orientation, descriptor -----------------------------------------------------
     if ((rc = nm_orient_launch(tab, n, c->capacity, counts, kpts, meta, orient, st)) != NM_OK) return rc;
     ++launches;
-    if (timing) cudaEventRecord(c->ev[4], st);
+    if (timing) cudaEventRecord(c->ev[5], st);
     if ((rc = nm_describe_launch(tab, n, c->capacity, counts, kpts, meta, orient, desc, x, y, P.num_dog_levels,
                                  c->exact_desc, st)) != NM_OK) return rc;
     ++launches;
-    if (timing) cudaEventRecord(c->ev[5], st);
+    if (timing) cudaEventRecord(c->ev[6], st);
     c->last_launches = launches;
     return NM_OK;
 }
@@ -463,7 +477,7 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
         int rc;
         if (use_graphs) {
             nm_sift_ctx::StageGraph& g = c->stage_graph[k];
-            if (!g.exec || g.f0 != f0 || g.n != n || g.mask != c->mask_tex || g.exact != c->exact_desc) {
+            if (!g.exec || g.f0 != f0 || g.n != n || g.mask != c->mask_tex || g.exact != (c->exact_desc | (c->dense_grad << 1))) {
                 if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
                 cudaGraph_t graph = nullptr;
                 NM_CUDA_TRY(cudaStreamBeginCapture(sk, cudaStreamCaptureModeThreadLocal));
@@ -476,7 +490,7 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
                 const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
                 cudaGraphDestroy(graph);
                 if (ie != cudaSuccess) { g.exec = nullptr; return nm_cuda_err(ie); }
-                g.f0 = f0; g.n = n; g.mask = c->mask_tex; g.exact = c->exact_desc; g.launches = c->last_launches;
+                g.f0 = f0; g.n = n; g.mask = c->mask_tex; g.exact = c->exact_desc | (c->dense_grad << 1); g.launches = c->last_launches;
             }
             NM_CUDA_TRY(cudaGraphLaunch(g.exec, sk));
             launches += g.launches;
@@ -603,12 +617,32 @@ extern "C" int nm_sift_enable_timing(nm_sift_ctx* c, int enable)
     return NM_OK;
 }
 
+// ms6 = {pyramid, extrema + gradient maps, compaction, orientation, descriptor, total} of the last timed run
 extern "C" int nm_sift_stage_ms(nm_sift_ctx* c, float* ms6)
 {
-    if (!c || !ms6) return NM_ERR_INVALID;
-    NM_CUDA_TRY(cudaEventSynchronize(c->ev[5]));
-    for (int i = 0; i < 5; ++i) NM_CUDA_TRY(cudaEventElapsedTime(&ms6[i], c->ev[i], c->ev[i + 1]));
-    NM_CUDA_TRY(cudaEventElapsedTime(&ms6[5], c->ev[0], c->ev[5]));
+    float m[7];
+    const int rc = nm_sift_stage_ms7(c, m);
+    if (rc != NM_OK || !ms6) return rc != NM_OK ? rc : NM_ERR_INVALID;
+    ms6[0] = m[0]; ms6[1] = m[1] + m[3]; ms6[2] = m[2]; ms6[3] = m[4]; ms6[4] = m[5]; ms6[5] = m[6];
+    return NM_OK;
+}
+
+// ms7 = {pyramid, extrema, compaction, gradient maps, orientation, descriptor, total}
+extern "C" int nm_sift_stage_ms7(nm_sift_ctx* c, float* ms7)
+{
+    if (!c || !ms7) return NM_ERR_INVALID;
+    NM_CUDA_TRY(cudaEventSynchronize(c->ev[6]));
+    for (int i = 0; i < 6; ++i) NM_CUDA_TRY(cudaEventElapsedTime(&ms7[i], c->ev[i], c->ev[i + 1]));
+    NM_CUDA_TRY(cudaEventElapsedTime(&ms7[6], c->ev[0], c->ev[6]));
+    return NM_OK;
+}
+
+// 1: gradient maps computed for every pixel (callers that read nm_sift_grad); 0 (default): only the 8 x 32 blocks an
+// orientation / descriptor window of an emitted keypoint reads -- the results of the run are identical.
+extern "C" int nm_sift_set_dense_gradients(nm_sift_ctx* c, int dense)
+{
+    if (!c) return NM_ERR_INVALID;
+    c->dense_grad = dense ? 1 : 0;
     return NM_OK;
 }
 

@@ -6,6 +6,7 @@
 //     grad    [B][3][h_o][pitch_o] float2    gradient maps   (reference PyramidData::_grad)
 //     bitmap  [B][3][h_o][wpr_o]   uint32    1 bit per pixel: accepted keypoint
 //     wprefix [B][3][h_o*wpr_o]    int32     exclusive popcount prefix inside the segment
+//     need    [B][3][ceil(h_o/8)][wpr_o] u8  gradient blocks (8 rows x 32 columns) read by a keypoint window
 //   seg_raw   [B][n_oct*3] int   accepted keypoints per (octave, level) before the
 //                                early-return rule
 //   seg_cnt   [B][n_oct*3] int   after the rule (siftfunctions.cu:145: levels after the
@@ -24,6 +25,7 @@ struct NmOctave {
     float2*   grad;
     uint32_t* bitmap;
     int*      wprefix;
+    unsigned char* need;       // [B][3][ceil(h/8)][wpr]: 8-row x 32-column blocks of the gradient maps that a keypoint window reads
     long long level_elems;     // h*pitch
     int       w, h, pitch, wpr;
     float     xper;
@@ -45,14 +47,24 @@ struct NmBlurTma;
 // TMA descriptor of an octave's level planes for `batch` frames (oc.levels = first frame): box = the
 // extrema kernel's 36 x 34 x 6 window.  Without a valid descriptor the kernel stages the window with plain loads.
 bool nm_extrema_make_tma(NmBlurTma* t, const NmOctave& oc, int batch);
+// fused = true: the round-1 kernel that also writes dense gradient maps (the only one for sources TMA cannot
+// describe); fused = false: extrema_kernel (needs a valid descriptor), gradient maps by nm_gradmap_launch.
 int nm_extrema_launch(const NmOctave& oc, int octave_index, int n_oct, const NmDetectParams& dp,
-                      int batch, cudaStream_t stream, const NmBlurTma* tma = nullptr);
+                      int batch, cudaStream_t stream, const NmBlurTma* tma, bool fused);
+// true when nm_extrema_launch takes the fused round-1 kernel (which also writes dense gradient maps) for this source
+bool nm_extrema_is_fused(const NmBlurTma* tma);
+// gradient maps of levels 1..3 for all octaves; dense = 0: only the blocks marked in NmOctave::need
+int nm_gradmap_launch(const NmOctaveTable& tab, int batch, int dense, cudaStream_t stream);
 int nm_rank_launch(const NmOctaveTable& tab, int batch, int* seg_raw, cudaStream_t stream);
 int nm_plan_launch(const int* seg_raw, int* seg_cnt, int* seg_off, int* counts, int n_oct, int batch,
                    int capacity, cudaStream_t stream);
-int nm_emit_launch(const NmOctave& oc, int octave_index, int n_oct, const NmDetectParams& dp, int batch,
+// emit: slot <- pixel (x, y, level) of every set bit, in copy_if order; kprefine: slot <- refined keypoint payload
+// (one thread per keypoint), mark != 0 also marks NmOctave::need from the keypoint's windows
+int nm_emit_launch(const NmOctave& oc, int octave_index, int n_oct, int batch,
                    const int* seg_cnt, const int* seg_off, int capacity, float4* kpts, int* meta,
                    cudaStream_t stream);
+int nm_kprefine_launch(const NmOctaveTable& tab, const NmDetectParams& dp, int batch, int capacity, const int* counts,
+                       float4* kpts, const int* meta, int mark, cudaStream_t stream);
 
 // nm_orient_desc.cu
 int nm_orient_launch(const NmOctaveTable& tab, int batch, int capacity, const int* counts,

@@ -95,6 +95,11 @@ class SiftBatch:
     def set_exact_descriptor(self, exact: bool):
         check(self.lib.nm_sift_set_exact_descriptor(self._ctx, int(exact)), "nm_sift_set_exact_descriptor")
 
+    def set_dense_gradients(self, dense: bool):
+        """True: gradient maps of every pixel (needed before reading grad()); False (default): only the
+        blocks that keypoint windows read."""
+        check(self.lib.nm_sift_set_dense_gradients(self._ctx, int(dense)), "nm_sift_set_dense_gradients")
+
     def run(self, frames) -> None:
         """frames: cuda float32 tensor (n, height, width), contiguous.  Asynchronous."""
         assert frames.is_cuda and frames.is_contiguous() and frames.dtype.is_floating_point and frames.element_size() == 4
@@ -184,9 +189,13 @@ class SiftBatch:
         check(self.lib.nm_sift_enable_timing(self._ctx, int(on)), "nm_sift_enable_timing")
 
     def stage_ms(self):
-        buf = (C.c_float * 6)()
-        check(self.lib.nm_sift_stage_ms(self._ctx, buf), "nm_sift_stage_ms")
-        return dict(zip(["pyramid", "extrema_grad", "compaction", "orientation", "descriptor", "total"], list(buf)))
+        """Stage times of the last timed run: extrema (DoG + 26-neighbour test + refinement) and gradient (the
+        gradient maps of the blocks keypoint windows read) are separate kernels; extrema_grad is their sum."""
+        buf = (C.c_float * 7)()
+        check(self.lib.nm_sift_stage_ms7(self._ctx, buf), "nm_sift_stage_ms7")
+        d = dict(zip(["pyramid", "extrema", "compaction", "gradient", "orientation", "descriptor", "total"], list(buf)))
+        d["extrema_grad"] = d["extrema"] + d["gradient"]
+        return d
 
 
 # ---- per-stage operators on torch tensors (used by the parity tests) --------------------

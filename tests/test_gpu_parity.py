@@ -38,7 +38,9 @@ def _cu(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-def run_product(nm, frames, peak=0.0, capacity=8192, exact=False, num_octaves=-1):
+def run_product(nm, frames, peak=0.0, capacity=8192, exact=False, num_octaves=-1, dense_grad=True):
+    """dense_grad: the whole gradient maps are read back below, so they are computed everywhere; the default of
+    the product (only the blocks keypoint windows read) is covered by test_sparse_gradient_maps_*."""
     n, h, w = frames.shape
     P = nm.SiftParams(w, h)
     P._peak_threshold = peak
@@ -46,6 +48,7 @@ def run_product(nm, frames, peak=0.0, capacity=8192, exact=False, num_octaves=-1
         P._num_octaves = num_octaves
     sb = nm.SiftBatch(P, n, capacity)
     sb.set_exact_descriptor(exact)
+    sb.set_dense_gradients(dense_grad)
     sb.run(_cu(frames))
     torch.cuda.synchronize()
     r = sb.results()
@@ -336,6 +339,53 @@ def test_1080p_batch_strip_blur_vs_oracle(nm, oracle):
     ref = [oracle.sift_frame(frames[f], capacity=16384) for f in (0, 1)]
     for f in (0, 9, 19):
         assert_frame_matches(out[f], ref[f % 2])
+
+
+def test_sparse_gradient_maps_give_identical_results(nm):
+    """Default mode: gradient maps only for the 8 x 32 blocks marked by emit_kernel from the keypoints' orientation
+    and descriptor windows.  Keypoints, orientations, descriptors and coordinates must be BITWISE those of the
+    dense-map run (same kernels reading the same samples), at both thresholds, on frames of several sizes, with
+    stale data in the unmarked blocks (the context is reused: the maps hold the previous frame's values)."""
+    for (w, h, peak) in [(256, 192, 0.0), (256, 192, 2.0), (640, 480, 0.0), (333, 250, 4.0)]:
+        frames = np.stack([synth.scene(w, h, synth.SEED_BASE + 40 + i) for i in range(3)])
+        P = nm.SiftParams(w, h)
+        P._peak_threshold = peak
+        sb = nm.SiftBatch(P, 3, 8192)
+        res = {}
+        for mode in ("dense", "sparse", "sparse_again"):
+            sb.set_dense_gradients(mode == "dense")
+            fr = frames if mode != "sparse_again" else frames[::-1].copy()      # other frames left their maps behind
+            sb.run(_cu(fr))
+            torch.cuda.synchronize()
+            if mode == "sparse_again":
+                sb.run(_cu(frames))
+                torch.cuda.synchronize()
+            r = sb.results()
+            res[mode] = {k: r[k].cpu().numpy().copy() for k in ("counts", "kpts", "orient", "desc", "x", "y")}
+        assert res["dense"]["counts"].min() > 0
+        for mode in ("sparse", "sparse_again"):
+            for f in range(3):
+                c = int(res["dense"]["counts"][f])
+                assert res[mode]["counts"][f] == c
+                for k in ("kpts", "orient", "desc", "x", "y"):
+                    assert np.array_equal(res[mode][k][f, :c], res["dense"][k][f, :c]), (w, h, peak, mode, f, k)
+        sb.close()
+
+
+def test_fused_extrema_fallback_parity_suite():
+    """NM_EXTREMA_FUSED=1 selects the fused round-1 kernel (DoG + extrema + dense gradient maps in one pass), which
+    is also the path for levels TMA cannot describe; the SIFT parity tests are re-run that way in a child process."""
+    import subprocess
+    import sys
+    if os.environ.get("NM_EXTREMA_FUSED"):
+        pytest.skip("already the forced run")
+    env = dict(os.environ, NM_EXTREMA_FUSED="1")
+    sel = ("test_sift_vs_oracle or test_sift_vs_reference_golden or test_forced_octave_count or "
+           "test_masked_detector_batched_vs_reference_and_oracle or test_sparse_gradient_maps_give_identical_results")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", __file__, "-k", sel],
+                       env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
 
 
 def test_forced_strip_blur_parity_suite():

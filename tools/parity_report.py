@@ -25,6 +25,7 @@ def product_frame(image, peak, capacity=65536, exact=False, num_octaves=-1):
     if num_octaves > 0:
         P._num_octaves = num_octaves
     sb = nm.SiftBatch(P, 1, capacity)
+    sb.set_dense_gradients(True)          # the whole maps are compared below
     sb.set_exact_descriptor(exact)
     fr = torch.from_numpy(image[None]).cuda()
     sb.run(fr)
