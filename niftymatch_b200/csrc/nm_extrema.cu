@@ -206,6 +206,20 @@ __global__ void __launch_bounds__(256, 4) extrema_grad_kernel(const NmOctave oc,
     }
 }
 
+struct GlobalDogFetch {
+    const float* L;            // frame's level 0 at the candidate pixel
+    long long le;              // level_elems
+    int pitch, l;
+    __device__ __forceinline__ float dogv(int k, int dx, int dy) const
+    {
+        const float* p = L + (long long)dy * pitch + dx;
+        return __fsub_rn(__ldg(p + (k + 1) * le), __ldg(p + k * le));
+    }
+    __device__ __forceinline__ float cur(int dx, int dy) const { return dogv(l + 1, dx, dy); }
+    __device__ __forceinline__ float down(int dx, int dy) const { return dogv(l, dx, dy); }
+    __device__ __forceinline__ float up(int dx, int dy) const { return dogv(l + 2, dx, dy); }
+};
+
 // ------------------------- split pipeline: extrema without gradients -------------------------
 // DoG values formed on the fly from the staged Gaussian levels (cudamath.cu:34: next - this).
 struct SmemLevelFetch {
@@ -221,28 +235,34 @@ struct SmemLevelFetch {
 };
 
 constexpr int EX2_MAXC = EX_TW * EX_TH * 3;                     // every pixel of every level a candidate: cannot overflow
-constexpr int EX2_SMEM = 2 * (int)EX_TILE_BYTES + EX2_MAXC * (int)sizeof(unsigned short) + 2 * 3 * EX_TH * 4 + 64;
+constexpr int EX2_LIST = 32;                                    // candidates of a tile handed to refine_list_kernel (one warp)
+constexpr int EX2_SMEM = 2 * (int)EX_TILE_BYTES + EX2_MAXC * (int)sizeof(unsigned short) + 3 * EX_TH * 4 + 64;   // 71 872: 3 CTAs / SM
 
 // Persistent CTAs walk the 32 x 32 tiles of a launch (x fastest, so the CTAs in flight work on neighbouring
 // tiles and the halo columns / rows they share are L2 hits).  The six-level window of the NEXT tile is
 // fetched by TMA into the other half of a double buffer while the current one is processed: the window is
-// read-only (the DoG differences are formed in registers), so no thread ever waits for a load at CTA start
+// read-only (the DoG differences are formed in registers), so no thread waits for a load at CTA start
 // (13.8 % of the stall samples of the fused round-1 kernel) and the DoG pass with its barrier is gone.
-// Per tile: (1) the separable 26-neighbour test for 4 pixels x 3 levels per thread, the Gaussian levels carried
-// in registers from one DoG level to the next; extremum candidates (about 0.2 % of the pixels) go to a list in
-// shared memory; (2) the list is refined by consecutive threads (a warp refines 32 candidates at once instead of
-// one 32-pixel row with a single live lane); accepted pixels set bits in a shared-memory copy of the tile's
-// bitmap rows; (3) 96 threads store the rows.  Gradient maps are not produced here (gradmap_kernel).
-__global__ void __launch_bounds__(256, 2) extrema_kernel(const NmOctave oc, const NmDetectParams dp,
+// Per tile: the separable 26-neighbour test for 4 pixels x 3 levels per thread, the Gaussian levels carried
+// in registers from one DoG level to the next; the extremum candidates (about 0.2 % of the pixels) go to a
+// list in shared memory and, after the tile's ONE barrier, to the tile's slot of a global list that
+// refine_list_kernel works through with one lane per candidate -- in this kernel the ~300-instruction
+// refinement (IEEE divisions, a dependent chain of ~1500 cycles) would leave seven warps waiting at a barrier
+// for the one that has a candidate.  Tiles with more than 32 candidates (not seen on images; possible on
+// synthetic noise) are refined here.  Gradient maps are not produced here (gradmap_kernel).
+__global__ void __launch_bounds__(256, 3) extrema_kernel(const NmOctave oc, const NmDetectParams dp,
                                                          const __grid_constant__ CUtensorMap tmap,
-                                                         int tiles_x, int tiles_y, int n_tiles)
+                                                         int tiles_x, int tiles_y, int n_tiles,
+                                                         int* __restrict__ cand_n, unsigned short* __restrict__ cand)
 {
     extern __shared__ __align__(128) unsigned char ex_smem[];
     float (*s_win)[6][EX_ROWS][EX_P] = reinterpret_cast<float (*)[6][EX_ROWS][EX_P]>(ex_smem);      // [2]
-    unsigned short* s_cand = reinterpret_cast<unsigned short*>(ex_smem + 2 * EX_TILE_BYTES);
-    unsigned (*s_bits)[3][EX_TH] = reinterpret_cast<unsigned (*)[3][EX_TH]>(ex_smem + 2 * EX_TILE_BYTES + EX2_MAXC * 2);   // [2]
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(ex_smem + 2 * EX_TILE_BYTES + EX2_MAXC * 2 + 2 * 3 * EX_TH * 4);        // [2]
-    int* s_ncand = reinterpret_cast<int*>(s_bar + 2);                                                                      // [2]
+    unsigned short* s_cand = reinterpret_cast<unsigned short*>(ex_smem + 2 * EX_TILE_BYTES);                               // [EX2_MAXC], read by crowded tiles only
+    unsigned (*s_bits)[EX_TH] = reinterpret_cast<unsigned (*)[EX_TH]>(ex_smem + 2 * EX_TILE_BYTES + EX2_MAXC * 2);        // [3], crowded tiles only
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(ex_smem + 2 * EX_TILE_BYTES + EX2_MAXC * 2 + 3 * EX_TH * 4);             // [2]
+    // candidate counters rotate over three slots: slot it % 3 is pushed to before tile it's barrier, read after it, and
+    // cleared after the barrier of tile it + 1 (every thread has read it by then; the next pushes come after barrier it + 2)
+    int* s_ncand = reinterpret_cast<int*>(s_bar + 2);                                                                      // [3]
     const int tid = threadIdx.y * 32 + threadIdx.x, lane = threadIdx.x;
     const long long bm_words = (long long)oc.h * oc.wpr;
     const int nrb = (oc.h + NM_NEED_ROWS - 1) / NM_NEED_ROWS;
@@ -262,18 +282,17 @@ __global__ void __launch_bounds__(256, 2) extrema_kernel(const NmOctave oc, cons
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ex_smem_u32(&s_bar[0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ex_smem_u32(&s_bar[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_ncand[0] = s_ncand[1] = 0;
+        s_ncand[0] = s_ncand[1] = s_ncand[2] = 0;
         if (tile < n_tiles) issue(tile, 0);
     }
-    if (tid < 2 * 3 * EX_TH) (&s_bits[0][0][0])[tid] = 0u;
     __syncthreads();
 
     const float t = __fmul_rn(0.8f, dp.peak);
     for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
-        const int buf = it & 1;
+        const int buf = it & 1, cnt = it % 3;
         const int tx = tile % tiles_x, q = tile / tiles_x, ty = q % tiles_y, f = q / tiles_y;
         const int x0 = tx * EX_TW, y0 = ty * EX_TH;
-        // the other buffer was last read before the closing barrier of the previous iteration
+        // the other buffer was last read before the barrier of the previous iteration
         if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, buf ^ 1);
         asm volatile(
             "{\n"
@@ -286,7 +305,7 @@ __global__ void __launch_bounds__(256, 2) extrema_kernel(const NmOctave oc, cons
             "}\n" ::"r"(ex_smem_u32(&s_bar[buf])), "r"((it >> 1) & 1) : "memory");
         const float (*L)[EX_ROWS][EX_P] = s_win[buf];
 
-        // ---- (1) separable 26-neighbour test, same comparisons as keypoint.cu:19-105 / :195-196 ----
+        // ---- separable 26-neighbour test, same comparisons as keypoint.cu:19-105 / :195-196 ----
         unsigned extmask = 0;                      // bit l * 4 + j
         {
             const int c = lane + EX_HL, rbase = threadIdx.y * (EX_TH / 8);     // window row of the first pixel's upper neighbour
@@ -343,105 +362,132 @@ __global__ void __launch_bounds__(256, 2) extrema_kernel(const NmOctave oc, cons
         }
         if (extmask) {
             const int n = __popc(extmask);
-            int pos = atomicAdd(&s_ncand[buf], n);
+            int pos = atomicAdd(&s_ncand[cnt], n);
             while (extmask) {
                 const int b = __ffs(extmask) - 1;
                 extmask &= extmask - 1;
-                // level (2 bits) | tile row (5 bits) | tile column (5 bits)
-                s_cand[pos++] = (unsigned short)(((b >> 2) << 10) | ((threadIdx.y * (EX_TH / 8) + (b & 3)) << 5) | lane);
-            }
-        }
-        // this tile's blocks of the gradient-need map start clear (marked by emit_kernel, read by gradmap_kernel)
-        if (tid < 3 * (EX_TH / NM_NEED_ROWS)) {
-            const int l = tid / (EX_TH / NM_NEED_ROWS), rb = ty * (EX_TH / NM_NEED_ROWS) + tid % (EX_TH / NM_NEED_ROWS);
-            if (rb < nrb) oc.need[(((long long)f * 3 + l) * nrb + rb) * oc.wpr + tx] = 0;
-        }
-        __syncthreads();
-
-        // ---- (2) refinement of the listed candidates (keypoint.cu:108-180, 214) ----
-        const int ncand = s_ncand[buf];
-        for (int i = tid; i < ncand; i += 256) {
-            const unsigned e = s_cand[i];
-            const int l = e >> 10, ly = (e >> 5) & 31, lx = e & 31;
-            const int gx = x0 + lx, gy = y0 + ly;
-            const bool masked_out = dp.mask != 0 &&
-                tex2D<float>((cudaTextureObject_t)dp.mask, (gx + 0.5f) * oc.xper, (gy + 0.5f) * oc.xper) < 1.f;
-            if (!masked_out) {
-                SmemLevelFetch ft{L, l, ly + 1, lx + EX_HL};
-                float4 out;
-                if (nm_refine(ft, gx, gy, dp.peak, dp.edge, oc.xper, dp.sigma_0, dp.num_dogs, l, out))
-                    atomicOr(&s_bits[buf][l][ly], 1u << lx);
+                // level (2 bits) | tile row (5 bits) | tile column (5 bits); the first EX2_LIST straight to the tile's global list
+                const unsigned short e = (unsigned short)(((b >> 2) << 10) | ((threadIdx.y * (EX_TH / 8) + (b & 3)) << 5) | lane);
+                s_cand[pos] = e;
+                if (pos < EX2_LIST) cand[(long long)tile * EX2_LIST + pos] = e;
+                ++pos;
             }
         }
         __syncthreads();
 
-        // ---- (3) one 32-bit word per tile row and level; reset this parity's state for the tile after next ----
+        const int ncand = s_ncand[cnt];
+        // the tile's bitmap words and its blocks of the gradient-need map start clear (set by refine_list_kernel /
+        // below, marked by kprefine_kernel)
         if (tid < 3 * EX_TH) {
-            const int l = tid / EX_TH, ly = tid % EX_TH, gy = y0 + ly;
-            const unsigned m = s_bits[buf][l][ly];
-            s_bits[buf][l][ly] = 0u;
-            if (gy < oc.h) oc.bitmap[((long long)f * 3 + l) * bm_words + (long long)gy * oc.wpr + tx] = m;
+            const int l = tid / EX_TH, gy = y0 + tid % EX_TH;
+            if (gy < oc.h) oc.bitmap[((long long)f * 3 + l) * bm_words + (long long)gy * oc.wpr + tx] = 0u;
+        } else if (tid < 3 * EX_TH + 3 * (EX_TH / NM_NEED_ROWS)) {
+            const int i = tid - 3 * EX_TH;
+            const int l = i / (EX_TH / NM_NEED_ROWS), rb = ty * (EX_TH / NM_NEED_ROWS) + i % (EX_TH / NM_NEED_ROWS);
+            if (rb < nrb) oc.need[(((long long)f * 3 + l) * nrb + rb) * oc.wpr + tx] = 0;
+        } else if (tid == 255) {
+            cand_n[tile] = ncand <= EX2_LIST ? ncand : 0;
+            s_ncand[(it + 2) % 3] = 0;             // the previous tile's counter
         }
-        if (tid == 255) s_ncand[buf] = 0;
+        if (ncand > EX2_LIST) {
+            // ---- crowded tile: refined here (keypoint.cu:108-180, 214), bits through shared memory ----
+            if (tid < 3 * EX_TH) (&s_bits[0][0])[tid] = 0u;
+            __syncthreads();
+            for (int i = tid; i < ncand; i += 256) {
+                const unsigned e = s_cand[i];
+                const int l = e >> 10, ly = (e >> 5) & 31, lx = e & 31;
+                const int gx = x0 + lx, gy = y0 + ly;
+                const bool masked_out = dp.mask != 0 &&
+                    tex2D<float>((cudaTextureObject_t)dp.mask, (gx + 0.5f) * oc.xper, (gy + 0.5f) * oc.xper) < 1.f;
+                if (!masked_out) {
+                    SmemLevelFetch ft{L, l, ly + 1, lx + EX_HL};
+                    float4 out;
+                    if (nm_refine(ft, gx, gy, dp.peak, dp.edge, oc.xper, dp.sigma_0, dp.num_dogs, l, out))
+                        atomicOr(&s_bits[l][ly], 1u << lx);
+                }
+            }
+            __syncthreads();
+            if (tid < 3 * EX_TH) {
+                const int l = tid / EX_TH, ly = tid % EX_TH, gy = y0 + ly;
+                if (gy < oc.h) oc.bitmap[((long long)f * 3 + l) * bm_words + (long long)gy * oc.wpr + tx] = s_bits[l][ly];
+            }
+            __syncthreads();                       // s_cand / the window are rewritten by the next tiles
+        }
     }
+}
+
+// One warp per tile of the extrema launch, one lane per listed candidate: mask test (keypoint.cu:214), refinement
+// and rejection (keypoint.cu:108-180) on DoG values formed from the Gaussian levels in global memory (L2 hits: the
+// extrema kernel has just read them); accepted pixels set their bit in the keypoint bitmap.
+__global__ void __launch_bounds__(256) refine_list_kernel(const NmOctave oc, const NmDetectParams dp, int tiles_x, int tiles_y,
+                                                          int n_tiles, const int* __restrict__ cand_n,
+                                                          const unsigned short* __restrict__ cand)
+{
+    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (tile >= n_tiles) return;
+    if (lane >= cand_n[tile]) return;
+    const unsigned e = cand[(long long)tile * EX2_LIST + lane];
+    const int tx = tile % tiles_x, q = tile / tiles_x, ty = q % tiles_y, f = q / tiles_y;
+    const int l = e >> 10, gy = ty * EX_TH + ((e >> 5) & 31), gx = tx * EX_TW + (e & 31);
+    if (dp.mask != 0 && tex2D<float>((cudaTextureObject_t)dp.mask, (gx + 0.5f) * oc.xper, (gy + 0.5f) * oc.xper) < 1.f) return;
+    GlobalDogFetch ft{oc.levels + (long long)f * 6 * oc.level_elems + (long long)gy * oc.pitch + gx, oc.level_elems, oc.pitch, l};
+    float4 out;
+    if (nm_refine(ft, gx, gy, dp.peak, dp.edge, oc.xper, dp.sigma_0, dp.num_dogs, l, out))
+        atomicOr(oc.bitmap + ((long long)f * 3 + l) * oc.h * oc.wpr + (long long)gy * oc.wpr + tx, 1u << (e & 31));
 }
 
 // Gradient maps of levels 1..3 (compute_gradients, siftfunctions.cu:53-63 -> cudamath.cu:38-54; border
 // pixels = (0, 0)), restricted to the 8-row x 32-column blocks that an orientation or descriptor window
-// touches (need map, marked by emit_kernel).  One warp per block: lane = column, 8 rows; the four
-// neighbours come straight from global memory (the rows are L1 / L2 hits of the neighbouring lanes and
-// rows).  `dense` != 0 computes every block (tests and tools that read whole maps).
-struct NmGradTasks {
-    long long first[NM_MAX_OCTAVES];       // first task of octave o; tasks of an octave = batch * 3 * nrb * wpr
-    long long total;
-};
-
-__global__ void __launch_bounds__(256, 3) gradmap_kernel(const NmOctaveTable tab, const NmGradTasks tasks, int dense)
+// touches (need map, marked by kprefine_kernel).  A CTA covers 256 columns x 32 rows of one level: a warp
+// owns a 32-column strip and walks its four blocks; lane = column.  The four neighbours come straight from
+// global memory (the rows are L1 / L2 hits of the neighbouring lanes and rows), all 26 loads of a block in
+// flight before its first gradient is evaluated.  `dense` != 0 computes every block (tests and tools that read
+// whole maps).
+__global__ void __launch_bounds__(256, 3) gradmap_kernel(const NmOctave oc, int strips_x, int dense)
 {
-    const long long task = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (task >= tasks.total) return;
-    int o = 0;
-    long long base = 0;
-#pragma unroll
-    for (int k = 1; k < NM_MAX_OCTAVES; ++k)
-        if (k < tab.n_oct && task >= tasks.first[k]) { o = k; base = tasks.first[k]; }
-    const NmOctave& oc = tab.o[o];
-    const int nrb = (oc.h + NM_NEED_ROWS - 1) / NM_NEED_ROWS;
-    long long r = task - base;
-    const int cb = (int)(r % oc.wpr); r /= oc.wpr;
-    const int rb = (int)(r % nrb); r /= nrb;                  // r = frame * 3 + level
-    if (!dense && oc.need[(r * nrb + rb) * oc.wpr + cb] == 0) return;
-    const int l = (int)(r % 3);
-    const long long f = r / 3;
-    const int w = oc.w, h = oc.h, pitch = oc.pitch;
-    const int x = cb * 32 + lane, y0 = rb * NM_NEED_ROWS;
-    if (x >= w) return;
-    const float* __restrict__ p = oc.levels + (f * 6 + l + 1) * oc.level_elems + (long long)y0 * pitch + x;
-    float2* __restrict__ q = oc.grad + (f * 3 + l) * oc.level_elems + (long long)y0 * pitch + x;
+    const int cb = (blockIdx.x % strips_x) * 8 + (threadIdx.x >> 5), rb0 = (blockIdx.x / strips_x) * 4;
+    const int fl = blockIdx.y;                                  // frame * 3 + level
+    const int w = oc.w, h = oc.h, pitch = oc.pitch, wpr = oc.wpr;
+    const int x = cb * 32 + lane;
+    if (cb >= wpr) return;
+    const int nrb = (h + NM_NEED_ROWS - 1) / NM_NEED_ROWS;
+    const int f = fl / 3, l = fl - 3 * f;
+    const unsigned char* __restrict__ need = oc.need + ((long long)fl * nrb) * wpr + cb;
+    const float* __restrict__ src = oc.levels + ((long long)f * 6 + l + 1) * oc.level_elems + x;
+    float2* __restrict__ G = oc.grad + (long long)fl * oc.level_elems + x;
     const bool intx = x >= 1 && x <= w - 2;
-    // all 26 loads of the block in flight before the first gradient is evaluated
-    float ctr[NM_NEED_ROWS + 2], lf[NM_NEED_ROWS], rt[NM_NEED_ROWS];
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        const int rb = rb0 + k;
+        if (rb >= nrb) break;
+        if (!dense && need[rb * wpr] == 0) continue;            // warp uniform
+        if (x >= w) continue;
+        const int y0 = rb * NM_NEED_ROWS;
+        const float* __restrict__ p = src + y0 * pitch;         // offsets inside a level fit 32 bits
+        float ctr[NM_NEED_ROWS + 2], lf[NM_NEED_ROWS], rt[NM_NEED_ROWS];
 #pragma unroll
-    for (int j = -1; j <= NM_NEED_ROWS; ++j) {
-        const int y = y0 + j;
-        ctr[j + 1] = (intx && y >= 0 && y < h) ? __ldg(p + j * pitch) : 0.f;
-    }
+        for (int j = -1; j <= NM_NEED_ROWS; ++j) {
+            const int y = y0 + j;
+            ctr[j + 1] = (intx && y >= 0 && y < h) ? __ldg(p + j * pitch) : 0.f;
+        }
 #pragma unroll
-    for (int j = 0; j < NM_NEED_ROWS; ++j) {
-        const int y = y0 + j;
-        const bool interior = intx && y >= 1 && y <= h - 2;
-        lf[j] = interior ? __ldg(p + j * pitch - 1) : 0.f;
-        rt[j] = interior ? __ldg(p + j * pitch + 1) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < NM_NEED_ROWS; ++j) {
-        const int y = y0 + j;
-        if (y < h) {
+        for (int j = 0; j < NM_NEED_ROWS; ++j) {
+            const int y = y0 + j;
             const bool interior = intx && y >= 1 && y <= h - 2;
-            float2 g = make_float2(0.f, 0.f);
-            if (interior) g = nm_gradient_at(rt[j], lf[j], ctr[j + 2], ctr[j]);
-            q[j * pitch] = g;
+            lf[j] = interior ? __ldg(p + j * pitch - 1) : 0.f;
+            rt[j] = interior ? __ldg(p + j * pitch + 1) : 0.f;
+        }
+        float2* __restrict__ q = G + y0 * pitch;
+#pragma unroll
+        for (int j = 0; j < NM_NEED_ROWS; ++j) {
+            const int y = y0 + j;
+            if (y < h) {
+                const bool interior = intx && y >= 1 && y <= h - 2;
+                float2 g = make_float2(0.f, 0.f);
+                if (interior) g = nm_gradient_at(rt[j], lf[j], ctr[j + 2], ctr[j]);
+                q[j * pitch] = g;
+            }
         }
     }
 }
@@ -525,19 +571,6 @@ __global__ void plan_kernel(const int* __restrict__ seg_raw, int* __restrict__ s
     counts[f] = off < capacity ? off : capacity;
 }
 
-struct GlobalDogFetch {
-    const float* L;            // frame's level 0 at the candidate pixel
-    long long le;              // level_elems
-    int pitch, l;
-    __device__ __forceinline__ float dogv(int k, int dx, int dy) const
-    {
-        const float* p = L + (long long)dy * pitch + dx;
-        return __fsub_rn(__ldg(p + (k + 1) * le), __ldg(p + k * le));
-    }
-    __device__ __forceinline__ float cur(int dx, int dy) const { return dogv(l + 1, dx, dy); }
-    __device__ __forceinline__ float down(int dx, int dy) const { return dogv(l, dx, dy); }
-    __device__ __forceinline__ float up(int dx, int dy) const { return dogv(l + 2, dx, dy); }
-};
 
 // The blocks of the level's gradient map that the keypoint's orientation window (orientation.cu:43-53) and
 // descriptor window (descriptor.cu:57-65, diagonal 16 x 16 chunks :94-97) read: same geometry routines as
@@ -753,9 +786,12 @@ int nm_extrema_launch(const NmOctave& oc, int, int, const NmDetectParams& dp, in
             configured_dev = dev;
         }
         const long long n_tiles = (long long)grid.x * grid.y * grid.z;
-        if (n_tiles >= (1LL << 31)) return NM_ERR_OVERFLOW;
+        if (n_tiles >= (1LL << 31) / EX2_LIST || !oc.cand_n || !oc.cand) return NM_ERR_OVERFLOW;
         const int ctas = (int)(n_tiles < (long long)n_sms * ctas_per_sm ? n_tiles : (long long)n_sms * ctas_per_sm);
-        extrema_kernel<<<ctas, block, EX2_SMEM, stream>>>(oc, dp, tma->map, (int)grid.x, (int)grid.y, (int)n_tiles);
+        extrema_kernel<<<ctas, block, EX2_SMEM, stream>>>(oc, dp, tma->map, (int)grid.x, (int)grid.y, (int)n_tiles, oc.cand_n, oc.cand);
+        NM_LAUNCH_CHECK();
+        refine_list_kernel<<<(unsigned)nm_div_up64(n_tiles, 8), 256, 0, stream>>>(oc, dp, (int)grid.x, (int)grid.y, (int)n_tiles,
+                                                                                oc.cand_n, oc.cand);
     } else if (tma && tma->valid && getenv("NM_EXTREMA_NO_TMA") == nullptr) {
         extrema_grad_kernel<true><<<grid, block, 0, stream>>>(oc, dp, tma->map);
     } else {
@@ -768,18 +804,14 @@ int nm_extrema_launch(const NmOctave& oc, int, int, const NmDetectParams& dp, in
 
 int nm_gradmap_launch(const NmOctaveTable& tab, int batch, int dense, cudaStream_t stream)
 {
-    NmGradTasks tasks;
-    long long total = 0;
+    if (batch * 3 > 65535) return NM_ERR_OVERFLOW;
     for (int o = 0; o < tab.n_oct; ++o) {
-        tasks.first[o] = total;
-        total += (long long)batch * 3 * nm_div_up(tab.o[o].h, NM_NEED_ROWS) * tab.o[o].wpr;
+        const NmOctave& oc = tab.o[o];
+        const int strips_x = nm_div_up(oc.wpr, 8), nrb = nm_div_up(oc.h, NM_NEED_ROWS);
+        dim3 grid(strips_x * nm_div_up(nrb, 4), batch * 3);
+        gradmap_kernel<<<grid, 256, 0, stream>>>(oc, strips_x, dense);
+        NM_LAUNCH_CHECK();
     }
-    for (int o = tab.n_oct; o < NM_MAX_OCTAVES; ++o) tasks.first[o] = total;
-    tasks.total = total;
-    const long long blocks = nm_div_up64(total, 8);
-    if (blocks >= (1LL << 31)) return NM_ERR_OVERFLOW;
-    gradmap_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tab, tasks, dense);
-    NM_LAUNCH_CHECK();
     return NM_OK;
 }
 

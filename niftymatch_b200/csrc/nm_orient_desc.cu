@@ -392,7 +392,7 @@ static int compat_table(NmOctaveTable& tab, const float* grad2, int ow, int oh, 
 {
     tab.n_oct = 1;
     NmOctave& oc = tab.o[0];
-    oc.levels = nullptr; oc.bitmap = nullptr; oc.wprefix = nullptr; oc.need = nullptr;
+    oc.levels = nullptr; oc.bitmap = nullptr; oc.wprefix = nullptr; oc.need = nullptr; oc.cand_n = nullptr; oc.cand = nullptr;
     oc.grad = reinterpret_cast<float2*>(const_cast<float*>(grad2));
     oc.w = ow; oc.h = oh; oc.pitch = ow; oc.wpr = nm_div_up(ow, 32);
     oc.level_elems = (long long)ow * oh;

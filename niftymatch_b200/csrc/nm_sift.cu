@@ -214,6 +214,9 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
         if (rc == NM_OK) rc = dev_alloc(c, &oc.bitmap, B * 3 * nwords);
         if (rc == NM_OK) rc = dev_alloc(c, &oc.wprefix, B * 3 * nwords);
         if (rc == NM_OK) rc = dev_alloc(c, &oc.need, B * 3 * (size_t)nm_div_up(oc.h, 8) * oc.wpr);
+        const size_t tiles = (size_t)nm_div_up(oc.w, 32) * nm_div_up(oc.h, 32);
+        if (rc == NM_OK) rc = dev_alloc(c, &oc.cand_n, B * tiles);
+        if (rc == NM_OK) rc = dev_alloc(c, &oc.cand, B * tiles * 32);
     }
     const size_t S = (size_t)c->n_oct * 3, cap = (size_t)capacity;
     if (rc == NM_OK) rc = dev_alloc(c, &c->seg_raw, B * S);
@@ -272,6 +275,9 @@ static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, in
         oc.bitmap += (long long)first * 3 * nwords;
         oc.wprefix += (long long)first * 3 * nwords;
         oc.need += (long long)first * 3 * nm_div_up(oc.h, 8) * oc.wpr;
+        const long long tiles = (long long)nm_div_up(oc.w, 32) * nm_div_up(oc.h, 32);
+        oc.cand_n += first * tiles;
+        oc.cand += first * tiles * 32;
     }
     const long long S = (long long)c->n_oct * 3, cap = c->capacity;
     int* seg_raw = c->seg_raw + first * S;
@@ -345,7 +351,7 @@ static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, in
     if (fused) for (int o = 0; o < c->n_oct; ++o) tab.o[o].need = nullptr;      // emit_kernel does not mark
     for (int o = 0; o < c->n_oct; ++o) {
         if ((rc = nm_extrema_launch(tab.o[o], o, c->n_oct, dp, n, st, &ts->ex[o], fused)) != NM_OK) return rc;
-        ++launches;
+        launches += fused ? 1 : 2;
     }
     if (timing) cudaEventRecord(c->ev[2], st);
     // ---- ordered compaction (emit also marks the gradient blocks the keypoint windows read) ----
@@ -362,7 +368,7 @@ static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, in
     // ---- gradient maps of the marked blocks ----------------------------------------------
     if (!fused) {
         if ((rc = nm_gradmap_launch(tab, n, c->dense_grad, st)) != NM_OK) return rc;
-        ++launches;
+        launches += c->n_oct;
     }
     if (timing) cudaEventRecord(c->ev[4], st);
     // ---- orientation, descriptor -----------------------------------------------------

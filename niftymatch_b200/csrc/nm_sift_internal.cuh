@@ -25,6 +25,8 @@ struct NmOctave {
     float2*   grad;
     uint32_t* bitmap;
     int*      wprefix;
+    int*      cand_n;          // [B * tiles]: candidates of each 32 x 32 tile handed from extrema_kernel to refine_list_kernel
+    unsigned short* cand;      // [B * tiles][32]: level << 10 | tile row << 5 | tile column
     unsigned char* need;       // [B][3][ceil(h/8)][wpr]: 8-row x 32-column blocks of the gradient maps that a keypoint window reads
     long long level_elems;     // h*pitch
     int       w, h, pitch, wpr;

@@ -27,13 +27,32 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 INC="-I$HERE/shim -I$REF/utils -I$REF/gpu/kernels -I$REF/gpu/utils -I$REF/gpu/sift"
 FLAGS="$ARCH -std=c++17 -O2 -DUSE_CUDA -Xcompiler -fPIC -w $INC"
 sed -e 's/#define CHUNK 16/#define CHUNK 4/' "$REF/gpu/kernels/match.cu" > "$TMP/match.cu"
-# orientation.cu is included textually by ref_driver.cu (see there)
+# orientation.cu is included textually by ref_driver.cu (see there).  A second, patched temporary copy gives the
+# reference's PUBLIC orientation kernel in a form that terminates on sm_70+: kernel_orientations_optim calls
+# __syncthreads() inside `if (index < NBINS - 1)` (orientation.cu:68-86), which deadlocks under independent thread
+# scheduling.  The copy hoists the two barriers out of the branch and keeps every arithmetic statement (the
+# 10-pixel window clamp :29-30, the in-place update of hist[35] by thread 0 :78-80 with its race against thread 34,
+# first-two-peaks :118-127); the symbols get a _hoisted suffix so that both variants link into one library.
+ORI="$REF/gpu/kernels/orientation.cu"
+l68="$(sed -n 68p "$ORI")"; l71="$(sed -n 71p "$ORI")"; l81="$(sed -n 81p "$ORI")"; l83="$(sed -n 83p "$ORI")"; l84="$(sed -n 84p "$ORI")"
+case "$l68" in *"if (index < NBINS - 1) {"*) ;; *) echo "[build_ref] orientation.cu:68 is not what the patch expects" >&2; exit 1;; esac
+case "$l71" in *"for (int iter = 0; iter < 6; ++iter) {"*) ;; *) echo "[build_ref] orientation.cu:71 unexpected" >&2; exit 1;; esac
+case "$l81$l84" in *"__syncthreads();"*"__syncthreads();"*) ;; *) echo "[build_ref] orientation.cu:81/84 unexpected" >&2; exit 1;; esac
+case "$l83" in *"hist[index] = temp[index];"*) ;; *) echo "[build_ref] orientation.cu:83 unexpected" >&2; exit 1;; esac
+sed -e '68s/.*/    { const bool nm_act = (index < NBINS - 1);/' \
+    -e '71s/.*/        for (int iter = 0; iter < 6; ++iter) { if (nm_act) {/' \
+    -e '81s/.*/            } __syncthreads();/' \
+    -e '83s/.*/            if (nm_act) hist[index] = temp[index];/' \
+    -e 's/kernel_orientations_optim/kernel_orientations_optim_hoisted/g' \
+    -e 's/kernel_orientations_naive/kernel_orientations_naive_unused/g' \
+    -e 's/detect_orientations/detect_orientations_hoisted/g' "$ORI" > "$TMP/orientation_hoisted.cu"
 SRCS=(convolution downsample cudamath keypoint descriptor transpose bgra_2_gray cast undistort resample)
 pids=()
 for s in "${SRCS[@]}"; do
     $NVCC $FLAGS -c "$REF/gpu/kernels/$s.cu" -o "$TMP/$s.o" & pids+=($!)
 done
 $NVCC $FLAGS -c "$TMP/match.cu" -o "$TMP/match.o" & pids+=($!)
+$NVCC $FLAGS -c "$TMP/orientation_hoisted.cu" -o "$TMP/orientation_hoisted.o" & pids+=($!)
 for s in pyramidata siftdata siftfunctions; do
     $NVCC $FLAGS -c "$REF/gpu/sift/$s.cu" -o "$TMP/$s.o" & pids+=($!)
 done

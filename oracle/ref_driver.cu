@@ -34,6 +34,11 @@
 // In that build only the public API is used (orientation mode 0 works there: no deadlock).
 #ifndef NM_COMPAT_BUILD
 #include "orientation.cu"
+// The reference's public kernel with its two divergent barriers hoisted out of the branch (a patched temporary
+// copy of the same source, made and compiled by oracle/build_ref.sh): orientation mode 3.
+void detect_orientations_hoisted(const float4* key_pts, const float2* grad, const int num_pts, const int octave_width,
+                                 const int octave_height, float gauss_factor, const float xper, float2* result,
+                                 cudaStream_t stream);
 #define NMREF(name) nmref_##name
 #else
 #define NMREF(name) nmcompat_##name
@@ -68,7 +73,8 @@ struct Cfg {
     int   clear_grad;       // 1: client zeroes PyramidData::_grad before each octave (defined borders)
     int   orient_mode;      // 0: detect_orientations (public API; deadlocks on sm_70+, refused unless
                             //    NMREF_ALLOW_DEADLOCK is set), 1: the reference's kernel_orientations_naive,
-                            // 2: orientations injected by the caller (orient_in)
+                            // 2: orientations injected by the caller (orient_in),
+                            // 3: the reference's public kernel with the barriers hoisted (build_ref.sh; reference build only)
 };
 
 // compute_orientations of the reference (siftfunctions.cu:136-152) with a selectable kernel.
@@ -91,6 +97,10 @@ void orientations_step(PyramidData& py, const SiftParams& P, int o, int ow, int 
         } else if (mode == 2) {
             cudaMemcpy(orient, orient_in + 2 * (size_t)(*inject_off), n * sizeof(float2), cudaMemcpyHostToDevice);
             *inject_off += n;
+        } else if (mode == 3) {
+#ifndef NM_COMPAT_BUILD
+            detect_orientations_hoisted(key_pts, grad, n, ow, oh, 1.5f, xper, orient, 0);
+#endif
         } else {
             detect_orientations(key_pts, grad, n, ow, oh, 1.5f, xper, orient);
         }
@@ -244,7 +254,7 @@ int NMREF(sift_frame)(const float* image_host, int w, int h, const float* cfg6,
 #ifndef NM_COMPAT_BUILD
     if (c.orient_mode == 0 && !std::getenv("NMREF_ALLOW_DEADLOCK")) return -1;
 #else
-    if (c.orient_mode == 1) return -3;     // the reference's non-public kernel does not exist here
+    if (c.orient_mode == 1 || c.orient_mode == 3) return -3;     // the reference's non-public / patched kernels do not exist here
 #endif
     if (c.orient_mode == 2 && !orient_in) return -2;
     SiftParams P = make_params(w, h, c);
@@ -275,7 +285,7 @@ int NMREF(sift_frame_masked)(const float* image_host, int w, int h, const float*
 #ifndef NM_COMPAT_BUILD
     if (c.orient_mode == 0 && !std::getenv("NMREF_ALLOW_DEADLOCK")) return -1;
 #else
-    if (c.orient_mode == 1) return -3;
+    if (c.orient_mode == 1 || c.orient_mode == 3) return -3;
 #endif
     if (c.orient_mode == 2 && !orient_in) return -2;
     if (!mask_host) return -4;
@@ -314,7 +324,7 @@ int NMREF(sift_bench)(const float* frames_dev, int n_frames, int w, int h, const
 {
     Cfg c = { cfg6[0], cfg6[1], (int)cfg6[2], (int)cfg6[3], (int)cfg6[4], (int)cfg6[5] };
 #ifndef NM_COMPAT_BUILD
-    if (c.orient_mode != 1) return -1;     // only the runnable configuration can be timed
+    if (c.orient_mode != 1 && c.orient_mode != 3) return -1;     // only the runnable configurations can be timed
 #else
     if (c.orient_mode != 0) return -1;
 #endif

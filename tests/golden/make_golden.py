@@ -175,6 +175,42 @@ def mosaic(outdir):
     np.savez_compressed(os.path.join(outdir, "mosaic_128x90.npz"), **out)
 
 
+def orient_pub(outdir):
+    """Orientations and descriptors through the reference's PUBLIC orientation kernel (kernel_orientations_optim,
+    orientation.cu:11-129) in the terminating form oracle/build_ref.sh builds (its two divergent __syncthreads()
+    hoisted out of the branch, arithmetic untouched): the 10-pixel window clamp (:29-30), the smoothing with the
+    in-place hist[35] update (:78-80), first-two-peaks (:118-127), then compute_descriptors on ITS orientations.
+    The kernel has a write/read race on hist[35] (thread 0 writes it in place while thread 34 reads it),
+    so the capture is repeated and the run-to-run spread is stored beside the values."""
+    os.makedirs(outdir, exist_ok=True)
+    ref, orc = load_reflib(), load_oracle()
+    assert ref is not None, "oracle/_ref/libnmref.so missing"
+    out = {}
+    for (w, h, seed) in [(256, 192, synth.SEED_BASE), (384, 256, synth.SEED_BASE + 3)]:
+        img = synth.scene(w, h, seed)
+        for peak in (0.0, 2.0):
+            tag = f"{w}x{h}_p{int(peak)}"
+            runs = [ref.sift_frame(img, peak=peak, want_levels=False, orient_mode=3) for _ in range(5)]
+            r = runs[0]
+            c = orc.sift_frame(img, peak=peak, want_levels=False, orient_mode=0)
+            assert np.array_equal(r["seg_counts"], c["seg_counts"])
+            spread = max(float(np.abs(q["orient"] - r["orient"]).max()) for q in runs[1:])
+            dspread = max(float(np.abs(q["desc"] - r["desc"]).max() / max(np.abs(r["desc"]).max(), 1e-20)) for q in runs[1:])
+            out[f"{tag}_seg_counts"] = r["seg_counts"]
+            out[f"{tag}_kpts"] = r["kpts"]
+            out[f"{tag}_orient"] = r["orient"]
+            out[f"{tag}_desc"] = r["desc"]
+            out[f"{tag}_x"], out[f"{tag}_y"] = r["x"], r["y"]
+            out[f"{tag}_run_spread"] = np.array([spread, dspread])
+            ok = (r["orient"] >= 0) & (c["orient"] >= 0)
+            d = np.abs(r["orient"] - c["orient"])[ok]
+            d = np.minimum(d, 2 * np.pi - d)
+            print("orient_pub", tag, "n =", r["n"], "run-to-run spread", spread, dspread,
+                  "| vs oracle mode 0: peaks differ", int(((r["orient"] >= 0) != (c["orient"] >= 0)).sum()),
+                  "max", float(d.max()) if d.size else 0.0, "count > 1e-5:", int((d > 1e-5).sum()), "> 1e-3:", int((d > 1e-3).sum()))
+    np.savez_compressed(os.path.join(outdir, "sift_orient_public.npz"), **out)
+
+
 def main(outdir):
     os.makedirs(outdir, exist_ok=True)
     ref, orc = load_reflib(), load_oracle()
@@ -242,9 +278,12 @@ if __name__ == "__main__":
         preprocess(out)
     elif len(sys.argv) > 2 and sys.argv[2] == "mosaic":
         mosaic(out)
+    elif len(sys.argv) > 2 and sys.argv[2] == "orient":
+        orient_pub(out)
     else:
         main(out)
         masked(out)
         ransac(out)
         preprocess(out)
         mosaic(out)
+        orient_pub(out)
