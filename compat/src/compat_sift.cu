@@ -6,6 +6,7 @@
 //     octave in the reference): the detector reads the linear DoG buffers;
 //   * compute_sift_matches is one call: no transposes, no second N_A x N_B matrix;
 //   * every call honours the caller's stream.
+#include <cstdlib>
 #include "nm_compat.hpp"
 #include "nm_b200.h"
 
@@ -132,10 +133,17 @@ void PyramidData::gpu_collate_keypoints_for_level(int level, int num_pixels)
 }
 
 // ---- siftfunctions.h ----------------------------------------------------------------------------
+// The reference fills the caller's N_A x N_B `distance` buffer (siftfunctions.cu:25-33), so a non-null buffer is
+// filled here too -- bitwise, which means 128 sequential fp32 multiply-adds per pair on the CUDA cores (the exact
+// engine; the matrix cannot come out of a tensor-core contraction bit for bit).  Clients that only read
+// _match_indexes can skip it and get the tcgen05 engine (same indices): pass distance = nullptr (an extension: the
+// reference would dereference it), or set NM_COMPAT_SKIP_DISTANCE=1 to leave an unmodified client's buffer
+// untouched.
 void compute_sift_matches(SiftData* A, SiftData* B, float* distance, float ambiguity, cudaStream_t stream)
 {
+    static const bool skip_distance = std::getenv("NM_COMPAT_SKIP_DISTANCE") != nullptr;
     nm_check(nm_match_f32(dev(A->_desc), A->_num_items, dev(B->_desc), B->_num_items, ambiguity, dev(A->_match_indexes),
-                          distance, stream),
+                          skip_distance ? nullptr : distance, stream),
              "compute_sift_matches");
 }
 

@@ -201,6 +201,28 @@ def test_sift_vs_reference_golden(nm, name):
         assert np.array_equal(p["x"], g[f"{tag}_x"]) and np.array_equal(p["y"], g[f"{tag}_y"])
 
 
+def test_sift_vs_reference_public_orientation_kernel(nm):
+    """The whole chain against reference-derived numbers with NO oracle in between: keypoints, the orientations of the
+    reference's public kernel_orientations_optim (barriers hoisted so that it terminates on sm_70+, arithmetic
+    untouched; tests/golden/README.md) and the descriptors the reference computed from ITS orientations."""
+    g = _gold("sift_orient_public.npz")
+    for (w, h, seed) in [(256, 192, synth.SEED_BASE), (384, 256, synth.SEED_BASE + 3)]:
+        img = synth.scene(w, h, seed)
+        for peak in (0.0, 2.0):
+            tag = f"{w}x{h}_p{int(peak)}"
+            p = run_product(nm, img[None], peak=peak)[0]
+            assert np.array_equal(p["seg_counts"], g[f"{tag}_seg_counts"])
+            assert np.array_equal(p["kpts"], g[f"{tag}_kpts"]), "keypoints not bitwise equal to the reference's"
+            go = g[f"{tag}_orient"]
+            assert np.array_equal(p["orient"] < 0, go < 0)
+            assert ang_diff(p["orient"][go >= 0], go[go >= 0]).max() <= ORIENT_TOL
+            gd = g[f"{tag}_desc"]
+            assert p["n"] == len(gd)
+            rel = np.linalg.norm(p["desc"] - gd, axis=1) / np.maximum(np.linalg.norm(gd, axis=1), 1e-20)
+            assert rel.max() <= 1e-3, rel.max()
+            assert np.array_equal(p["x"], g[f"{tag}_x"]) and np.array_equal(p["y"], g[f"{tag}_y"])
+
+
 @pytest.mark.parametrize("size,peak", [((640, 480), 0.0), ((640, 480), 2.0), ((250, 130), 0.0), ((97, 161), 0.0)])
 def test_sift_vs_oracle(nm, oracle, size, peak):
     w, h = size
