@@ -775,16 +775,17 @@ int nm_extrema_launch(const NmOctave& oc, int, int, const NmDetectParams& dp, in
     dim3 block(32, 8), grid(nm_div_up(oc.w, EX_TW), nm_div_up(oc.h, EX_TH), batch);
     if (!fused) {
         if (extrema_use_fused(tma) && !(tma && tma->valid)) return NM_ERR_INVALID;
-        static int configured_dev = -1, n_sms = 0, ctas_per_sm = 2;
-        int dev = 0;
-        NM_CUDA_TRY(cudaGetDevice(&dev));
-        if (configured_dev != dev) {
+        static NmDeviceOnce once;
+        static std::atomic<int> ctas_cfg{2};
+        if (once.first()) {
+            int per_sm = 2;
             NM_CUDA_TRY(cudaFuncSetAttribute(extrema_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EX2_SMEM));
-            NM_CUDA_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-            NM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, extrema_kernel, 256, EX2_SMEM));
-            if (ctas_per_sm < 1) ctas_per_sm = 1;
-            configured_dev = dev;
+            NM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extrema_kernel, 256, EX2_SMEM));
+            ctas_cfg.store(per_sm < 1 ? 1 : per_sm);
+            once.done();
         }
+        const int n_sms = nm_sm_count(), ctas_per_sm = ctas_cfg.load();
+        if (n_sms <= 0) return NM_ERR_NO_DEVICE;
         const long long n_tiles = (long long)grid.x * grid.y * grid.z;
         if (n_tiles >= (1LL << 31) / EX2_LIST || !oc.cand_n || !oc.cand) return NM_ERR_OVERFLOW;
         const int ctas = (int)(n_tiles < (long long)n_sms * ctas_per_sm ? n_tiles : (long long)n_sms * ctas_per_sm);
@@ -905,7 +906,7 @@ extern "C" int nm_collate_f32(const float* dense4, int num_pixels, float* out4, 
     cudaStream_t st = (cudaStream_t)stream;
     const int nblocks = nm_div_up(num_pixels, COL_CHUNK);
     int* block_counts = nullptr;
-    NM_CUDA_TRY(cudaMallocAsync(&block_counts, sizeof(int) * nblocks, st));
+    NM_CUDA_TRY(nm_ws_alloc(&block_counts, sizeof(int) * nblocks, st));
     collate_count_kernel<<<nblocks, 256, 0, st>>>(reinterpret_cast<const float4*>(dense4), num_pixels, block_counts);
     collate_scan_kernel<<<1, 32, 0, st>>>(block_counts, nblocks, count_dev);
     collate_write_kernel<<<nblocks, 256, 0, st>>>(reinterpret_cast<const float4*>(dense4), num_pixels,

@@ -310,7 +310,7 @@ int nm_match_scan_exact(const float* A, long long a_sa, long long a_sk, int nA, 
     const int per = nm_div_up(b_tiles, splits);
     splits = nm_div_up(b_tiles, per);
     float4* part = rec4;
-    if (splits > 1) NM_CUDA_TRY(cudaMallocAsync(&part, sizeof(float4) * (size_t)splits * nA, stream));
+    if (splits > 1) NM_CUDA_TRY(nm_ws_alloc(&part, sizeof(float4) * (size_t)splits * nA, stream));
     dim3 grid(a_tiles, splits);
     if (D)
         scan_exact_kernel<true, false><<<grid, 256, 0, stream>>>(A, a_sa, a_sk, nA, B, nB, dim, index_offset, per, part, D, d_sa, d_sb, nullptr, nullptr, nullptr, nullptr);
@@ -335,13 +335,15 @@ int nm_match_scan_exact_rows(const float* A, int nA, const float* B, int nB, int
                              const int* row_list, const int* row_count, float4* rec4, cudaStream_t stream)
 {
     if (nA <= 0 || nB <= 0 || dim <= 0 || !row_list || !row_count) return NM_ERR_INVALID;
+    // scan_rows_small_kernel is written for 128-D rows read with 16-byte loads
+    if (dim != 128 || ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15)) return NM_ERR_INVALID;
     const int b_tiles = nm_div_up(nB, MT);
     const int per = 4;                                            // 4 x 64 database rows per block
     const int splits = nm_div_up(b_tiles, per);
     if (splits > 65535) return NM_ERR_OVERFLOW;
     const int row_blocks = min(nm_div_up(nA, MT), 32);
     unsigned char* keys = nullptr;
-    NM_CUDA_TRY(cudaMallocAsync(&keys, 12 * (size_t)nA, stream));
+    NM_CUDA_TRY(nm_ws_alloc(&keys, 12 * (size_t)nA, stream));
     unsigned long long* key1 = reinterpret_cast<unsigned long long*>(keys);
     unsigned* key2 = reinterpret_cast<unsigned*>(keys + 8 * (size_t)nA);
     cudaError_t e = cudaMemsetAsync(keys, 0xff, 12 * (size_t)nA, stream);
@@ -420,7 +422,7 @@ extern "C" int nm_match_f32(const float* A, int nA, const float* B, int nB, floa
     if (!A || !B || !match_io || nA <= 0 || nB <= 0) return NM_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     float4* rec = nullptr;
-    NM_CUDA_TRY(cudaMallocAsync(&rec, sizeof(float4) * (size_t)nA, st));
+    NM_CUDA_TRY(nm_ws_alloc(&rec, sizeof(float4) * (size_t)nA, st));
     int rc;
     const bool aligned = !((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15);
     if (distance || !aligned || pick_engine((long long)nA * nB) == 0)
@@ -447,7 +449,7 @@ extern "C" int nm_dist2_f32(const float* A_t, int size_A, const float* B, int si
     if (!A_t || !B || !result_t || size_A <= 0 || size_B <= 0 || vector_dim <= 0) return NM_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     float4* rec = nullptr;
-    NM_CUDA_TRY(cudaMallocAsync(&rec, sizeof(float4) * (size_t)size_A, st));
+    NM_CUDA_TRY(nm_ws_alloc(&rec, sizeof(float4) * (size_t)size_A, st));
     // A(a,k) = A_t[k*size_A + a];  D^T[b*size_A + a]   (match.h:7-23)
     int rc = nm_match_scan_exact(A_t, 1, size_A, size_A, B, size_B, vector_dim, 0, rec, result_t, 1, size_A, st);
     cudaFreeAsync(rec, st);

@@ -28,10 +28,10 @@
 //             first; its 4 best per row start every list (a running top-k inserts at rate k/n).
 //  3. rerank: one warp per query row dedupes and ranks the <= 32 candidates by score, evaluates the
 //             reference's exact fp32 distance for the 4 best (up to 10 when needed), and takes the
-//             best two.  The row is CERTIFIED when the exact second distance is below a rigorous
-//             lower bound on the true distance of every non-candidate (the fp16 rounding
-//             displacement of both operands is measured, the fp32 accumulation error bounded;
-//             see DESIGN.md); otherwise the row index is appended to a list and re-scanned by the
+//             best two.  The row is CERTIFIED when the exact second distance is below a lower bound
+//             on the true distance of every non-candidate: the fp16 rounding displacement of both
+//             operands is measured (rigorous), the tensor-core accumulation error is bounded by an
+//             empirical eta with a 8x margin over what the tests measure; otherwise the row index is appended to a list and re-scanned by the
 //             exact fp32 engine (nm_match.cu).  Either way the record is exact, so match indices
 //             equal the reference's.
 #include "nm_match.cuh"
@@ -538,14 +538,20 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict_
     // max_j |b^_j - s b_j| (measured by the pack kernel), so by the triangle inequality
     // s * sqrt(true d) >= sqrt(|a^-b^|^2) - delta.
     const double sc = (double)scale;
-    const double bmax2 = (double)__uint_as_float(hdr[1]) * sc * sc * (1.0 + 1e-5);
-    const double eta = ldexp(nh2 + bmax2, -17);    // measured: see tests (accumulation error < 2^-20 (|a^|^2+|b^|^2))
+    // margins: |b^|^2 differs from |s b|^2 by up to ~2^-10 relative (fp16 rounding of every element), hence 1 + 2^-9;
+    // eta = 2^-17 (|a^|^2 + |b^|^2max) is an EMPIRICAL bound on the tensor-core accumulation error (measured below
+    // 2^-20 of that sum, tests/test_gpu_match.py) plus an absolute 2^-16 for the subnormal tail of the fp16 split of
+    // -|b^|^2/512 on all-tiny rows
+    const double bmax2 = (double)__uint_as_float(hdr[1]) * sc * sc * (1.0 + 1.953125e-3);
+    const double eta = ldexp(nh2 + bmax2, -17) + 1.52587890625e-5;
     const double delta = (sqrt(ne2) + sqrt((double)__uint_as_float(hdr[2]))) * (1.0 + 1e-5) + 1e-7;
     auto lower_bound = [&](float t) -> double {    // on the true distance of every column with score <= t
         if (t <= -FLT_MAX) return (double)INFINITY;
         const double dh = nh2 - 2.0 * (double)t - eta;
         const double root = (dh > 0.0 ? sqrt(dh) : 0.0) - delta;
-        return root > 0.0 ? (root / sc) * (root / sc) * (1.0 - 1e-6) : 0.0;
+        // 1 - 2e-5: the reference's 128-step fp32 FMA distance carries up to 129 * 2^-24 = 7.7e-6 relative rounding
+        // error on both the second distance and the non-candidate it is compared with
+        return root > 0.0 ? (root / sc) * (root / sc) * (1.0 - 2e-5) : 0.0;
     };
     auto exact_distance = [&](int col) -> float {  // match.cu:36-42: i ascending, t = a - b, acc = fma(t, t, acc)
         const float4* __restrict__ bp = reinterpret_cast<const float4*>(B + (size_t)col * 128);
@@ -600,43 +606,34 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict_
     }
 }
 
-struct TcDeviceState {
-    int checked = 0;
-    bool ok = false;
-};
-TcDeviceState g_state;
 uint32_t g_lbo = TC_KSTRIDE, g_sbo = 128;
 
 } // namespace
 
+// Per device: compute capability 10.x, enough opt-in shared memory, and the scan kernel's dynamic shared memory
+// attribute set (cudaFuncSetAttribute applies to the current device only).
 bool nm_match_tc_available()
 {
-    if (!g_state.checked) {
-        int dev = 0, major = 0, smem = 0;
-        bool ok = cudaGetDevice(&dev) == cudaSuccess &&
-                  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess && major == 10 &&
-                  cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess &&
-                  smem >= TC_SMEM_BYTES;
-        if (ok) ok = cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
-        if (!ok) cudaGetLastError();
-        if (ok) {
-            // the engine allocates its workspace stream-ordered per call: keep freed blocks in the
-            // default pool instead of returning them to the driver at every synchronisation
-            cudaMemPool_t pool;
-            unsigned long long keep = ~0ull;
-            if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess ||
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess)
-                cudaGetLastError();
-        }
-        // bring-up aid: NM_TC_DESC="lbo,sbo" overrides the descriptor strides (bytes)
-        if (const char* env = getenv("NM_TC_DESC")) {
-            unsigned l = 0, b = 0;
-            if (sscanf(env, "%u,%u", &l, &b) == 2) { g_lbo = l; g_sbo = b; }
-        }
-        g_state.ok = ok;
-        g_state.checked = 1;
+    static std::atomic<signed char> state[64];                  // 0 unknown, 1 usable, -1 not
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (dev >= 0 && dev < 64) {
+        const signed char s = state[dev].load(std::memory_order_acquire);
+        if (s != 0) return s > 0;
     }
-    return g_state.ok;
+    int major = 0, smem = 0;
+    bool ok = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess && major == 10 &&
+              cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess &&
+              smem >= TC_SMEM_BYTES;
+    if (ok) ok = cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    // bring-up aid: NM_TC_DESC="lbo,sbo" overrides the descriptor strides (bytes)
+    if (const char* env = getenv("NM_TC_DESC")) {
+        unsigned l = 0, b = 0;
+        if (sscanf(env, "%u,%u", &l, &b) == 2) { g_lbo = l; g_sbo = b; }
+    }
+    if (dev >= 0 && dev < 64) state[dev].store(ok ? 1 : -1, std::memory_order_release);
+    return ok;
 }
 
 // Number of database splits: enough CTAs to fill the machine, at most 8 (32 candidates per
@@ -701,7 +698,7 @@ static int tc_run(const float* A, int nA, const float* B, int nB, int index_offs
     const size_t off_bp = off_ap + (size_t)n_atiles * TC_TILE_BYTES;
     const size_t total = off_bp + (size_t)n_btiles * TC_TILE_BYTES;
     uint8_t* ws = nullptr;
-    NM_CUDA_TRY(cudaMallocAsync(&ws, total, stream));
+    NM_CUDA_TRY(nm_ws_alloc(&ws, total, stream));
     unsigned* hdr = reinterpret_cast<unsigned*>(ws);
     int* fb_count = reinterpret_cast<int*>(ws + off_cnt);
     int* fb_list = reinterpret_cast<int*>(ws + off_list);

@@ -368,12 +368,12 @@ int nm_describe_launch(const NmOctaveTable& tab, int batch, int capacity, const 
                        const float4* kpts, const int* meta, const float2* orient, float* desc,
                        float* x, float* y, int num_dogs, int exact, cudaStream_t stream)
 {
-    static bool configured = false;
+    static NmDeviceOnce once;
     constexpr int smem = DE_WARPS * DE_BINS * DE_COPIES * (int)sizeof(float);
-    if (!configured) {
+    if (once.first()) {
         NM_CUDA_TRY(cudaFuncSetAttribute(describe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         NM_CUDA_TRY(cudaFuncSetAttribute(describe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        once.done();
     }
     dim3 grid(nm_div_up(capacity, DE_WARPS), batch);
     if (exact)
@@ -404,8 +404,8 @@ namespace {
 struct CompatScratch { int* counts; int* meta; };
 int compat_scratch(CompatScratch& sc, int n, cudaStream_t st)
 {
-    NM_CUDA_TRY(cudaMallocAsync(&sc.counts, sizeof(int), st));
-    NM_CUDA_TRY(cudaMallocAsync(&sc.meta, sizeof(int) * n, st));
+    NM_CUDA_TRY(nm_ws_alloc(&sc.counts, sizeof(int), st));
+    NM_CUDA_TRY(nm_ws_alloc(&sc.meta, sizeof(int) * n, st));
     compat_fill_meta<<<nm_div_up(n, 256), 256, 0, st>>>(sc.meta, sc.counts, n);
     NM_LAUNCH_CHECK();
     return NM_OK;

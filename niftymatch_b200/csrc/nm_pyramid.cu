@@ -529,16 +529,7 @@ __global__ void blur_cols_generic(const NmBlurArgs a)
         a.dst2[(long long)f * a.dst2_fstride + (long long)(y >> 1) * a.dst2_pitch + (x >> 1)] = sum;
 }
 
-int sm_count()
-{
-    static int n_sms = 0;
-    if (n_sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-            n_sms = 0;
-    }
-    return n_sms;
-}
+int sm_count() { return nm_sm_count(); }
 
 // The strip-walking kernel is taken for TMA-describable sources with enough chunks: below ~8 chunks per CTA the
 // lead-in row pass of a piece that starts inside a strip costs more than the tile kernels' halo rows.
@@ -548,7 +539,8 @@ bool strip_eligible(const NmBlurArgs& a, const NmBlurTma* tma)
     static const bool no_strip = getenv("NM_BLUR_TILE") != nullptr || getenv("NM_BLUR_WALK") != nullptr;
     const int n_sms = sm_count();
     if (no_strip || !tma || !tma->valid || !tma->valid_strip || n_sms <= 0 || a.radius < 1 || a.radius > 16) return false;
-    static const long long strip_min = getenv("NM_BLUR_STRIP_MIN") ? atoll(getenv("NM_BLUR_STRIP_MIN")) : 16LL * n_sms;
+    static const long long strip_min_env = getenv("NM_BLUR_STRIP_MIN") ? atoll(getenv("NM_BLUR_STRIP_MIN")) : -1;
+    const long long strip_min = strip_min_env >= 0 ? strip_min_env : 16LL * n_sms;
     const long long strips = (long long)nm_div_up(a.w, kTW) * a.batch;
     const long long total = strips * nm_div_up(a.h + 2 * a.radius, kCH);
     return total >= strip_min && strips < (1LL << 31);
@@ -558,33 +550,24 @@ template <int R>
 int launch_tile(const NmBlurArgs& a, cudaStream_t stream, const NmBlurTma* tma)
 {
     if (a.src_bgra && !strip_eligible(a, tma)) return NM_ERR_INVALID;     // only the strip kernel converts
-    static bool configured = false;
+    static NmDeviceOnce once;
     constexpr int smem = blur_smem_bytes(R);
-    if (!configured) {
+    if (once.first()) {
         NM_CUDA_TRY(cudaFuncSetAttribute(blur_tile_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         NM_CUDA_TRY(cudaFuncSetAttribute(blur_tile_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        NM_CUDA_TRY(cudaFuncSetAttribute(blur_walk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        NM_CUDA_TRY(cudaFuncSetAttribute(blur_strip_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, strip_smem_bytes(R)));
+        once.done();
     }
     dim3 grid(nm_div_up(a.w, kTW), nm_div_up(a.h, kTH), a.batch);
     if (tma && tma->valid) {
-        static int n_sms = 0;
-        if (n_sms == 0) {
-            int dev = 0;
-            NM_CUDA_TRY(cudaGetDevice(&dev));
-            NM_CUDA_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-            NM_CUDA_TRY(cudaFuncSetAttribute(blur_walk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        }
+        const int n_sms = nm_sm_count();
+        if (n_sms <= 0) return NM_ERR_NO_DEVICE;
         const long long n_tiles = (long long)grid.x * grid.y * grid.z;
         static const bool no_walk = getenv("NM_BLUR_TILE") != nullptr;        // tuning aid
         const int chunks = nm_div_up(a.h + 2 * R, kCH);
         const long long total = (long long)grid.x * a.batch * chunks;
         if (strip_eligible(a, tma)) {
-            static bool strip_configured = false;
-            if (!strip_configured) {
-                NM_CUDA_TRY(cudaFuncSetAttribute(blur_strip_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 strip_smem_bytes(R)));
-                strip_configured = true;
-            }
             const long long n_strips = (long long)grid.x * a.batch;
             blur_strip_kernel<R><<<2 * n_sms, kThreads, strip_smem_bytes(R), stream>>>(a, tma->map_strip, (int)grid.x, chunks,
                                                                                       (int)(n_strips / (2 * n_sms)), total);

@@ -461,7 +461,7 @@ int ransac_batch(int kind, const Pairs& P, int n_pairs, float thr, int iteration
                  o_H = o_rand + sizeof(int) * np * (size_t)draws, o_inl = o_H + sizeof(float) * 9 * np * (size_t)iterations,
                  o_skip = o_inl + sizeof(int) * np * (size_t)iterations, total = o_skip + np * (size_t)iterations;
     char* ws = nullptr;
-    NM_CUDA_TRY(cudaMallocAsync(&ws, total, st));
+    NM_CUDA_TRY(nm_ws_alloc(&ws, total, st));
     int* valid = reinterpret_cast<int*>(ws + o_valid);
     int* state = reinterpret_cast<int*>(ws + o_state);
     int* rand_list = reinterpret_cast<int*>(ws + o_rand);
@@ -503,7 +503,7 @@ extern "C" int nm_ransac_hypotheses_f32(int kind, const float* src_x, const floa
     if (!src_x || !src_y || !dst_x || !dst_y || !rand_list || !homographies || !inliers) return NM_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* skip = nullptr;
-    NM_CUDA_TRY(cudaMallocAsync(&skip, (size_t)iterations, st));
+    NM_CUDA_TRY(nm_ws_alloc(&skip, (size_t)iterations, st));
     const Pairs P{src_x, src_y, dst_x, dst_y, 0, nullptr, num_pts};
     const int rc = launch_hypotheses(kind, P, 1, rand_list, iterations, inlier_threshold, nullptr, homographies, inliers, skip, st);
     NM_CUDA_TRY(cudaFreeAsync(skip, st));

@@ -7,6 +7,7 @@
 #include "nm_sift_internal.cuh"
 #include "nm_pyramid.cuh"
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
@@ -44,7 +45,7 @@ struct nm_sift_ctx {
     float2* orient;
     float *desc, *x, *y;
     float* frames_stage;     // device staging for nm_sift_run_host: [B][h][w]
-    float* scratch;          // generic-radius blur scratch (lazily allocated)
+    float* scratch;          // row-pass buffer of the generic blur, [B][h][w]; allocated when a radius exceeds 16
     int exact_desc;
     int dense_grad;          // 1: gradient maps computed everywhere (tests / tools that read them), 0: only where keypoint windows read
     unsigned long long mask_tex;   // detector mask (0 = none); mask_arr/mask_own: texture made by nm_sift_set_mask_image
@@ -69,6 +70,32 @@ int dev_alloc(nm_sift_ctx* c, T** p, size_t count)
 }
 
 } // namespace
+
+cudaError_t nm_ws_alloc(void** p, size_t bytes, cudaStream_t stream)
+{
+    static std::atomic<cudaMemPool_t> pools[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaMallocAsync(p, bytes, stream);
+    cudaMemPool_t pool = pools[dev].load(std::memory_order_acquire);
+    if (pool == nullptr) {
+        cudaMemPoolProps props;
+        std::memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t fresh = nullptr;
+        if ((e = cudaMemPoolCreate(&fresh, &props)) != cudaSuccess) return e;
+        unsigned long long keep = ~0ull;                       // keep freed blocks: the workspaces recur every call
+        cudaMemPoolSetAttribute(fresh, cudaMemPoolAttrReleaseThreshold, &keep);
+        cudaMemPool_t expected = nullptr;
+        if (pools[dev].compare_exchange_strong(expected, fresh, std::memory_order_acq_rel)) pool = fresh;
+        else { cudaMemPoolDestroy(fresh); pool = expected; }   // another host thread was first
+    }
+    return cudaMallocFromPoolAsync(p, bytes, pool, stream);
+}
 
 extern "C" const char* nm_version(void) { return "nm-b200 0.1 (sm_100a)"; }
 
@@ -230,6 +257,11 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
     if (rc == NM_OK) rc = dev_alloc(c, &c->x, B * cap);
     if (rc == NM_OK) rc = dev_alloc(c, &c->y, B * cap);
     if (rc == NM_OK) rc = dev_alloc(c, &c->frames_stage, B * (size_t)P.width * P.height);
+    // radii above 16 (sigma > 4; the reference allows up to 45, MAX_KERNEL_LENGTH 91) take the generic two-pass blur,
+    // which needs a row-pass buffer: [B][h][w] of octave 0 covers every octave
+    bool wide = false;
+    for (int i = 0; i < 6; ++i) wide = wide || c->radii[i] > 16;
+    if (rc == NM_OK && wide) rc = dev_alloc(c, &c->scratch, B * (size_t)P.width * P.height);
     if (rc == NM_OK) {
         // descriptor slots start at 0 like SiftData::initialize_data (siftdata.cu:34)
         if (cudaMemset(c->desc, 0, B * cap * 128 * sizeof(float)) != cudaSuccess) rc = NM_ERR_ALLOC;
@@ -316,6 +348,7 @@ static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, in
             a.src = frames_dev; a.src_pitch = P.width; a.src_fstride = (long long)P.width * P.height;
             a.dst = oc.levels; a.dst_pitch = oc.pitch; a.dst_fstride = fstride;
             a.taps = c->taps[0]; a.radius = c->radii[0]; a.w = oc.w; a.h = oc.h; a.batch = n;
+            a.scratch = c->scratch ? c->scratch + (long long)first * P.width * P.height : nullptr;
             NmBlurTma base;
             nm_blur_make_tma(&base, frames_dev, P.width, P.height, P.width, (long long)P.width * P.height, n, c->radii[0], bgra);
             a.src_bgra = bgra ? 1 : 0;
@@ -335,6 +368,7 @@ static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, in
             a.src = oc.levels + i * oc.level_elems; a.src_pitch = oc.pitch; a.src_fstride = fstride;
             a.dst = oc.levels + (i + 1) * oc.level_elems; a.dst_pitch = oc.pitch; a.dst_fstride = fstride;
             a.taps = c->taps[i + 1]; a.radius = c->radii[i + 1]; a.w = oc.w; a.h = oc.h; a.batch = n;
+            a.scratch = c->scratch ? c->scratch + (long long)first * P.width * P.height : nullptr;
             if (i + 1 == P.num_dog_levels && o + 1 < c->n_oct) {
                 // level 3 (sigma doubled) decimated by 2 = next octave's level 0 (downsample.cu:15-16)
                 const NmOctave& nx = tab.o[o + 1];

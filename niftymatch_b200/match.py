@@ -17,14 +17,32 @@ def get_engine() -> int:
     return _lib.load().nm_match_get_engine()
 
 
+def _desc(t, name):
+    """The C-ABI reads raw memory: contiguous cuda float32 (n, 128) or nothing."""
+    import torch
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[1] == 128):
+        raise TypeError(f"{name}: expected a cuda float32 tensor of shape (n, 128), got {getattr(t, 'dtype', type(t))} "
+                        f"{tuple(getattr(t, 'shape', ()))}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _i32(t, name, n):
+    import torch
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.int32 and t.is_contiguous() and t.numel() == n):
+        raise TypeError(f"{name}: expected a contiguous cuda int32 tensor of {n} elements")
+    return t
+
+
 def match(A, B, ambiguity: float = 0.8, match_io=None, want_distance: bool = False):
     """compute_sift_matches semantics (reference src/gpu/sift/siftfunctions.cu:15-40).
     A: (nA,128), B: (nB,128) cuda float32.  Returns match indices (int32, -1 = rejected),
     and the nA x nB squared-distance matrix when want_distance."""
     import torch
+    A, B = _desc(A, "A"), _desc(B, "B")
     nA, nB = A.shape[0], B.shape[0]
     if match_io is None:
         match_io = torch.full((nA,), -1, dtype=torch.int32, device=A.device)
+    _i32(match_io, "match_io", nA)
     dist = torch.empty((nA, nB), dtype=torch.float32, device=A.device) if want_distance else None
     check(_lib.load().nm_match_f32(C.c_void_p(A.data_ptr()), nA, C.c_void_p(B.data_ptr()), nB, ambiguity,
                                    C.c_void_p(match_io.data_ptr()),
@@ -35,6 +53,8 @@ def match(A, B, ambiguity: float = 0.8, match_io=None, want_distance: bool = Fal
 def match_top2(A, B, index_offset: int = 0):
     """Per-shard records (nA,4) float32: (d1, bits(i1+offset), d2, 0)."""
     import torch
+    A = _desc(A, "A")
+    B = _desc(B, "B") if B.shape[0] else B
     nA, nB = A.shape[0], B.shape[0]
     rec = torch.empty((nA, 4), dtype=torch.float32, device=A.device)
     check(_lib.load().nm_match_top2_f32(C.c_void_p(A.data_ptr()), nA, C.c_void_p(B.data_ptr()) if nB else None, nB,
@@ -45,9 +65,13 @@ def match_top2(A, B, index_offset: int = 0):
 def merge_top2(recs, ambiguity: float = 0.8, match_io=None):
     """recs: (n_shards, nA, 4) records -> match indices."""
     import torch
+    if not (recs.is_cuda and recs.dtype == torch.float32 and recs.dim() == 3 and recs.shape[2] == 4):
+        raise TypeError("recs: expected a cuda float32 tensor of shape (n_shards, nA, 4)")
+    recs = recs if recs.is_contiguous() else recs.contiguous()
     n_shards, nA = recs.shape[0], recs.shape[1]
     if match_io is None:
         match_io = torch.full((nA,), -1, dtype=torch.int32, device=recs.device)
+    _i32(match_io, "match_io", nA)
     check(_lib.load().nm_match_merge_top2(C.c_void_p(recs.data_ptr()), n_shards, nA, ambiguity,
                                           C.c_void_p(match_io.data_ptr()), _stream_ptr()), "nm_match_merge_top2")
     return match_io
@@ -59,6 +83,7 @@ def tc_probe(A, B, want_candidates: bool = False):
     the candidate lists of the tcgen05 scan with the power-of-two scale that was applied."""
     import numpy as np
     import torch
+    A, B = _desc(A, "A"), _desc(B, "B")
     nA, nB = A.shape[0], B.shape[0]
     rec = torch.empty((nA, 4), dtype=torch.float32, device=A.device)
     fb, nl, sc = C.c_int(-1), C.c_int(0), C.c_float(0)

@@ -143,3 +143,30 @@ def test_reference_client_matcher_on_dropin():
     m, D = cl.match(g["A"], g["B"], 0.8, match_io=g["m0"], want_distance=True)
     assert np.array_equal(m, g["m"])
     assert np.array_equal(D, g["D"])
+
+
+@pytest.mark.gpu
+def test_dropin_matcher_reaches_the_tensor_core_engine_without_the_distance_matrix():
+    """compute_sift_matches fills the caller's distance matrix bitwise (exact engine).  NM_COMPAT_SKIP_DISTANCE=1 (or a
+    null `distance`) skips the matrix and lets the drop-in take the tcgen05 engine: same match indices.  3000 x 3000
+    descriptors = 9M pairs, above the auto-engine threshold; run in a child process because the switch is read once."""
+    if not os.path.exists(CLIENT):
+        pytest.skip("build/compat/libnmcompat.so not built")
+    import sys
+    from niftymatch_b200 import synth
+    from tests._util import FrameChecker
+    B = synth.descriptors(3000, 2)
+    A = synth.descriptors(3000, 1, planted_from=B)
+    m_exact = FrameChecker(C.CDLL(CLIENT), "nmcompat").match(A, B, 0.8)
+    code = ("import ctypes as C, numpy as np, sys; sys.path.insert(0, %r);"
+            "from niftymatch_b200 import synth; from tests._util import FrameChecker;"
+            "B = synth.descriptors(3000, 2); A = synth.descriptors(3000, 1, planted_from=B);"
+            "m = FrameChecker(C.CDLL(%r), 'nmcompat').match(A, B, 0.8); np.save(sys.argv[1], m)" % (ROOT, CLIENT))
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "m.npy")
+        r = subprocess.run([sys.executable, "-c", code, out], env=dict(os.environ, NM_COMPAT_SKIP_DISTANCE="1"),
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        m_tc = np.load(out)
+    assert (m_exact >= 0).sum() > 300
+    assert np.array_equal(m_tc, m_exact)

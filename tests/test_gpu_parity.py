@@ -363,6 +363,32 @@ def test_1080p_batch_strip_blur_vs_oracle(nm, oracle):
         assert_frame_matches(out[f], ref[f % 2])
 
 
+def test_wide_blur_radius_in_the_batched_path(nm, oracle):
+    """SiftParams members are mutable and the reference accepts kernels up to 91 taps (radius 45): a level sigma
+    above 4 gives a radius above 16, which the tiled TMA blur does not cover -- the batched path then runs the generic
+    two-pass blur through the context's row-pass buffer (nm_sift_create allocates it).  Every level must still be
+    bitwise the oracle's convolution of the level below, and the run must produce keypoints."""
+    w, h = 200, 150
+    img = synth.scene(w, h, synth.SEED_BASE + 77)
+    P = nm.SiftParams(w, h)
+    P.c.sigmas[3] = 4.3            # radius 18
+    P.c.sigmas[4] = 5.2            # radius 21
+    sb = nm.SiftBatch(P, 2, 4096)
+    sb.run(_cu(np.stack([img, img[::-1].copy()])))
+    torch.cuda.synchronize()
+    assert int(sb.results()["counts"][0].item()) > 20
+    for f, im in enumerate((img, img[::-1].copy())):
+        for lvl, sigma in ((4, 4.3), (5, 5.2)):
+            taps, radius = nm.gaussian_taps(sigma)
+            assert radius > 16
+            src = sb.level(f, 0, lvl - 1).cpu().numpy().copy()
+            res, buf = np.zeros_like(src), np.zeros_like(src)
+            oracle.lib.orc_convolve(res.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p), buf.ctypes.data_as(C.c_void_p),
+                                    w, h, taps.ctypes.data_as(C.c_void_p), radius)
+            assert np.array_equal(sb.level(f, 0, lvl).cpu().numpy(), res), (f, lvl)
+    sb.close()
+
+
 def test_sparse_gradient_maps_give_identical_results(nm):
     """Default mode: gradient maps only for the 8 x 32 blocks marked by emit_kernel from the keypoints' orientation
     and descriptor windows.  Keypoints, orientations, descriptors and coordinates must be BITWISE those of the
