@@ -11,8 +11,9 @@ SRCS      := $(CSRC)/nm_pyramid.cu $(CSRC)/nm_extrema.cu $(CSRC)/nm_orient_desc.
 OBJS      := $(patsubst $(CSRC)/%.cu,build/obj/%.o,$(SRCS))
 HDRS      := $(wildcard $(CSRC)/*.cuh) include/nm_b200.h
 LIB       := niftymatch_b200/libnm_b200.so
+MGPU      := niftymatch_b200/libnm_b200_mgpu.so
 
-all: $(LIB) oracle/libnm_oracle.so
+all: $(LIB) $(MGPU) oracle/libnm_oracle.so
 
 build/obj/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build/obj
@@ -20,6 +21,10 @@ build/obj/%.o: $(CSRC)/%.cu $(HDRS)
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
+
+# multi-GPU entries (include/nm_b200_mgpu.h): host orchestration over the C-ABI + NCCL
+$(MGPU): $(CSRC)/nm_mgpu.cu include/nm_b200_mgpu.h $(LIB)
+	$(NVCC) $(NVFLAGS) -shared $(CSRC)/nm_mgpu.cu -o $@ -Lniftymatch_b200 -lnm_b200 -lnccl -Xlinker -rpath -Xlinker '$$ORIGIN'
 
 oracle/libnm_oracle.so: oracle/nm_oracle.c
 	gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC -Wall -o $@ $< -lm
@@ -31,7 +36,7 @@ ref:
 # laid out like the reference's install tree (<prefix>/include/nm, <prefix>/lib/nm).
 CPREFIX   := build/compat/prefix
 CFLAGS_C  := $(ARCH) -O2 -std=c++17 -Xcompiler -fPIC -w -I$(CPREFIX)/include/nm
-compat: $(LIB)
+compat: $(LIB) $(MGPU)
 	@mkdir -p $(CPREFIX)/include/nm $(CPREFIX)/lib/nm build/compat/obj
 	cp compat/include/nm/*.h compat/include/nm/nm_compat.hpp include/nm_b200.h compat/NiftyMatchConfig.cmake $(CPREFIX)/include/nm/
 	$(NVCC) $(CFLAGS_C) -c compat/src/compat_utils.cu -o build/compat/obj/compat_utils.o
@@ -42,6 +47,8 @@ compat: $(LIB)
 	ar rcs $(CPREFIX)/lib/nm/libkernels.a build/compat/obj/compat_kernels.o
 	ar rcs $(CPREFIX)/lib/nm/libsift.a build/compat/obj/compat_sift.o
 	cp $(LIB) $(CPREFIX)/lib/nm/libnm_b200.so
+	cp $(MGPU) $(CPREFIX)/lib/nm/libnm_b200_mgpu.so
+	cp include/nm_b200_mgpu.h $(CPREFIX)/include/nm/
 
 # The client loop that drives the REFERENCE in the parity tests (oracle/ref_driver.cu), compiled
 # unchanged against the drop-in tree: test artefact, entry points nmcompat_*.
@@ -50,6 +57,6 @@ compat-client: compat
 	    -L$(CPREFIX)/lib/nm -lsift -lkernels -lgpuutils -lnm_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/prefix/lib/nm'
 
 clean:
-	rm -rf build $(LIB) oracle/libnm_oracle.so
+	rm -rf build $(LIB) $(MGPU) oracle/libnm_oracle.so
 
 .PHONY: all ref clean compat compat-client

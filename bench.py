@@ -697,9 +697,19 @@ def match_leg(nm, torch, dist, synth, shard_bounds, rank, world, args, barrier, 
     A = torch.from_numpy(Ah).cuda()
     Bs = torch.from_numpy(np.ascontiguousarray(Bh[blo:bhi])).cuda()
 
+    mg = None
+    if world > 1:
+        # the C-ABI multi-GPU entry (include/nm_b200_mgpu.h): its own NCCL communicator, created from a unique id that
+        # rank 0 makes and torch.distributed carries to the other ranks
+        from niftymatch_b200 import mgpu
+        uid_t = torch.tensor(list(mgpu.unique_id() if rank == 0 else bytes(mgpu.ID_BYTES)), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid_t, 0)
+        mg = mgpu.MultiGpu(rank=rank, world=world, uid=bytes(uid_t.cpu().tolist()))
+        io = torch.full((nq,), -1, dtype=torch.int32, device="cuda")
+
     def match_step():
-        if world > 1:
-            return nm.match_sharded(A, Bs, blo, 0.8)
+        if mg is not None:
+            return mg.match([A], [Bs], [blo], 0.8, match_io=[io], streams=[torch.cuda.current_stream()])[0]
         return nm.match(A, Bs, 0.8)
 
     msteps = max(3, min(args.steps, 10))
@@ -729,6 +739,16 @@ def match_leg(nm, torch, dist, synth, shard_bounds, rank, world, args, barrier, 
                                   "(BASELINE.json configs[3]); database rows sharded over the ranks, "
                                   "NCCL all-gather of per-shard top-2 records + merge",
                       "matched": int((mh >= 0).sum()), "index_hash": index_hash}}
+    if mg is not None:
+        mg.set_trace(True)
+        match_step()
+        torch.cuda.synchronize()
+        ph = mg.match_phase_ms()
+        t = torch.tensor([ph["shard_scan"], ph["all_gather"], ph["merge"], ph["total"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["phases_ms_max_over_ranks"] = dict(zip(["shard_scan", "all_gather_incl_wait_for_slowest_rank", "merge", "total"], t.tolist()))
+        out["entry"] = "nm_mgpu_match_f32 (C-ABI, one process per GPU)"
+        mg.close()
     del A, Bs
     # the sizes the reference can address (its arm prints the same list): one GPU
     if world == 1:

@@ -33,6 +33,22 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert n in names, f"{n} bound in Python but not declared in nm_b200.h"
 
 
+def test_multi_gpu_library_exports_its_header():
+    """include/nm_b200_mgpu.h <-> niftymatch_b200/mgpu.py SIGNATURES <-> libnm_b200_mgpu.so (loads without a GPU)."""
+    import niftymatch_b200.mgpu as M
+    src = open(os.path.join(ROOT, "include", "nm_b200_mgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(nm_mgpu_[a-z0-9_]+)\s*\(", src)))
+    assert len(names) >= 10
+    lib = M.load()
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in nm_b200_mgpu.h but not exported"
+        assert n in M.SIGNATURES, f"{n} not bound in mgpu.SIGNATURES"
+    for n in M.SIGNATURES:
+        assert n in names, f"{n} bound in Python but not declared in nm_b200_mgpu.h"
+    assert lib.nm_mgpu_world(None) == -1 and lib.nm_mgpu_destroy(None) == 0
+
+
 def test_struct_layout_matches_header():
     # nm_sift_params: 6 ints, 5 floats, 8 floats, 1 int, 2 floats = 22 * 4 bytes
     assert C.sizeof(L.SiftParamsC) == 22 * 4
