@@ -163,6 +163,23 @@ int nm_match_top2_f32(const float* A, int nA, const float* B, int nB, int index_
  * bit-identical to a single-GPU nm_match_f32 over the concatenated database. */
 int nm_match_merge_top2(const float* recs4, int n_shards, int nA, float ambiguity,
                         int* match_io, nm_stream_t stream);
+/* The same with shard_stride_rows >= nA rows between the record arrays of consecutive shards (recs[s*stride + a]). */
+int nm_match_merge_top2_strided(const float* recs4, int n_shards, long long shard_stride_rows, int nA,
+                                float ambiguity, int* match_io, nm_stream_t stream);
+
+/* compute_sift_matches (gpu/sift/siftfunctions.cu:15-40) for every CONSECUTIVE pair of a SIFT batch -- frame p
+ * against frame p + 1, p = 0 .. n_frames-2 -- in one launch sequence on the tcgen05 engine with no host
+ * synchronisation: every size is read on the device (BASELINE.json configs[4], the mosaicking stream).
+ *   desc        [n_frames][capacity][128] floats, the layout of nm_sift_results (capacity a multiple of 256)
+ *   counts_dev  [n_frames] descriptors per frame (device memory)
+ *   match_out   [n_frames-1][capacity] ints: entry (p, a), a < counts[p], receives the index into frame p + 1 or -1;
+ *               like _match_indexes in the reference, an entry whose second distance is <= 0 keeps its value
+ *               (match.cu:107), and so do the rows >= counts[p]
+ *   rec_out4    optional [n_frames-1][capacity] records (d1, bits(i1), d2, 0) -- exact, as nm_match_top2_f32
+ *   fallback_rows_dev  optional device int, incremented per row whose exactness certificate failed (those rows
+ *               are scanned exactly inside the same kernel) */
+int nm_match_pairs_f32(const float* desc, const int* counts_dev, int n_frames, int capacity, float ambiguity,
+                       int* match_out, float* rec_out4, int* fallback_rows_dev, nm_stream_t stream);
 
 /* Which candidate-search engine nm_match_* uses: 0 = exact fp32 SIMT scan,
  * 1 = tcgen05 contraction + fp32 re-rank (default when the device is sm_100). */
@@ -239,6 +256,13 @@ int nm_transform_blend_bgra(void* canvas, int cw, int ch, unsigned long long fra
 int nm_align_points_f32(const float* src_x, const float* src_y, const float* dst_x, const float* dst_y,
                         float* c_src_x, float* c_src_y, float* c_dst_x, float* c_dst_y,
                         const int* matches, int num_pts, nm_stream_t stream);
+
+/* align_points for every consecutive pair of a SIFT batch (frame p, frame p + 1), sizes read on the device:
+ * x, y: [n_frames][capacity] keypoint coordinates (nm_sift_results), matches: [n_frames-1][capacity] indices of
+ * nm_match_pairs_f32, counts_dev: [n_frames].  Outputs [n_frames-1][capacity]: correspondence (p, i) =
+ * (frame p point i, frame p+1 point matches[p][i]), or (-1,-1,-1,-1) when unmatched or i >= counts[p]. */
+int nm_align_pairs_f32(const float* x, const float* y, const int* matches, const int* counts_dev, int n_frames,
+                       int capacity, float* c_src_x, float* c_src_y, float* c_dst_x, float* c_dst_y, nm_stream_t stream);
 
 /* Estimator kinds. */
 #define NM_RANSAC_TRANSLATION 0   /* 1 correspondence / hypothesis (ransac.cu:467-486) */

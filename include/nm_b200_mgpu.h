@@ -59,6 +59,14 @@ int nm_mgpu_local(const nm_mgpu_ctx* ctx);        /* devices this process drives
 int nm_mgpu_match_f32(nm_mgpu_ctx* ctx, const float* const* A_dev, int nA, const float* const* B_dev, const int* nB,
                       const int* shard_offset, float ambiguity, int* const* match_io_dev, void* const* streams);
 
+/* Two-dimensional sharding: the world is cut into q_groups query groups of D = world / q_groups ranks; rank r scans
+ * query block r / D (rows [q * ceil(nA / Q), ...) of A) against database shard r % D -- the caller passes, on every
+ * rank, the shard of its r % D (the database is cut D ways and held by Q ranks each).  The per-row costs of a scan
+ * (query packing, seed pass, exact re-rank of every row) then shrink with Q as the scan itself shrinks with D; the
+ * exchange stays ONE all-gather (world blocks of ceil(nA / Q) records) followed by one merge per query block.  q_groups
+ * must divide the world; 1 (default) = database sharding only.  The result does not depend on it. */
+int nm_mgpu_set_query_groups(nm_mgpu_ctx* ctx, int q_groups);
+
 /* Device milliseconds of the phases of the LAST nm_mgpu_match_f32 on local device 0 when tracing was enabled
  * (nm_mgpu_set_trace(ctx, 1)): {shard scan (pack, tcgen05 scan, exact re-rank, fallback), all-gather, merge, total}. */
 int nm_mgpu_set_trace(nm_mgpu_ctx* ctx, int enable);

@@ -8,6 +8,6 @@ streams and torch.distributed.
 """
 from ._lib import load, NmError, LIB_PATH, SiftParamsC  # noqa: F401
 from .sift import SiftParams, SiftBatch, gaussian_taps, grayscale, cast_u8, undistort_map  # noqa: F401
-from .match import match, match_top2, merge_top2, set_engine, get_engine, tc_probe  # noqa: F401
+from .match import match, match_top2, merge_top2, match_pairs, set_engine, get_engine, tc_probe  # noqa: F401
 from .ransac import align_points, ransac, ransac_batch, ransac_hypotheses, TRANSLATION, SIMILARITY, HOMOGRAPHY  # noqa: F401
 from .dist import shard_bounds, match_sharded, frame_range, register_stream  # noqa: F401

@@ -239,13 +239,14 @@ __global__ void finish_rows_kernel(const unsigned long long* __restrict__ key1, 
 
 // Merge shard/split-major record arrays and (optionally) apply the ratio rule.
 __global__ void merge_kernel(const float4* __restrict__ recs, int n_shards, int nA, float4* __restrict__ out_rec,
-                             int apply_rule, float ambiguity, int* __restrict__ match_io)
+                             int apply_rule, float ambiguity, int* __restrict__ match_io, long long shard_stride = 0)
 {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= nA) return;
+    if (shard_stride <= 0) shard_stride = nA;
     float m1 = INFINITY, m2 = INFINITY; int mi = 0x7fffffff;
     for (int s = 0; s < n_shards; ++s) {
-        const float4 q = recs[(long long)s * nA + a];
+        const float4 q = recs[s * shard_stride + a];
         int qi = __float_as_int(q.y);
         if (qi < 0) qi = 0x7fffffff;
         rec_merge(m1, mi, m2, q.x, qi, q.z);
@@ -367,9 +368,10 @@ int nm_match_scan_exact_rows(const float* A, int nA, const float* B, int nB, int
     return nm_cuda_err(e);
 }
 
-int nm_match_finalize(const float4* recs, int n_shards, int nA, float ambiguity, int* match_io, cudaStream_t stream)
+int nm_match_finalize(const float4* recs, int n_shards, int nA, float ambiguity, int* match_io, cudaStream_t stream,
+                      long long shard_stride)
 {
-    merge_kernel<<<nm_div_up(nA, 256), 256, 0, stream>>>(recs, n_shards, nA, nullptr, 1, ambiguity, match_io);
+    merge_kernel<<<nm_div_up(nA, 256), 256, 0, stream>>>(recs, n_shards, nA, nullptr, 1, ambiguity, match_io, shard_stride);
     NM_LAUNCH_CHECK();
     return NM_OK;
 }
@@ -414,6 +416,14 @@ extern "C" int nm_match_merge_top2(const float* recs4, int n_shards, int nA, flo
 {
     if (!recs4 || !match_io || n_shards <= 0 || nA <= 0) return NM_ERR_INVALID;
     return nm_match_finalize(reinterpret_cast<const float4*>(recs4), n_shards, nA, ambiguity, match_io, (cudaStream_t)stream);
+}
+
+extern "C" int nm_match_merge_top2_strided(const float* recs4, int n_shards, long long shard_stride_rows, int nA,
+                                           float ambiguity, int* match_io, nm_stream_t stream)
+{
+    if (!recs4 || !match_io || n_shards <= 0 || nA <= 0 || shard_stride_rows < nA) return NM_ERR_INVALID;
+    return nm_match_finalize(reinterpret_cast<const float4*>(recs4), n_shards, nA, ambiguity, match_io, (cudaStream_t)stream,
+                             shard_stride_rows);
 }
 
 extern "C" int nm_match_f32(const float* A, int nA, const float* B, int nB, float ambiguity, int* match_io,

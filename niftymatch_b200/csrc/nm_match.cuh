@@ -22,5 +22,6 @@ int nm_match_scan_tc(const float* A, int nA, const float* B, int nB, int index_o
                      cudaStream_t stream);
 bool nm_match_tc_available();
 
+// shard_stride = rows between the record arrays of consecutive shards (0: nA, i.e. densely packed)
 int nm_match_finalize(const float4* recs, int n_shards, int nA, float ambiguity, int* match_io,
-                      cudaStream_t stream);
+                      cudaStream_t stream, long long shard_stride = 0);

@@ -282,6 +282,11 @@ struct TcScanArgs {
     const int4*    seed_i;
     int            nA, tile_first, tile_end, tiles_per_split;   // split s scans tiles tile_first + s*tps ...
     uint32_t       lbo, sbo;    // descriptor strides in bytes (k-chunk stride, 8-row-group stride)
+    // batched mode (nm_match_pairs_f32; counts != null): blockIdx.z = frame pair z, queries = frame z, database =
+    // frame z + 1; every size is read on the device.  a_pack / b_pack hold `capacity / 128` tiles per frame,
+    // the candidate lists are [pair][2 * gridDim.y][capacity].
+    const int*     counts;
+    int            capacity;
 };
 
 #define TC_INSERT(val, idx)                                                                        \
@@ -344,8 +349,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const TcScanArgs
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rb = blockIdx.x, split = blockIdx.y;
-    const int t0 = p.tile_first + split * p.tiles_per_split;
-    const int nt = min(p.tiles_per_split, p.tile_end - t0);
+    const uint8_t* __restrict__ a_pack = p.a_pack;
+    const uint8_t* __restrict__ b_pack = p.b_pack;
+    int nA = p.nA, tile_first = p.tile_first, tile_end = p.tile_end, tiles_per_split = p.tiles_per_split;
+    size_t list_base = 0;
+    int list_rows = p.nA;
+    if (p.counts != nullptr) {
+        const int pair = blockIdx.z;
+        nA = min(p.counts[pair], p.capacity);
+        const int nB = min(p.counts[pair + 1], p.capacity);
+        if (rb * TC_ROWBLK >= nA || nB <= 0) return;             // the whole CTA: nothing allocated or initialised yet
+        const size_t frame_bytes = (size_t)(p.capacity / TC_TROWS) * TC_TILE_BYTES;
+        a_pack += (size_t)pair * frame_bytes;
+        b_pack += (size_t)(pair + 1) * frame_bytes;
+        tile_first = 0;
+        tile_end = (nB + TC_TROWS - 1) / TC_TROWS;
+        tiles_per_split = (tile_end + (int)gridDim.y - 1) / (int)gridDim.y;
+        list_base = (size_t)pair * (2 * gridDim.y) * p.capacity;
+        list_rows = p.capacity;
+    }
+    const int t0 = tile_first + split * tiles_per_split;
+    const int nt = max(0, min(tiles_per_split, tile_end - t0));
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_NST; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
@@ -366,12 +390,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const TcScanArgs
         // ---- copy warp: A once, then the split's B tiles through the ring ----------------
         if (lane == 0) {
             mbar_expect_tx(a_full, 2 * TC_TILE_BYTES);
-            bulk_g2s(sA, p.a_pack + (size_t)rb * 2 * TC_TILE_BYTES, 2 * TC_TILE_BYTES, a_full);
+            bulk_g2s(sA, a_pack + (size_t)rb * 2 * TC_TILE_BYTES, 2 * TC_TILE_BYTES, a_full);
             for (int i = 0; i < nt; ++i) {
                 const int st = i % TC_NST, use = i / TC_NST;
                 if (use > 0) mbar_wait(empty + st, (use - 1) & 1);
                 mbar_expect_tx(full + st, TC_TILE_BYTES);
-                bulk_g2s(sB + st * TC_TILE_BYTES, p.b_pack + (size_t)(t0 + i) * TC_TILE_BYTES, TC_TILE_BYTES, full + st);
+                bulk_g2s(sB + st * TC_TILE_BYTES, b_pack + (size_t)(t0 + i) * TC_TILE_BYTES, TC_TILE_BYTES, full + st);
             }
         }
         __syncwarp();
@@ -412,7 +436,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const TcScanArgs
         float s0 = -FLT_MAX, s1 = -FLT_MAX, s2 = -FLT_MAX, s3 = -FLT_MAX;
         int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
         const int row = rb * TC_ROWBLK + half * TC_TROWS + q * 32 + lane;
-        if (p.seed_s != nullptr && row < p.nA) {
+        if (p.seed_s != nullptr && row < nA) {
             // start from the row's 4 best of the seed pass (merge of its two lists): the insertion
             // rate of a running top-k falls like k/n, so a few thousand seed columns remove most
             // of the (warp-divergent) insertions of the main scan
@@ -436,9 +460,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const TcScanArgs
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + as * 2 + half);   // this warp is done with the TMEM half-stage
         }
-        if (row < p.nA) {
-            p.cand_s[(size_t)(split * 2 + ch) * p.nA + row] = make_float4(s0, s1, s2, s3);
-            p.cand_i[(size_t)(split * 2 + ch) * p.nA + row] = make_int4(i0, i1, i2, i3);
+        if (row < nA) {
+            p.cand_s[list_base + (size_t)(split * 2 + ch) * list_rows + row] = make_float4(s0, s1, s2, s3);
+            p.cand_i[list_base + (size_t)(split * 2 + ch) * list_rows + row] = make_int4(i0, i1, i2, i3);
         }
     }
     tc_fence_before();
@@ -462,20 +486,21 @@ __device__ __forceinline__ void rec_merge_lex(float& t1, int& i1, float& t2, flo
     (void)j1; (void)u2;
 }
 
-__global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict__ A, int nA, const float* __restrict__ B,
-                                                        int nB, int n_lists, const float4* __restrict__ cand_s,
-                                                        const int4* __restrict__ cand_i, const unsigned* __restrict__ hdr,
-                                                        int index_offset, float4* __restrict__ rec4,
-                                                        int* __restrict__ fb_list, int* __restrict__ fb_count)
+// One warp re-ranks one query row.  a_row: the row's 128 values (global), s_row: 128 floats of shared memory for
+// it; the candidate lists of the row are cand_s / cand_i [list * list_stride]; hdr_max / hdr_b2 / hdr_e2 = bits of
+// max |x|, max |b|^2, max |b^ - s b|^2 (tc_pack_kernel).  Returns whether the record (t1, i1, t2) is certified exact;
+// i1 is a local database row (0x7fffffff: none).
+__device__ __forceinline__ bool tc_rerank_row(const float* __restrict__ a_row, float* __restrict__ s_row,
+                                              const float* __restrict__ B, int nB, int n_lists,
+                                              const float4* __restrict__ cand_s, const int4* __restrict__ cand_i,
+                                              size_t list_stride, unsigned hdr_max, unsigned hdr_b2, unsigned hdr_e2,
+                                              float& t1_out, int& i1_out, float& t2_out)
 {
-    __shared__ __align__(16) float s_a[8][128];
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a = blockIdx.x * 8 + wid;
-    if (a >= nA) return;                                          // warp uniform
-    const float4 av = __ldg(reinterpret_cast<const float4*>(A + (size_t)a * 128) + lane);
-    *reinterpret_cast<float4*>(&s_a[wid][lane * 4]) = av;
+    const int lane = threadIdx.x & 31;
+    const float4 av = __ldg(reinterpret_cast<const float4*>(a_row) + lane);
+    *reinterpret_cast<float4*>(&s_row[lane * 4]) = av;
     // norms of the row: exact-ish |a| and the fp16-rounded |a^| (scaled units), in double
-    const float scale = tc_scale_from_max(hdr[0]);
+    const float scale = tc_scale_from_max(hdr_max);
     double ne2 = 0.0, nh2 = 0.0;
     {
         const float x[4] = {av.x, av.y, av.z, av.w};
@@ -499,8 +524,8 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict_
     int idx = -1;
     float thr = -FLT_MAX;                                         // 4th-best score of the lane's split
     if (sp < n_lists) {
-        const int4 ci = cand_i[(size_t)sp * nA + a];
-        const float4 cs = cand_s[(size_t)sp * nA + a];
+        const int4 ci = cand_i[(size_t)sp * list_stride];
+        const float4 cs = cand_s[(size_t)sp * list_stride];
         idx = k == 0 ? ci.x : k == 1 ? ci.y : k == 2 ? ci.z : ci.w;
         thr = cs.w;
     }
@@ -511,7 +536,7 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict_
     float sc_own = -FLT_MAX;
     int my_rank = 32;
     if (sp < n_lists) {
-        const float4 cs = cand_s[(size_t)sp * nA + a];
+        const float4 cs = cand_s[(size_t)sp * list_stride];
         sc_own = k == 0 ? cs.x : k == 1 ? cs.y : k == 2 ? cs.z : cs.w;
     }
     {
@@ -542,9 +567,9 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict_
     // eta = 2^-17 (|a^|^2 + |b^|^2max) is an EMPIRICAL bound on the tensor-core accumulation error (measured below
     // 2^-20 of that sum, tests/test_gpu_match.py) plus an absolute 2^-16 for the subnormal tail of the fp16 split of
     // -|b^|^2/512 on all-tiny rows
-    const double bmax2 = (double)__uint_as_float(hdr[1]) * sc * sc * (1.0 + 1.953125e-3);
+    const double bmax2 = (double)__uint_as_float(hdr_b2) * sc * sc * (1.0 + 1.953125e-3);
     const double eta = ldexp(nh2 + bmax2, -17) + 1.52587890625e-5;
-    const double delta = (sqrt(ne2) + sqrt((double)__uint_as_float(hdr[2]))) * (1.0 + 1e-5) + 1e-7;
+    const double delta = (sqrt(ne2) + sqrt((double)__uint_as_float(hdr_e2))) * (1.0 + 1e-5) + 1e-7;
     auto lower_bound = [&](float t) -> double {    // on the true distance of every column with score <= t
         if (t <= -FLT_MAX) return (double)INFINITY;
         const double dh = nh2 - 2.0 * (double)t - eta;
@@ -559,7 +584,7 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict_
 #pragma unroll 8
         for (int i = 0; i < 32; ++i) {
             const float4 b4 = __ldg(bp + i);
-            const float4 a4 = *reinterpret_cast<const float4*>(&s_a[wid][i * 4]);
+            const float4 a4 = *reinterpret_cast<const float4*>(&s_row[i * 4]);
             float t;
             t = __fsub_rn(a4.x, b4.x); acc = __fmaf_rn(t, t, acc);
             t = __fsub_rn(a4.y, b4.y); acc = __fmaf_rn(t, t, acc);
@@ -596,12 +621,188 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict_
         certified = n_eval >= nB || (double)t2 < lower_bound(fmaxf(thr, cut));     // warp uniform
         lo = hi;
     }
+    t1_out = t1; i1_out = i1; t2_out = t2;
+    return certified;
+}
+
+__global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict__ A, int nA, const float* __restrict__ B,
+                                                        int nB, int n_lists, const float4* __restrict__ cand_s,
+                                                        const int4* __restrict__ cand_i, const unsigned* __restrict__ hdr,
+                                                        int index_offset, float4* __restrict__ rec4,
+                                                        int* __restrict__ fb_list, int* __restrict__ fb_count)
+{
+    __shared__ __align__(16) float s_a[8][128];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a = blockIdx.x * 8 + wid;
+    if (a >= nA) return;                                          // warp uniform
+    float t1, t2;
+    int i1;
+    const bool certified = tc_rerank_row(A + (size_t)a * 128, s_a[wid], B, nB, n_lists, cand_s + a, cand_i + a, (size_t)nA,
+                                         hdr[0], hdr[1], hdr[2], t1, i1, t2);
     if (lane == 0) {
         if (certified) {
             rec4[a] = make_float4(t1, __int_as_float(i1 == 0x7fffffff ? -1 : i1 + index_offset), t2, 0.f);
         } else {
             const int slot = atomicAdd(fb_count, 1);
             fb_list[slot] = a;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Batched consecutive-frame matching (nm_match_pairs_f32): frame p against frame p + 1 for every p of a SIFT
+// batch, all sizes on the device.  Same three steps as above; every frame is packed ONCE in both operand
+// formats (it is the database of pair p - 1 and the query set of pair p).
+// ---------------------------------------------------------------------------------------
+// hdr[0] = bits of max |x| over all valid rows of the batch (one scale for the whole batch).
+__global__ void __launch_bounds__(256) pairs_absmax_kernel(const float* __restrict__ desc, const int* __restrict__ counts,
+                                                           int capacity, unsigned* __restrict__ hdr)
+{
+    const int f = blockIdx.y;
+    const long long n4 = (long long)min(counts[f], capacity) * 32;
+    const float4* __restrict__ X = reinterpret_cast<const float4*>(desc + (size_t)f * capacity * 128);
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(X + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(hdr, __float_as_uint(m));
+}
+
+// Tile `blockIdx.x` of frame `blockIdx.y` in both formats (see tc_pack_kernel): the 128 x 128 fp16 part is the same,
+// the K = 16 slab holds the constant 256 (query format) or the three-term split of -|b^|^2 / 512 (database format).
+// fhdr[2 f] / fhdr[2 f + 1] = bits of max |b|^2 and max |b^ - s b|^2 over frame f.
+__global__ void __launch_bounds__(256) pairs_pack_kernel(const float* __restrict__ desc, const int* __restrict__ counts,
+                                                         int capacity, uint8_t* __restrict__ outA, uint8_t* __restrict__ outB,
+                                                         const unsigned* __restrict__ hdr, unsigned* __restrict__ fhdr)
+{
+    const int tile = blockIdx.x, f = blockIdx.y, rr = threadIdx.x >> 4, kc = threadIdx.x & 15;
+    const int n = min(counts[f], capacity);
+    if (tile * TC_TROWS >= n) return;
+    const float scale = tc_scale_from_max(hdr[0]);
+    const float* __restrict__ X = desc + (size_t)f * capacity * 128;
+    const size_t toff = ((size_t)f * (capacity / TC_TROWS) + tile) * TC_TILE_BYTES;
+    uint8_t* ta = outA + toff;
+    uint8_t* tb = outB + toff;
+    float bmax2 = 0.f, emax2 = 0.f;
+    for (int pass = 0; pass < TC_TROWS / 16; ++pass) {
+        const int row = pass * 16 + rr;
+        const long long g = (long long)tile * TC_TROWS + row;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (g < n) {
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(X + g * 128 + kc * 8));
+            const float4 q1 = __ldg(reinterpret_cast<const float4*>(X + g * 128 + kc * 8 + 4));
+            v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+        }
+        __half h[8];
+        float nh = 0.f, nx = 0.f, ne = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float xs = v[i] * scale;
+            h[i] = __float2half_rn(xs);
+            const float fv = __half2float(h[i]);
+            const float er = fv - xs;
+            nh = fmaf(fv, fv, nh);
+            nx = fmaf(v[i], v[i], nx);
+            ne = fmaf(er, er, ne);
+        }
+#pragma unroll
+        for (int d = 8; d > 0; d >>= 1) {
+            nh += __shfl_xor_sync(0xffffffffu, nh, d);
+            nx += __shfl_xor_sync(0xffffffffu, nx, d);
+            ne += __shfl_xor_sync(0xffffffffu, ne, d);
+        }
+        *reinterpret_cast<uint4*>(ta + kc * TC_KSTRIDE + row * 16) = *reinterpret_cast<const uint4*>(h);
+        *reinterpret_cast<uint4*>(tb + kc * TC_KSTRIDE + row * 16) = *reinterpret_cast<const uint4*>(h);
+        if (kc < 2) {
+            __half qa[8], qb[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) qa[i] = qb[i] = __float2half_rn(0.f);
+            if (kc == 0) {
+                qa[0] = qa[1] = qa[2] = __float2half_rn(TC_AUG_C);
+                if (g < n) {
+                    const float t = -nh * (0.5f / TC_AUG_C);
+                    const __half h0 = __float2half_rn(t);
+                    const float r1 = t - __half2float(h0);
+                    const __half h1 = __float2half_rn(r1);
+                    const __half h2 = __float2half_rn(r1 - __half2float(h1));
+                    qb[0] = h0; qb[1] = h1; qb[2] = h2;
+                } else {
+                    qb[0] = __float2half_rn(TC_PAD_H0);
+                }
+            }
+            *reinterpret_cast<uint4*>(ta + (16 + kc) * TC_KSTRIDE + row * 16) = *reinterpret_cast<const uint4*>(qa);
+            *reinterpret_cast<uint4*>(tb + (16 + kc) * TC_KSTRIDE + row * 16) = *reinterpret_cast<const uint4*>(qb);
+        }
+        if (g < n) { bmax2 = fmaxf(bmax2, nx); emax2 = fmaxf(emax2, ne); }
+    }
+    if (kc == 0) {
+        if (bmax2 > 0.f) atomicMax(fhdr + 2 * f, __float_as_uint(bmax2));
+        if (emax2 > 0.f) atomicMax(fhdr + 2 * f + 1, __float_as_uint(emax2));
+    }
+}
+
+// One warp per (query row, pair): exact re-rank with the certificate; a row that is not certified is scanned
+// exactly against the whole database frame BY THIS WARP (lanes stride over the rows; a few thousand rows: microseconds,
+// and it happens to a fraction of a per cent of the rows), so the record is exact either way.  Then the reference's
+// ratio rule (match.cu:88-116) writes the match index.
+__global__ void __launch_bounds__(256) pairs_rerank_kernel(const float* __restrict__ desc, const int* __restrict__ counts,
+                                                           int capacity, int n_lists, const float4* __restrict__ cand_s,
+                                                           const int4* __restrict__ cand_i, const unsigned* __restrict__ hdr,
+                                                           const unsigned* __restrict__ fhdr, float ambiguity,
+                                                           int* __restrict__ match_out, float4* __restrict__ rec_out,
+                                                           int* __restrict__ fallback_rows)
+{
+    __shared__ __align__(16) float s_a[8][128];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a = blockIdx.x * 8 + wid, pair = blockIdx.y;
+    const int nA = min(counts[pair], capacity), nB = min(counts[pair + 1], capacity);
+    if (a >= nA || nB <= 0) return;                               // warp uniform
+    const float* __restrict__ A = desc + (size_t)pair * capacity * 128;
+    const float* __restrict__ B = desc + (size_t)(pair + 1) * capacity * 128;
+    const size_t lists = (size_t)pair * n_lists * capacity + a;
+    float t1, t2;
+    int i1;
+    const bool certified = tc_rerank_row(A + (size_t)a * 128, s_a[wid], B, nB, n_lists, cand_s + lists, cand_i + lists,
+                                         (size_t)capacity, hdr[0], fhdr[2 * (pair + 1)], fhdr[2 * (pair + 1) + 1], t1, i1, t2);
+    if (!certified) {
+        // exact scan: match.cu:36-42 per column, ties to the lowest index
+        float d1 = INFINITY, d2 = INFINITY;
+        int j1 = 0x7fffffff;
+        for (int col = lane; col < nB; col += 32) {
+            const float4* __restrict__ bp = reinterpret_cast<const float4*>(B + (size_t)col * 128);
+            float acc = 0.f;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+                const float4 b4 = __ldg(bp + i);
+                const float4 a4 = *reinterpret_cast<const float4*>(&s_a[wid][i * 4]);
+                float t;
+                t = __fsub_rn(a4.x, b4.x); acc = __fmaf_rn(t, t, acc);
+                t = __fsub_rn(a4.y, b4.y); acc = __fmaf_rn(t, t, acc);
+                t = __fsub_rn(a4.z, b4.z); acc = __fmaf_rn(t, t, acc);
+                t = __fsub_rn(a4.w, b4.w); acc = __fmaf_rn(t, t, acc);
+            }
+            if (acc < d1) { d2 = d1; d1 = acc; j1 = col; }
+            else if (acc < d2) d2 = acc;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const float u1 = __shfl_xor_sync(0xffffffffu, d1, d);
+            const int k1 = __shfl_xor_sync(0xffffffffu, j1, d);
+            const float u2 = __shfl_xor_sync(0xffffffffu, d2, d);
+            rec_merge_lex(d1, j1, d2, u1, k1, u2);
+        }
+        t1 = d1; i1 = j1; t2 = d2;
+        if (lane == 0 && fallback_rows) atomicAdd(fallback_rows, 1);
+    }
+    if (lane == 0) {
+        const size_t o = (size_t)pair * capacity + a;
+        if (rec_out) rec_out[o] = make_float4(t1, __int_as_float(i1 == 0x7fffffff ? -1 : i1), t2, 0.f);
+        if (i1 != 0x7fffffff) {
+            const float min2 = (i1 == 0) ? fminf(2139095040.0f, t2) : t2;      // match.cu:91 + scan order
+            if (min2 > 0.f) match_out[o] = (__fdiv_rn(t1, min2) < ambiguity) ? i1 : -1;   // match.cu:107-114
         }
     }
 }
@@ -681,7 +882,9 @@ static int tc_run(const float* A, int nA, const float* B, int nB, int index_offs
     const int n_btiles = nm_div_up(nB, TC_TROWS);
     // seed pass: the first TC_SEED_TILES tiles are scanned first, for all rows; their 4 best per row
     // start every list of the main scan (which then skips those tiles)
-    const int seed_tiles = n_btiles >= 4 * TC_SEED_TILES ? TC_SEED_TILES : 0;
+    // (a sixteenth of the database, at least 4 and at most TC_SEED_TILES tiles: a shard of a sharded database is short,
+    // and the seed launch scans its tiles with one CTA per row block only)
+    const int seed_tiles = n_btiles >= 32 ? (n_btiles / 16 < 4 ? 4 : n_btiles / 16 > TC_SEED_TILES ? TC_SEED_TILES : n_btiles / 16) : 0;
     const int main_tiles = n_btiles - seed_tiles;
     const int n_splits = tc_pick_splits(n_rowblocks, main_tiles, n_sms);
     const int tiles_per_split = nm_div_up(main_tiles, n_splits);
@@ -717,11 +920,11 @@ static int tc_run(const float* A, int nA, const float* B, int nB, int index_offs
         tc_absmax_kernel<<<ga + gb, 256, 0, stream>>>(A, ea4, ga, B, eb4, hdr);
         tc_pack_kernel<<<n_atiles + n_btiles, 256, 0, stream>>>(A, nA, n_atiles, a_pack, B, nB, b_pack, hdr);
         if (seed_tiles > 0) {
-            TcScanArgs ss{a_pack, b_pack, seed_s, seed_i, nullptr, nullptr, nA, 0, seed_tiles, seed_tiles, g_lbo, g_sbo};
+            TcScanArgs ss{a_pack, b_pack, seed_s, seed_i, nullptr, nullptr, nA, 0, seed_tiles, seed_tiles, g_lbo, g_sbo, nullptr, 0};
             tc_scan_kernel<<<dim3(n_rowblocks, 1), TC_THREADS, TC_SMEM_BYTES, stream>>>(ss);
         }
         TcScanArgs sa{a_pack, b_pack, cand_s, cand_i, seed_tiles > 0 ? seed_s : nullptr, seed_tiles > 0 ? seed_i : nullptr,
-                      nA, seed_tiles, n_btiles, tiles_per_split, g_lbo, g_sbo};
+                      nA, seed_tiles, n_btiles, tiles_per_split, g_lbo, g_sbo, nullptr, 0};
         tc_scan_kernel<<<dim3(n_rowblocks, n_splits), TC_THREADS, TC_SMEM_BYTES, stream>>>(sa);
         tc_rerank_kernel<<<nm_div_up(nA, 8), 256, 0, stream>>>(A, nA, B, nB, n_lists, cand_s, cand_i, hdr, index_offset, rec4,
                                                                fb_list, fb_count);
@@ -749,6 +952,54 @@ static int tc_run(const float* A, int nA, const float* B, int nB, int index_offs
     if (rc == NM_OK) rc = nm_match_scan_exact_rows(A, nA, B, nB, 128, index_offset, fb_list, fb_count, rec4, stream);
     cudaFreeAsync(ws, stream);
     return rc;
+}
+
+// compute_sift_matches (gpu/sift/siftfunctions.cu:15-40) for every consecutive pair of a SIFT batch, in one launch
+// sequence with no host synchronisation: BASELINE.json configs[4] (frame t matched to t + 1).
+//   desc       [n_frames][capacity][128] floats (the layout of nm_sift_results)
+//   counts_dev [n_frames] descriptors per frame (device)
+//   match_out  [n_frames - 1][capacity] ints: entry (p, a), a < counts[p], gets the index into frame p + 1 or -1;
+//              entries whose second distance is <= 0 keep their previous value (match.cu:107), rows >= counts[p] too
+//   rec_out    optional [n_frames - 1][capacity] float4 records (d1, bits(i1), d2, 0); fallback_rows_dev optional
+//              device counter of the rows that were scanned exactly
+extern "C" int nm_match_pairs_f32(const float* desc, const int* counts_dev, int n_frames, int capacity, float ambiguity,
+                                  int* match_out, float* rec_out4, int* fallback_rows_dev, nm_stream_t stream_)
+{
+    if (!desc || !counts_dev || !match_out || n_frames < 2 || capacity <= 0) return NM_ERR_INVALID;
+    if (capacity % TC_ROWBLK) return NM_ERR_INVALID;             // whole 256-row blocks per frame
+    if (reinterpret_cast<uintptr_t>(desc) & 15) return NM_ERR_INVALID;
+    if (!nm_match_tc_available()) return NM_ERR_UNSUPPORTED;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int n_pairs = n_frames - 1;
+    const int tiles = capacity / TC_TROWS, rowblocks = capacity / TC_ROWBLK;
+    // splits: a frame pair is small (a few thousand rows each way), so the database is cut in up to 4 pieces to get
+    // enough CTAs per pair and 8 candidate lists (32 candidates) per row for the certificate
+    const int n_splits = 4, n_lists = 2 * n_splits;
+    const size_t off_f = 256;                                                                   // per-frame headers
+    const size_t off_cs = (off_f + sizeof(unsigned) * 2 * (size_t)n_frames + 255) & ~size_t(255);
+    const size_t off_ci = off_cs + sizeof(float4) * (size_t)n_pairs * n_lists * capacity;
+    const size_t off_ap = (off_ci + sizeof(int4) * (size_t)n_pairs * n_lists * capacity + 255) & ~size_t(255);
+    const size_t off_bp = off_ap + (size_t)n_frames * tiles * TC_TILE_BYTES;
+    const size_t total = off_bp + (size_t)n_frames * tiles * TC_TILE_BYTES;
+    uint8_t* ws = nullptr;
+    NM_CUDA_TRY(nm_ws_alloc(&ws, total, stream));
+    unsigned* hdr = reinterpret_cast<unsigned*>(ws);
+    unsigned* fhdr = reinterpret_cast<unsigned*>(ws + off_f);
+    float4* cand_s = reinterpret_cast<float4*>(ws + off_cs);
+    int4* cand_i = reinterpret_cast<int4*>(ws + off_ci);
+    cudaError_t e = cudaMemsetAsync(ws, 0, off_cs, stream);
+    if (e == cudaSuccess) {
+        pairs_absmax_kernel<<<dim3(32, n_frames), 256, 0, stream>>>(desc, counts_dev, capacity, hdr);
+        pairs_pack_kernel<<<dim3(tiles, n_frames), 256, 0, stream>>>(desc, counts_dev, capacity, ws + off_ap, ws + off_bp, hdr, fhdr);
+        TcScanArgs sa{ws + off_ap, ws + off_bp, cand_s, cand_i, nullptr, nullptr, 0, 0, 0, 0, g_lbo, g_sbo, counts_dev, capacity};
+        tc_scan_kernel<<<dim3(rowblocks, n_splits, n_pairs), TC_THREADS, TC_SMEM_BYTES, stream>>>(sa);
+        pairs_rerank_kernel<<<dim3(capacity / 8, n_pairs), 256, 0, stream>>>(desc, counts_dev, capacity, n_lists, cand_s, cand_i, hdr,
+                                                                            fhdr, ambiguity, match_out,
+                                                                            reinterpret_cast<float4*>(rec_out4), fallback_rows_dev);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(ws, stream);
+    return nm_cuda_err(e);
 }
 
 int nm_match_scan_tc(const float* A, int nA, const float* B, int nB, int index_offset, float4* rec4, cudaStream_t stream)

@@ -33,6 +33,7 @@ struct nm_mgpu_ctx {
     // matcher workspace per local device, grown on demand: this rank's records and everybody's
     std::vector<float*> rec, allrec;
     std::vector<size_t> rec_cap;
+    int q_groups = 1;                    // query groups Q: world = Q x D, rank r scans query block r / D against shard r % D
     // tracing (local device 0)
     int trace = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -159,49 +160,71 @@ extern "C" int nm_mgpu_match_phase_ms(nm_mgpu_ctx* c, float* ms4)
     return NM_OK;
 }
 
+extern "C" int nm_mgpu_set_query_groups(nm_mgpu_ctx* c, int q_groups)
+{
+    if (!c || q_groups <= 0 || c->world % q_groups) return NM_ERR_INVALID;
+    c->q_groups = q_groups;
+    return NM_OK;
+}
+
 extern "C" int nm_mgpu_match_f32(nm_mgpu_ctx* c, const float* const* A_dev, int nA, const float* const* B_dev, const int* nB,
                                  const int* shard_offset, float ambiguity, int* const* match_io_dev, void* const* streams)
 {
     if (!c || !A_dev || !B_dev || !nB || !shard_offset || !match_io_dev || nA <= 0) return NM_ERR_INVALID;
     DeviceGuard guard;
-    const size_t rec_floats = (size_t)nA * 4;
+    // rank r = (query group r / D, database shard r % D): the rank scans ITS block of the queries against its shard,
+    // so the per-row costs of a scan (query packing, seed pass, exact re-rank) shrink with Q as the scan itself does with D
+    const int Q = c->q_groups, D = c->world / Q;
+    const int nAq = (nA + Q - 1) / Q;                            // rows per query block (the last one may be shorter)
+    const size_t blk_floats = (size_t)nAq * 4;
     // workspaces (kept across calls: no allocation on the hot path once they are large enough)
     for (int d = 0; d < c->n_local; ++d) {
         if (!A_dev[d] || !match_io_dev[d] || nB[d] < 0 || (nB[d] > 0 && !B_dev[d])) return NM_ERR_INVALID;
-        if (c->rec_cap[d] < rec_floats) {
+        if (c->rec_cap[d] < blk_floats) {
             MG_CUDA(cudaSetDevice(c->dev[d]));
             if (c->rec[d]) cudaFree(c->rec[d]);
             if (c->allrec[d]) cudaFree(c->allrec[d]);
             c->rec[d] = c->allrec[d] = nullptr; c->rec_cap[d] = 0;
-            MG_CUDA(cudaMalloc(&c->rec[d], rec_floats * sizeof(float)));
-            MG_CUDA(cudaMalloc(&c->allrec[d], rec_floats * sizeof(float) * c->world));
-            c->rec_cap[d] = rec_floats;
+            MG_CUDA(cudaMalloc(&c->rec[d], blk_floats * sizeof(float)));
+            MG_CUDA(cudaMalloc(&c->allrec[d], blk_floats * sizeof(float) * c->world));
+            c->rec_cap[d] = blk_floats;
         }
     }
     auto st = [&](int d) { return streams ? static_cast<cudaStream_t>(streams[d]) : c->stream[d]; };
-    // 1. every device scans its shard: records (d1, bits(i1 + offset), d2, 0) per query
+    // 1. every device scans its (query block, shard): records (d1, bits(i1 + offset), d2, 0) per query of the block
     for (int d = 0; d < c->n_local; ++d) {
         MG_CUDA(cudaSetDevice(c->dev[d]));
         if (d == 0 && c->trace) MG_CUDA(cudaEventRecord(c->ev[0], st(d)));
-        const int rc = nm_match_top2_f32(A_dev[d], nA, B_dev[d], nB[d], shard_offset[d], c->rec[d], st(d));
-        if (rc != NM_OK) return rc;
+        const int q = (c->rank0 + d) / D;
+        const int a0 = q * nAq, na = nA - a0 < nAq ? nA - a0 : nAq;
+        if (na < nAq) MG_CUDA(cudaMemsetAsync(c->rec[d], 0, blk_floats * sizeof(float), st(d)));   // padding rows of the last block
+        if (na > 0) {
+            const int rc = nm_match_top2_f32(A_dev[d] + (size_t)a0 * 128, na, B_dev[d], nB[d], shard_offset[d], c->rec[d], st(d));
+            if (rc != NM_OK) return rc;
+        }
         if (d == 0 && c->trace) MG_CUDA(cudaEventRecord(c->ev[1], st(d)));
     }
-    // 2. one all-gather of the 16-byte records (rank-major = shard-major, the order the merge rule needs)
+    // 2. one all-gather of the 16-byte records: rank-major = (query block, shard)-major, the order the merge needs
     if (c->world > 1) {
         MG_NCCL(ncclGroupStart());
         for (int d = 0; d < c->n_local; ++d) {
-            const ncclResult_t r = ncclAllGather(c->rec[d], c->allrec[d], rec_floats, ncclFloat, c->comm[d], st(d));
+            const ncclResult_t r = ncclAllGather(c->rec[d], c->allrec[d], blk_floats, ncclFloat, c->comm[d], st(d));
             if (r != ncclSuccess) { ncclGroupEnd(); return nccl_err(r); }
         }
         MG_NCCL(ncclGroupEnd());
     }
-    // 3. merge on every device + the reference's ratio rule (match.cu:88-116)
+    // 3. per query block: merge its D shard records on every device + the reference's ratio rule (match.cu:88-116)
     for (int d = 0; d < c->n_local; ++d) {
         MG_CUDA(cudaSetDevice(c->dev[d]));
         if (d == 0 && c->trace) MG_CUDA(cudaEventRecord(c->ev[2], st(d)));
-        const int rc = nm_match_merge_top2(c->world > 1 ? c->allrec[d] : c->rec[d], c->world, nA, ambiguity, match_io_dev[d], st(d));
-        if (rc != NM_OK) return rc;
+        for (int q = 0; q < Q; ++q) {
+            const int a0 = q * nAq, na = nA - a0 < nAq ? nA - a0 : nAq;
+            if (na <= 0) break;
+            const float* recs = c->world > 1 ? c->allrec[d] + (size_t)q * D * blk_floats : c->rec[d];
+            // shard s of the block sits nAq rows after shard s - 1 (the last query block may hold fewer than nAq rows)
+            const int rc = nm_match_merge_top2_strided(recs, D, nAq, na, ambiguity, match_io_dev[d] + a0, st(d));
+            if (rc != NM_OK) return rc;
+        }
         if (d == 0 && c->trace) MG_CUDA(cudaEventRecord(c->ev[3], st(d)));
     }
     if (!streams)

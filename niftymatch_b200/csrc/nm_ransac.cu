@@ -236,6 +236,23 @@ __global__ void align_kernel(const float* __restrict__ src_x, const float* __res
     c_dst_y[i] = ok ? dst_y[m] : -1.f;
 }
 
+// align_points for the consecutive pairs of a SIFT batch: pair p = (frame p, frame p + 1), sizes on the device
+__global__ void align_pairs_kernel(const float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ matches,
+                                   const int* __restrict__ counts, int capacity, float* __restrict__ c_src_x,
+                                   float* __restrict__ c_src_y, float* __restrict__ c_dst_x, float* __restrict__ c_dst_y)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (i >= capacity) return;
+    const long long o = (long long)p * capacity + i;
+    const int nA = min(counts[p], capacity), nB = min(counts[p + 1], capacity);
+    const int m = i < nA ? matches[o] : -1;
+    const bool ok = m >= 0 && m < nB;
+    c_src_x[o] = ok ? x[o] : -1.f;
+    c_src_y[o] = ok ? y[o] : -1.f;
+    c_dst_x[o] = ok ? x[o + capacity - i + m] : -1.f;
+    c_dst_y[o] = ok ? y[o + capacity - i + m] : -1.f;
+}
+
 // ---- batched estimator: every kernel indexes a PAIR of frames by a grid dimension ------------------------
 // Pair p reads its correspondences at (sx, sy, dx, dy) + p * stride, n(p) = counts ? min(counts[p], max_pts) :
 // max_pts of them; per-pair workspace slices: valid[p * max_pts], state[p * 4], rand[p * draws], H[p * it * 9],
@@ -491,6 +508,18 @@ extern "C" int nm_align_points_f32(const float* src_x, const float* src_y, const
     if (!src_x || !src_y || !dst_x || !dst_y || !c_src_x || !c_src_y || !c_dst_x || !c_dst_y || !matches) return NM_ERR_INVALID;
     align_kernel<<<nm_div_up(num_pts, 256), 256, 0, (cudaStream_t)stream>>>(src_x, src_y, dst_x, dst_y, c_src_x, c_src_y,
                                                                           c_dst_x, c_dst_y, matches, num_pts);
+    NM_LAUNCH_CHECK();
+    return NM_OK;
+}
+
+extern "C" int nm_align_pairs_f32(const float* x, const float* y, const int* matches, const int* counts_dev, int n_frames,
+                                  int capacity, float* c_src_x, float* c_src_y, float* c_dst_x, float* c_dst_y,
+                                  nm_stream_t stream)
+{
+    if (!x || !y || !matches || !counts_dev || !c_src_x || !c_src_y || !c_dst_x || !c_dst_y || n_frames < 2 || capacity <= 0)
+        return NM_ERR_INVALID;
+    align_pairs_kernel<<<dim3(nm_div_up(capacity, 256), n_frames - 1), 256, 0, (cudaStream_t)stream>>>(
+        x, y, matches, counts_dev, capacity, c_src_x, c_src_y, c_dst_x, c_dst_y);
     NM_LAUNCH_CHECK();
     return NM_OK;
 }

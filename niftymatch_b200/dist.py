@@ -115,3 +115,58 @@ def register_stream(sift_batch, frames, kind: int = 2, ambiguity: float = 0.8, i
     # one seed per PAIR INDEX of the whole stream, so a sharded run reproduces the single-rank run
     H, st = ransac_batch(kind, *c, counts, inlier_threshold, iterations, seed + lo)
     return pairs, H, st
+
+
+class StreamRegistrar:
+    """BASELINE.json configs[4] as ONE device-side launch sequence per chunk of frames: batched SIFT (nm_sift_run),
+    every frame matched to its successor on the tcgen05 engine (nm_match_pairs_f32), correspondences aligned
+    (nm_align_pairs_f32) and all pairs registered by one batched RANSAC (nm_ransac_batch_f32).  Keypoint counts never
+    leave the device and nothing synchronises; consecutive chunks share one frame (recomputed), so no state is carried
+    between chunks or between GPUs.  Pair t -> t + 1 draws with seed + t: the result does not depend on the chunking or
+    on how the stream is sharded over ranks (frame_range(..., overlap=1))."""
+
+    def __init__(self, sift_batch, chunk=None, kind: int = 2, ambiguity: float = 0.8, inlier_threshold: float = 4.0,
+                 iterations: int = 1024, seed: int = 0):
+        import torch
+        self.sb = sift_batch
+        self.chunk = min(chunk or sift_batch.max_batch, sift_batch.max_batch)
+        assert self.chunk >= 2 and sift_batch.capacity % 256 == 0
+        self.kind, self.ambiguity, self.thr, self.iters, self.seed = kind, ambiguity, inlier_threshold, iterations, seed
+        cap, n = sift_batch.capacity, self.chunk - 1
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.match = torch.empty((n, cap), dtype=torch.int32, device=dev)
+        self.corr = [torch.empty((n, cap), dtype=torch.float32, device=dev) for _ in range(4)]
+
+    def run(self, frames_of, lo: int, hi: int):
+        """frames_of(t0, t1) -> cuda float32 (t1 - t0, h, w) = frames [t0, t1) of the stream.  Registers every pair
+        (t, t + 1) with lo <= t < hi - 1.  Returns (homographies (hi - lo - 1, 9), status (hi - lo - 1, 3)) on the device."""
+        import ctypes as C
+        import torch
+        from . import _lib
+        from ._lib import check
+        from .sift import _stream_ptr
+        lib = _lib.load()
+        sb, cap = self.sb, self.sb.capacity
+        n_pairs = max(hi - lo - 1, 0)
+        H = torch.zeros((max(n_pairs, 1), 9), dtype=torch.float32, device=self.match.device)
+        st = torch.zeros((max(n_pairs, 1), 3), dtype=torch.int32, device=self.match.device)
+        if n_pairs == 0:
+            return H[:0], st[:0]
+        r = sb.results()
+        p = lambda t: C.c_void_p(t.data_ptr())
+        c0 = lo
+        while c0 < hi - 1:
+            c1 = min(hi, c0 + self.chunk)
+            n = c1 - c0
+            sb.run(frames_of(c0, c1))
+            self.match[: n - 1].fill_(-1)
+            check(lib.nm_match_pairs_f32(p(r["desc"]), p(r["counts"]), n, cap, self.ambiguity, p(self.match), None, None,
+                                         _stream_ptr()), "nm_match_pairs_f32")
+            check(lib.nm_align_pairs_f32(p(r["x"]), p(r["y"]), p(self.match), p(r["counts"]), n, cap, *[p(c) for c in self.corr],
+                                         _stream_ptr()), "nm_align_pairs_f32")
+            k = c0 - lo
+            check(lib.nm_ransac_batch_f32(self.kind, *[p(c) for c in self.corr], cap, p(r["counts"]), cap, n - 1, self.thr,
+                                          self.iters, (self.seed + c0) & 0xFFFFFFFFFFFFFFFF, p(H[k:]), p(st[k:]), _stream_ptr()),
+                  "nm_ransac_batch_f32")
+            c0 = c1 - 1
+        return H[:n_pairs], st[:n_pairs]

@@ -77,6 +77,25 @@ def merge_top2(recs, ambiguity: float = 0.8, match_io=None):
     return match_io
 
 
+def match_pairs(desc, counts, ambiguity: float = 0.8, match_out=None, want_records: bool = False):
+    """nm_match_pairs_f32: frame p matched to frame p + 1 for every p.  desc: (n_frames, capacity, 128) cuda float32
+    (the layout of SiftBatch.results()["desc"]), counts: (n_frames,) cuda int32.  Returns match indices
+    (n_frames - 1, capacity) int32 (-1 where unmatched / beyond the frame's count), optionally the exact records and
+    the device counter of rows that needed the exact fallback scan.  No host synchronisation."""
+    import torch
+    assert desc.is_cuda and desc.dtype == torch.float32 and desc.is_contiguous() and desc.dim() == 3 and desc.shape[2] == 128
+    n_frames, cap = desc.shape[0], desc.shape[1]
+    _i32(counts, "counts", n_frames)
+    if match_out is None:
+        match_out = torch.full((n_frames - 1, cap), -1, dtype=torch.int32, device=desc.device)
+    rec = torch.zeros((n_frames - 1, cap, 4), dtype=torch.float32, device=desc.device) if want_records else None
+    fb = torch.zeros(1, dtype=torch.int32, device=desc.device) if want_records else None
+    check(_lib.load().nm_match_pairs_f32(C.c_void_p(desc.data_ptr()), C.c_void_p(counts.data_ptr()), n_frames, cap, ambiguity,
+                                         C.c_void_p(match_out.data_ptr()), C.c_void_p(rec.data_ptr()) if rec is not None else None,
+                                         C.c_void_p(fb.data_ptr()) if fb is not None else None, _stream_ptr()), "nm_match_pairs_f32")
+    return (match_out, rec, fb) if want_records else match_out
+
+
 def tc_probe(A, B, want_candidates: bool = False):
     """Diagnostics of the tensor-core engine (nm_match_tc_probe): exact records (nA,4), the number
     of rows whose exactness certificate failed (re-scanned by the exact engine), and optionally

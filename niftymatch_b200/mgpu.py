@@ -21,6 +21,7 @@ SIGNATURES = {
     "nm_mgpu_world": (_i, [_vp]),
     "nm_mgpu_local": (_i, [_vp]),
     "nm_mgpu_match_f32": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp]),
+    "nm_mgpu_set_query_groups": (_i, [_vp, _i]),
     "nm_mgpu_set_trace": (_i, [_vp, _i]),
     "nm_mgpu_match_phase_ms": (_i, [_vp, _vp]),
     "nm_mgpu_sift_create": (_i, [_vp, C.POINTER(SiftParamsC), _i, _i]),
@@ -116,6 +117,11 @@ class MultiGpu:
                                          _ptr_array([b.data_ptr() if b.shape[0] else 0 for b in B]), nB, off, ambiguity,
                                          _ptr_array([m.data_ptr() for m in match_io]), st), "nm_mgpu_match_f32")
         return match_io
+
+    def set_query_groups(self, q_groups: int):
+        """world = q_groups x D: rank r scans query block r // D against database shard r % D."""
+        check(self.lib.nm_mgpu_set_query_groups(self._ctx, q_groups), "nm_mgpu_set_query_groups")
+        self.q_groups = q_groups
 
     def set_trace(self, on: bool = True):
         check(self.lib.nm_mgpu_set_trace(self._ctx, int(on)), "nm_mgpu_set_trace")

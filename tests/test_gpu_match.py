@@ -280,3 +280,48 @@ def test_unaligned_descriptor_pointers(nm, oracle):
     m = nm.match(At, Bt, 0.8).cpu().numpy()
     nm.set_engine(-1)
     assert np.array_equal(m, oracle.match(A, B, 0.8))
+
+
+def test_batched_pair_matching_equals_per_pair_calls(nm):
+    """nm_match_pairs_f32 (frame p -> p + 1 for a whole batch, all sizes on the device, tcgen05 engine) against one
+    nm_match_f32 call (exact engine) per pair: match indices AND the (d1, i1, d2) records must be bitwise equal.
+    Frames: planted true matches, counts that are not multiples of the 128-row tiles, a one-descriptor frame, an empty
+    frame in the middle (both of its pairs stay unmatched), stale rows beyond the counts, a duplicated database row
+    (min2 == 0: the entry keeps its previous value, match.cu:107), a frame matched against a copy of itself."""
+    cap = 2048
+    counts = [1500, 1337, 1, 0, 900, 2048, 700, 700]
+    n = len(counts)
+    rng = np.random.default_rng(11)
+    desc = (rng.random((n, cap, 128)) * 300).astype(np.float32)          # rows beyond the counts: stale values, must be ignored
+    prev = None
+    for f, c in enumerate(counts):
+        if c == 0:
+            prev = None
+            continue
+        d = synth.descriptors(c, 100 + f, planted_from=prev) if prev is not None and len(prev) else synth.descriptors(c, 100 + f)
+        desc[f, :c] = d
+        prev = d
+    desc[7, :700] = desc[6, :700]                                        # identical frames: d1 == 0 everywhere
+    desc[5, 11] = desc[5, 10]; desc[4, 3] = desc[5, 10]                  # query 3 of frame 4: two database rows at distance 0
+    dd, cc = _cu(desc), torch.tensor(counts, dtype=torch.int32, device="cuda")
+    init = torch.full((n - 1, cap), 55, dtype=torch.int32, device="cuda")
+    m, rec, fb = nm.match_pairs(dd, cc, 0.8, match_out=init.clone(), want_records=True)
+    torch.cuda.synchronize()
+    m, rec = m.cpu().numpy(), rec.cpu().numpy()
+    nm.set_engine(0)
+    try:
+        for p in range(n - 1):
+            nA, nB = counts[p], counts[p + 1]
+            assert (m[p, nA:] == 55).all(), p                            # rows beyond the count untouched
+            if nA == 0 or nB == 0:
+                assert (m[p] == 55).all(), p
+                continue
+            ref = nm.match(dd[p, :nA], dd[p + 1, :nB], 0.8, match_io=init[p, :nA].clone()).cpu().numpy()
+            r2 = nm.match_top2(dd[p, :nA], dd[p + 1, :nB]).cpu().numpy()
+            assert np.array_equal(m[p, :nA], ref), (p, np.nonzero(m[p, :nA] != ref)[0][:10])
+            assert np.array_equal(rec[p, :nA].view(np.uint32)[:, :3], r2.view(np.uint32)[:, :3]), p
+    finally:
+        nm.set_engine(-1)
+    assert m[4, 3] == 55                                                 # min2 == 0: left as it was
+    assert (m[0, :1500] >= 0).sum() > 150 and (m[6, :700] == 55).sum() == 0
+    assert int(fb.item()) < 200                                          # the exact fallback is the exception

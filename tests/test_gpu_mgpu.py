@@ -128,3 +128,21 @@ def test_sharded_match_one_process_per_gpu(two_gpus):
         for r in range(2):
             assert np.array_equal(np.load(os.path.join(td, f"m{r}.npy")), single), r
     assert (single >= 0).sum() > 400
+
+
+@pytest.mark.parametrize("nq", [4000, 4001])
+def test_query_groups_two_devices(two_gpus, nq):
+    """Two-dimensional sharding, Q = 2 query groups x D = 1 database shards on two devices: every device scans its
+    half of the queries against the whole database; one all-gather, one merge per query block (the last block is one
+    row short for an odd query count).  Same indices as the single-GPU call."""
+    nm, mgpu = two_gpus
+    A, B = _sets(nq, 6000)
+    torch.cuda.set_device(0)
+    single = nm.match(torch.from_numpy(A).cuda(0), torch.from_numpy(B).cuda(0), 0.8).cpu().numpy()
+    mg = mgpu.MultiGpu(n_dev=2)
+    mg.set_query_groups(2)
+    out = mg.match([torch.from_numpy(A).cuda(d) for d in range(2)], [torch.from_numpy(B).cuda(d) for d in range(2)], [0, 0], 0.8)
+    for d in range(2):
+        assert np.array_equal(out[d].cpu().numpy(), single), d
+    mg.close()
+    torch.cuda.set_device(0)

@@ -263,6 +263,43 @@ def test_register_stream_recovers_the_motion_and_shards(nm):
     sb.close()
 
 
+def test_stream_registrar_device_pipeline_equals_the_per_pair_path(nm):
+    """StreamRegistrar = configs[4] without host round trips: batched SIFT, nm_match_pairs_f32 (tcgen05 engine, device
+    counts), nm_align_pairs_f32 and one batched RANSAC per chunk.  Its homographies and inlier counts must be BITWISE
+    those of register_stream (one nm_match_f32 / align_points call per pair with host-side counts), whatever the chunk
+    size, and a two-rank sharding with one overlap frame must reproduce the single-rank run."""
+    from niftymatch_b200 import synth
+    from niftymatch_b200.dist import StreamRegistrar, frame_range
+    w, h = 512, 384
+    base = synth.scene(w + 64, h + 64, synth.SEED_BASE + 9)
+    offs = [(8, 8), (12, 10), (18, 9), (20, 16), (27, 20), (30, 26), (38, 30), (40, 35), (44, 41)]
+    frames = np.stack([base[oy: oy + h, ox: ox + w] for ox, oy in offs])
+    n = len(offs)
+    P = nm.SiftParams(w, h)
+    P._peak_threshold = 2.0
+    sb = nm.SiftBatch(P, 5, 8192)
+    fr = _cu(frames)
+    _, Href, sref = nm.register_stream(sb, fr, kind=nm.HOMOGRAPHY, inlier_threshold=1.0, iterations=512, seed=5, chunk=4)
+    Href, sref = Href.cpu().numpy(), sref.cpu().numpy()
+    assert (sref[:, 0] == 1).all() and sref[:, 1].min() > 30
+    frames_of = lambda t0, t1: fr[t0:t1].contiguous()
+    for chunk in (5, 3, 2):
+        reg = StreamRegistrar(sb, chunk=chunk, kind=nm.HOMOGRAPHY, inlier_threshold=1.0, iterations=512, seed=5)
+        H, st = reg.run(frames_of, 0, n)
+        assert np.array_equal(H.cpu().numpy(), Href), chunk
+        assert np.array_equal(st.cpu().numpy(), sref), chunk
+    reg = StreamRegistrar(sb, chunk=4, kind=nm.HOMOGRAPHY, inlier_threshold=1.0, iterations=512, seed=5)
+    for world in (2, 3):
+        got = []
+        for rank in range(world):
+            lo, hi = frame_range(n, world, rank, overlap=1)
+            H, st = reg.run(frames_of, lo, hi)
+            got.append((H.cpu().numpy(), st.cpu().numpy()))
+        assert np.array_equal(np.concatenate([g[0] for g in got]), Href), world
+        assert np.array_equal(np.concatenate([g[1] for g in got]), sref), world
+    sb.close()
+
+
 def test_dropin_ransac_header(nm):
     """ransac.h of the drop-in layer (compat/include/nm/ransac.h) through the same client code that drives the
     reference (oracle/ref_ransac_driver.cu built with -DNM_COMPAT_BUILD)."""
