@@ -323,5 +323,7 @@ def test_batched_pair_matching_equals_per_pair_calls(nm):
     finally:
         nm.set_engine(-1)
     assert m[4, 3] == 55                                                 # min2 == 0: left as it was
-    assert (m[0, :1500] >= 0).sum() > 150 and (m[6, :700] == 55).sum() == 0
+    assert (m[0, :1500] >= 0).sum() > 150
+    self_match = m[6, :700]                                              # identical frames: every row finds itself,
+    assert (self_match == np.arange(700))[self_match != 55].all() and (self_match == 55).sum() <= 4   # bar duplicated rows (min2 == 0)
     assert int(fb.item()) < 200                                          # the exact fallback is the exception
