@@ -14,8 +14,16 @@
 // 16x16 chunks of the descriptor window, no normalisation (SURVEY.md Q5,Q6,Q10,Q12,Q16).
 #include "nm_sift_internal.cuh"
 #include "nm_kpgeom.cuh"
+#include <cstdlib>
 
 namespace {
+
+__device__ __forceinline__ float exp2f_approx(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 constexpr int OR_WARPS = 8;      // warps per block, orientation
 constexpr int NBINS = 36;
@@ -53,6 +61,9 @@ __global__ void __launch_bounds__(OR_WARPS * 32) orient_kernel(const NmOctaveTab
         const int nx = xmax - xmin + 1, ny = ymax - ymin + 1;
         const int total = (nx > 0 && ny > 0) ? nx * ny : 0;
         const float den = __fmul_rn(sigma_w, __fadd_rn(sigma_w, sigma_w));  // 2*sigma_w*sigma_w
+        // :56 exp(r2 / den) = 2^(r2 * log2(e) / den): one division per keypoint, ex2.approx per sample (2 ulp; the
+        // orientation tolerance is 1e-3 rad, the measured deviation from the exact form stays below 1e-5)
+        const float k_exp = __fdiv_rn(1.4426950408889634f, den);
         // :55 compares (double)r2 < W*W + 0.6; W*W + 0.6 is not an fp32 number, so for fp32 r2 that is
         // r2 < (the smallest fp32 above it)
         const float lim_f = __double2float_ru(__dadd_rn((double)(W * W), 0.6));
@@ -87,7 +98,7 @@ __global__ void __launch_bounds__(OR_WARPS * 32) orient_kernel(const NmOctaveTab
                 const float dy = __fsub_rn((float)(ccy + g.yi), g.y);
                 const float r2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));         // :54
                 if (valid && r2 < lim_f) {                            // :55
-                    const float wgt = expf(__fdiv_rn(r2, den));       // :56 (positive exponent)
+                    const float wgt = exp2f_approx(__fmul_rn(r2, k_exp));   // :56 (positive exponent)
                     // :57  bin = floor((float)((double)(36 theta) / 2 pi)).  The fp32 product v * (1 / 2 pi) is within
                     // 7e-6 of that quotient (v <= 227), so its floor is the reference's unless it lies within 1e-5
                     // of an integer; only then (2e-5 of the samples) the double division decides.
@@ -96,9 +107,8 @@ __global__ void __launch_bounds__(OR_WARPS * 32) orient_kernel(const NmOctaveTab
                     float qfl = floorf(qf);
                     const float fr = __fsub_rn(qf, qfl);
                     if (!(fr > 1e-5f && fr < 0.99999f)) qfl = floorf((float)__ddiv_rn((double)v36, NM_TWO_PI_D));
-                    int bin = (int)qfl;
-                    bin %= NBINS;
-                    if (bin < 0) bin += NBINS;
+                    int bin = (int)qfl;                               // theta in [0, 2 pi]: 0 .. 36
+                    if ((unsigned)bin >= (unsigned)NBINS) { bin %= NBINS; if (bin < 0) bin += NBINS; }   // :58 bin % NBINS
                     float* p = priv + bin * OR_HP + lane;             // bank == lane: conflict free
                     *p = __fadd_rn(*p, __fmul_rn(gv.x, wgt));         // :58
                 }
@@ -345,6 +355,155 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
     if (lane == 0) { xo[kidx] = kp.x; yo[kidx] = kp.y; }              // :76
 }
 
+// ------------------------------- descriptor, fp32 mode, restructured -----------------------------------
+// Same formulas as describe_kernel<false>; what changes is the instruction count per sample (the kernel is
+// issue bound: ncu counted 135 warp instructions per 32 samples, 5 350 per keypoint):
+//   * the window is walked chunk by chunk and row by row (lane = column (0..15) + 16 * (row & 1), eight row steps
+//     per 16 x 16 chunk), so sample positions, validity and gradient addresses are increments, not a decode of a
+//     flat sample index; the eight gradient loads of the NEXT chunk are issued before the current chunk's
+//     arithmetic;
+//   * the rotation into the keypoint frame is folded with the 1 / SBP scale: nx = sn * dy + (cs * dx), one FFMA per
+//     coordinate with the per-chunk terms hoisted;
+//   * exp(r2 / 8) through ex2.approx (2 ulp; the tolerance is 1e-3), contributions added with one FFMA each;
+//   * COPIES = 32: one private histogram copy per lane, a single accumulation phase (16 KB per keypoint in flight);
+//     COPIES = 16: lanes l and l + 16 share a copy and take turns (8 KB).
+// Reduction order over the copies is fixed, so the output is bit-reproducible run to run.
+template <int COPIES>
+__global__ void __launch_bounds__(DE_WARPS * 32, 5) describe_fast_kernel(const NmOctaveTable tab, int capacity,
+                                                                      const int* __restrict__ counts,
+                                                                      const float4* __restrict__ kpts,
+                                                                      const int* __restrict__ meta,
+                                                                      const float2* __restrict__ orient,
+                                                                      float* __restrict__ desc, float* __restrict__ xo,
+                                                                      float* __restrict__ yo, int num_dogs)
+{
+    extern __shared__ __align__(16) float s_h[];      // [DE_WARPS][128 bins][COPIES]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int f = blockIdx.y;
+    const int j = blockIdx.x * DE_WARPS + wid;
+    if (j >= counts[f]) return;                                   // warp uniform
+    const long long kidx = (long long)f * capacity + j;
+    const float4 kp = kpts[kidx];
+    const NmOctave& oc = tab.o[meta[kidx]];
+    const KpGeom g = kp_geom(kp, oc.xper);                        // descriptor.cu:41-47
+    float* dout = desc + kidx * DE_BINS;
+    if (g.xi < 0 || g.xi >= oc.w || g.yi < 0 || g.yi >= oc.h || g.level < 0 || g.level >= num_dogs)
+        return;                                                   // :49 (slot left as is)
+    float* hist = s_h + wid * (DE_BINS * COPIES);
+    {
+        float4* h4 = reinterpret_cast<float4*>(hist);
+#pragma unroll
+        for (int b = 0; b < DE_BINS * COPIES / 128; ++b) h4[b * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+
+    const KpDescWindow dw = kp_desc_window(g, oc.w, oc.h);        // :54-65
+    const int xmin = dw.xmin, xmax = dw.xmax, ymin = dw.ymin, ymax = dw.ymax, chunks = dw.chunks;
+    const float th0 = orient[kidx].x;                             // :89; in [0, 2 pi] or -1 (no peak)
+    const float inv_sbp = __fdiv_rn(1.0f, dw.SBP);
+    const float cs = __fmul_rn(cosf(th0), inv_sbp), sn = __fmul_rn(sinf(th0), inv_sbp);   // :90-91 folded with 1 / SBP (:104-105)
+    const int pitch = oc.pitch;
+    const float2* __restrict__ G = oc.grad + ((long long)f * 3 + g.level) * oc.level_elems +
+                                   (long long)g.yi * pitch + g.xi;             // offsets inside one level fit 32 bits
+    float* const hcopy = hist + (lane & (COPIES - 1));
+    const int tx = lane & 15, ty = lane >> 4;
+
+    // gradient samples of chunk c for this lane: column xmin + 16 c + tx, rows ymin + 16 c + ty + 2 i (:94-97, :142-143)
+    auto load_chunk = [&](int c, float2 (&gv)[8]) {
+        const int bx = xmin + 16 * c + tx, by = ymin + 16 * c + ty;
+        const int idx = by * pitch + bx;                          // one IMAD.WIDE per load from a 32-bit index
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            gv[i] = make_float2(0.f, 0.f);
+            if (c < chunks && bx <= xmax && by + 2 * i <= ymax) gv[i] = __ldg(G + (idx + 2 * i * pitch));
+        }
+    };
+    auto process_chunk = [&](int c, const float2 (&cur)[8]) {
+        const int bx = xmin + 16 * c + tx, by = ymin + 16 * c + ty;
+        const bool vx = bx <= xmax;
+        const float dx = __fsub_rn((float)(g.xi + bx), g.x);                   // :102
+        const float ax = __fmul_rn(cs, dx), ay = -__fmul_rn(sn, dx);
+        const float fy0 = (float)(g.yi + by);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (by - ty + 2 * i > ymax) break;                                 // both rows of this step lie below the window (warp uniform)
+            const float dy = __fsub_rn(__fadd_rn(fy0, (float)(2 * i)), g.y);   // :103 (integers: the sum is exact)
+            const float nx = __fmaf_rn(sn, dy, ax), ny = __fmaf_rn(cs, dy, ay);            // :104-105
+            const float fx = floorf(__fsub_rn(nx, 0.5f)), fy = floorf(__fsub_rn(ny, 0.5f));   // :110-111
+            const int bx0 = (int)fx + 2, by0 = (int)fy + 2;
+            // about a third of the window (corners outside the rotated 4 x 4 cell grid) lands in no bin (:122-125)
+            const bool act = vx && by + 2 * i <= ymax && (unsigned)(bx0 + 1) <= 4u && (unsigned)(by0 + 1) <= 4u;
+            const float theta = nm_mod_2pi_once(__fsub_rn(cur[i].y, th0));     // :100
+            const float nt = __fmul_rn(theta, 1.2732395447351628f);            // :107, 8 / (2 pi)
+            const float ft = floorf(nt);
+            const int bint = (int)ft;                                          // :112
+            const float rbint = __fsub_rn(nt, ft);                             // :115
+            const float r2 = __fmaf_rn(nx, nx, __fmul_rn(ny, ny));
+            const float win = exp2f_approx(__fmul_rn(r2, 0.18033688011112042f));   // :108  exp(r2 / 8) = 2^(r2 * log2(e) / 8)
+            const float rbinx = __fsub_rn(nx, __fadd_rn(fx, 0.5f)), rbiny = __fsub_rn(ny, __fadd_rn(fy, 0.5f));   // :113-114
+            const float wm = __fmul_rn(win, cur[i].x);                         // :128-129
+            const float a1 = __fmul_rn(wm, rbinx), a0 = __fsub_rn(wm, a1);     // wm * |1 - rbinx|, wm * |rbinx|
+            const float w01 = __fmul_rn(a0, rbiny), w00 = __fsub_rn(a0, w01);
+            const float w11 = __fmul_rn(a1, rbiny), w10 = __fsub_rn(a1, w11);
+            const float at1 = rbint, at0 = __fsub_rn(1.f, rbint);
+            float* hp = hcopy + (by0 * 32 + bx0 * 8) * COPIES;                 // only dereferenced for valid cells
+            float* h0 = hp + (bint & 7) * COPIES;                              // :133 (bint + dbt) % 8
+            float* h1 = hp + ((bint + 1) & 7) * COPIES;
+            constexpr int OX = 8 * COPIES, OY = 32 * COPIES;
+            const bool vx0 = (unsigned)bx0 < 4u, vx1 = (unsigned)(bx0 + 1) < 4u;            // :122-125
+            const bool vy0 = (unsigned)by0 < 4u, vy1 = (unsigned)(by0 + 1) < 4u;
+            // The eight bins of a sample are distinct addresses: all eight loads are issued before the first store, so a
+            // sample costs ONE shared-memory round trip (load -> FFMA -> store) instead of eight dependent ones -- the
+            // compiler cannot know that h0[...] and h1[...] never alias and would order every load after the previous
+            // store (the round-1 kernel was bound by exactly that chain: twice the histogram copies, i.e. half the
+            // resident warps, made it 2.3x slower).
+            const bool p00 = vx0 && vy0, p01 = vx0 && vy1, p10 = vx1 && vy0, p11 = vx1 && vy1;
+#pragma unroll
+            for (int ph = 0; ph < 32 / COPIES; ++ph) {
+                if (act && (COPIES == 32 || (lane / COPIES) == ph)) {
+                    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f;
+                    if (p00) { v0 = h0[0]; v1 = h1[0]; }
+                    if (p01) { v2 = h0[OY]; v3 = h1[OY]; }
+                    if (p10) { v4 = h0[OX]; v5 = h1[OX]; }
+                    if (p11) { v6 = h0[OX + OY]; v7 = h1[OX + OY]; }
+                    v0 = __fmaf_rn(w00, at0, v0); v1 = __fmaf_rn(w00, at1, v1);                                          // :135
+                    v2 = __fmaf_rn(w01, at0, v2); v3 = __fmaf_rn(w01, at1, v3);
+                    v4 = __fmaf_rn(w10, at0, v4); v5 = __fmaf_rn(w10, at1, v5);
+                    v6 = __fmaf_rn(w11, at0, v6); v7 = __fmaf_rn(w11, at1, v7);
+                    if (p00) { h0[0] = v0; h1[0] = v1; }
+                    if (p01) { h0[OY] = v2; h1[OY] = v3; }
+                    if (p10) { h0[OX] = v4; h1[OX] = v5; }
+                    if (p11) { h0[OX + OY] = v6; h1[OX + OY] = v7; }
+                }
+                if (COPIES < 32) __syncwarp();
+            }
+        }
+    };
+    // two register sets take turns: the loads of chunk c + 1 are in flight while chunk c is accumulated
+    float2 ga[8], gb[8];
+    load_chunk(0, ga);
+    for (int c = 0; c < chunks; c += 2) {
+        load_chunk(c + 1, gb);
+        process_chunk(c, ga);
+        if (c + 1 < chunks) {
+            load_chunk(c + 2, ga);
+            process_chunk(c + 1, gb);
+        }
+    }
+    __syncwarp();
+    // fixed-order reduction; lane owns bins lane, lane+32, lane+64, lane+96
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int b = lane + 32 * q;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < COPIES; ++k)
+            acc = __fadd_rn(acc, hist[b * COPIES + ((k + lane / (32 / COPIES)) & (COPIES - 1))]);   // rotated: conflict free
+        dout[b] = acc;
+    }
+    if (lane == 0) { xo[kidx] = kp.x; yo[kidx] = kp.y; }              // :76
+}
+
 // ---------------------- compat: flat keypoint lists (one octave) ----------------------
 __global__ void compat_fill_meta(int* meta, int* count, int n)
 {
@@ -370,14 +529,24 @@ int nm_describe_launch(const NmOctaveTable& tab, int batch, int capacity, const 
 {
     static NmDeviceOnce once;
     constexpr int smem = DE_WARPS * DE_BINS * DE_COPIES * (int)sizeof(float);
+    constexpr int smem16 = DE_WARPS * DE_BINS * 16 * (int)sizeof(float), smem32 = DE_WARPS * DE_BINS * 32 * (int)sizeof(float);
     if (once.first()) {
         NM_CUDA_TRY(cudaFuncSetAttribute(describe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         NM_CUDA_TRY(cudaFuncSetAttribute(describe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        NM_CUDA_TRY(cudaFuncSetAttribute(describe_fast_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
+        NM_CUDA_TRY(cudaFuncSetAttribute(describe_fast_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32));
         once.done();
     }
+    // NM_DESCRIBE = 0: round-1 kernel, 16 (default): restructured kernel with 16 histogram copies, 32: with 32 (tuning aid;
+    // measured at 64 x 1080p: 2.26 / 1.86 / 1.98 ms)
+    static const int variant = getenv("NM_DESCRIBE") ? atoi(getenv("NM_DESCRIBE")) : 16;
     dim3 grid(nm_div_up(capacity, DE_WARPS), batch);
     if (exact)
         describe_kernel<true><<<grid, DE_WARPS * 32, smem, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
+    else if (variant == 32)
+        describe_fast_kernel<32><<<grid, DE_WARPS * 32, smem32, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
+    else if (variant == 16)
+        describe_fast_kernel<16><<<grid, DE_WARPS * 32, smem16, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
     else
         describe_kernel<false><<<grid, DE_WARPS * 32, smem, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
     NM_LAUNCH_CHECK();
