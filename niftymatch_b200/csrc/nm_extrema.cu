@@ -443,7 +443,45 @@ __global__ void __launch_bounds__(256) refine_list_kernel(const NmOctave oc, con
 // global memory (the rows are L1 / L2 hits of the neighbouring lanes and rows), all 26 loads of a block in
 // flight before its first gradient is evaluated.  `dense` != 0 computes every block (tests and tools that read
 // whole maps).
-__global__ void __launch_bounds__(256, 3) gradmap_kernel(const NmOctave oc, int strips_x, int dense)
+// R interior rows of a gradient map starting at `p0` (the source pixel of the first row) / `q` (its gradient): no
+// per-row predicates, all loads first, all R gradients through the branch-free main path (their chains interleave),
+// exact zeros (flat image areas) selected, the rare out-of-range arguments repaired afterwards.
+template <int R>
+__device__ __forceinline__ void gradmap_rows(const float* __restrict__ p0, float2* __restrict__ q, int pitch, bool intx)
+{
+    float ctr[R + 2], lf[R], rt[R];
+    const float* __restrict__ p = p0 - pitch;
+    ctr[0] = __ldg(p);
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        p += pitch;
+        lf[j] = __ldg(p - 1); ctr[j + 1] = __ldg(p); rt[j] = __ldg(p + 1);
+    }
+    ctr[R + 1] = __ldg(p + pitch);
+    float2 g[R];
+    unsigned bad = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const float dx = __fsub_rn(rt[j], lf[j]), dy = __fsub_rn(ctr[j + 2], ctr[j]);
+        g[j] = nm_gradient_main(dx, dy);
+        const bool zero = dx == 0.f && dy == 0.f;                   // library result: (0, 0)
+        if (zero || !intx) g[j] = make_float2(0.f, 0.f);
+        if (!zero && intx && !nm_gradient_in_range(dx, dy)) bad |= 1u << j;
+    }
+    if (bad) {
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+            if ((bad >> j) & 1u) g[j] = nm_gradient_lib(__fsub_rn(rt[j], lf[j]), __fsub_rn(ctr[j + 2], ctr[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        *q = g[j];
+        q += pitch;
+    }
+}
+
+template <int MINB, bool PREFETCH, int RSUB>
+__global__ void __launch_bounds__(256, MINB) gradmap_kernel(const NmOctave oc, int strips_x, int dense)
 {
     const int lane = threadIdx.x & 31;
     const int cb = (blockIdx.x % strips_x) * 8 + (threadIdx.x >> 5), rb0 = (blockIdx.x / strips_x) * 4;
@@ -457,14 +495,52 @@ __global__ void __launch_bounds__(256, 3) gradmap_kernel(const NmOctave oc, int 
     const float* __restrict__ src = oc.levels + ((long long)f * 6 + l + 1) * oc.level_elems + x;
     float2* __restrict__ G = oc.grad + (long long)fl * oc.level_elems + x;
     const bool intx = x >= 1 && x <= w - 2;
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-        const int rb = rb0 + k;
-        if (rb >= nrb) break;
-        if (!dense && need[rb * wpr] == 0) continue;            // warp uniform
-        if (x >= w) continue;
+    if (x >= w) return;
+
+    // block rb is "inner" when rows y0 - 1 .. y0 + 8 exist: nothing is predicated per row.  The +-1 column neighbours of
+    // the first / last column read a pad element or the neighbouring row (inside the level's allocation; the value is
+    // unused: those lanes store (0, 0)).  Pointer walk: one 64-bit add per row serves its three loads (immediate offsets).
+    auto wanted = [&](int rb) { return rb < nrb && (dense || need[rb * wpr] != 0); };
+    auto inner = [&](int rb) { return rb * NM_NEED_ROWS >= 1 && rb * NM_NEED_ROWS + NM_NEED_ROWS + 1 <= h; };
+    auto load_inner = [&](int rb, float (&ctr)[NM_NEED_ROWS + 2], float (&lf)[NM_NEED_ROWS], float (&rt)[NM_NEED_ROWS]) {
+        const float* __restrict__ p = src + (long long)(rb * NM_NEED_ROWS - 1) * pitch;
+        ctr[0] = __ldg(p);
+#pragma unroll
+        for (int j = 0; j < NM_NEED_ROWS; ++j) {
+            p += pitch;
+            lf[j] = __ldg(p - 1); ctr[j + 1] = __ldg(p); rt[j] = __ldg(p + 1);
+        }
+        ctr[NM_NEED_ROWS + 1] = __ldg(p + pitch);
+    };
+    // all eight gradients through the branch-free main path (their chains interleave), exact zeros (flat image areas)
+    // selected, the rare out-of-range arguments repaired afterwards
+    auto compute_inner = [&](int rb, const float (&ctr)[NM_NEED_ROWS + 2], const float (&lf)[NM_NEED_ROWS], const float (&rt)[NM_NEED_ROWS]) {
+        float2 g[NM_NEED_ROWS];
+        unsigned bad = 0;
+#pragma unroll
+        for (int j = 0; j < NM_NEED_ROWS; ++j) {
+            const float dx = __fsub_rn(rt[j], lf[j]), dy = __fsub_rn(ctr[j + 2], ctr[j]);
+            g[j] = nm_gradient_main(dx, dy);
+            const bool zero = dx == 0.f && dy == 0.f;                   // library result: (0, 0)
+            if (zero || !intx) g[j] = make_float2(0.f, 0.f);
+            if (!zero && intx && !nm_gradient_in_range(dx, dy)) bad |= 1u << j;
+        }
+        if (bad) {
+#pragma unroll
+            for (int j = 0; j < NM_NEED_ROWS; ++j)
+                if ((bad >> j) & 1u) g[j] = nm_gradient_lib(__fsub_rn(rt[j], lf[j]), __fsub_rn(ctr[j + 2], ctr[j]));
+        }
+        float2* __restrict__ q = G + (long long)(rb * NM_NEED_ROWS) * pitch;
+#pragma unroll
+        for (int j = 0; j < NM_NEED_ROWS; ++j) {
+            *q = g[j];
+            q += pitch;
+        }
+    };
+    auto border_block = [&](int rb) {
         const int y0 = rb * NM_NEED_ROWS;
-        const float* __restrict__ p = src + y0 * pitch;         // offsets inside a level fit 32 bits
+        const float* __restrict__ p = src + (long long)y0 * pitch;
+        float2* __restrict__ q = G + (long long)y0 * pitch;
         float ctr[NM_NEED_ROWS + 2], lf[NM_NEED_ROWS], rt[NM_NEED_ROWS];
 #pragma unroll
         for (int j = -1; j <= NM_NEED_ROWS; ++j) {
@@ -478,7 +554,6 @@ __global__ void __launch_bounds__(256, 3) gradmap_kernel(const NmOctave oc, int 
             lf[j] = interior ? __ldg(p + j * pitch - 1) : 0.f;
             rt[j] = interior ? __ldg(p + j * pitch + 1) : 0.f;
         }
-        float2* __restrict__ q = G + y0 * pitch;
 #pragma unroll
         for (int j = 0; j < NM_NEED_ROWS; ++j) {
             const int y = y0 + j;
@@ -488,6 +563,44 @@ __global__ void __launch_bounds__(256, 3) gradmap_kernel(const NmOctave oc, int 
                 if (interior) g = nm_gradient_at(rt[j], lf[j], ctr[j + 2], ctr[j]);
                 q[j * pitch] = g;
             }
+        }
+    };
+
+    if (PREFETCH) {
+        // the loads of the next wanted inner block are in flight while the current one is evaluated
+        float ca[NM_NEED_ROWS + 2], la[NM_NEED_ROWS], ra[NM_NEED_ROWS];
+        float cn[NM_NEED_ROWS + 2], ln[NM_NEED_ROWS], rn[NM_NEED_ROWS];
+        int cur = -1;
+#pragma unroll 1
+        for (int k = 0; k <= 4; ++k) {
+            const int rb = rb0 + k;
+            const bool go = k < 4 && wanted(rb);                    // warp uniform
+            if (go && !inner(rb)) { border_block(rb); continue; }
+            if (go) load_inner(rb, cn, ln, rn);
+            if (cur >= 0) compute_inner(cur, ca, la, ra);
+            cur = -1;
+            if (go) {
+                cur = rb;
+#pragma unroll
+                for (int j = 0; j < NM_NEED_ROWS + 2; ++j) ca[j] = cn[j];
+#pragma unroll
+                for (int j = 0; j < NM_NEED_ROWS; ++j) { la[j] = ln[j]; ra[j] = rn[j]; }
+            }
+        }
+        return;
+    }
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        const int rb = rb0 + k;
+        if (rb >= nrb) break;
+        if (!wanted(rb)) continue;                              // warp uniform
+        if (inner(rb)) {
+            // RSUB rows at a time: fewer live registers (more resident warps) against a few more halo-row loads
+#pragma unroll 1
+            for (int r0 = 0; r0 < NM_NEED_ROWS; r0 += RSUB)
+                gradmap_rows<RSUB>(src + (long long)(rb * NM_NEED_ROWS + r0) * pitch, G + (long long)(rb * NM_NEED_ROWS + r0) * pitch, pitch, intx);
+        } else {
+            border_block(rb);
         }
     }
 }
@@ -810,7 +923,17 @@ int nm_gradmap_launch(const NmOctaveTable& tab, int batch, int dense, cudaStream
         const NmOctave& oc = tab.o[o];
         const int strips_x = nm_div_up(oc.wpr, 8), nrb = nm_div_up(oc.h, NM_NEED_ROWS);
         dim3 grid(strips_x * nm_div_up(nrb, 4), batch * 3);
-        gradmap_kernel<<<grid, 256, 0, stream>>>(oc, strips_x, dense);
+        // NM_GRADMAP (tuning aid; 64 x 1080p): 1 (default) 64 registers, 4 CTAs / SM: 1.32 ms; 0: 72 registers, 3 CTAs: 1.49;
+        // 2: next block's loads prefetched, 117 registers: 1.87; 3..6: 4- / 2-row sub-blocks at 5..8 CTAs / SM: 1.34 .. 1.53
+        // (the kernel waits on its global loads: resident warps are what it needs)
+        static const int variant = getenv("NM_GRADMAP") ? atoi(getenv("NM_GRADMAP")) : 1;
+        if (variant == 1) gradmap_kernel<4, false, 8><<<grid, 256, 0, stream>>>(oc, strips_x, dense);
+        else if (variant == 2) gradmap_kernel<2, true, 8><<<grid, 256, 0, stream>>>(oc, strips_x, dense);
+        else if (variant == 3) gradmap_kernel<5, false, 4><<<grid, 256, 0, stream>>>(oc, strips_x, dense);
+        else if (variant == 4) gradmap_kernel<6, false, 4><<<grid, 256, 0, stream>>>(oc, strips_x, dense);
+        else if (variant == 5) gradmap_kernel<8, false, 2><<<grid, 256, 0, stream>>>(oc, strips_x, dense);
+        else if (variant == 6) gradmap_kernel<6, false, 2><<<grid, 256, 0, stream>>>(oc, strips_x, dense);
+        else gradmap_kernel<3, false, 8><<<grid, 256, 0, stream>>>(oc, strips_x, dense);
         NM_LAUNCH_CHECK();
     }
     return NM_OK;
