@@ -693,7 +693,13 @@ def match_leg(nm, torch, dist, synth, shard_bounds, rank, world, args, barrier, 
     nq = ndb = 100000
     Bh = synth.descriptors(ndb, 2)
     Ah = synth.descriptors(nq, 1, planted_from=Bh)
-    blo, bhi = shard_bounds(ndb, world, rank)
+    # world = Q x D: Q query groups, D database shards (rank r scans query block r // D against shard r % D); Q = 1 is
+    # pure database sharding.  The per-row costs of a scan shrink with Q, the scan itself with D.
+    qg = env_int("NM_BENCH_QGROUPS", {8: 4, 4: 2}.get(world, 1))
+    if world % qg:
+        qg = 1
+    n_db_shards = world // qg
+    blo, bhi = shard_bounds(ndb, n_db_shards, rank % n_db_shards)
     A = torch.from_numpy(Ah).cuda()
     Bs = torch.from_numpy(np.ascontiguousarray(Bh[blo:bhi])).cuda()
 
@@ -705,6 +711,7 @@ def match_leg(nm, torch, dist, synth, shard_bounds, rank, world, args, barrier, 
         uid_t = torch.tensor(list(mgpu.unique_id() if rank == 0 else bytes(mgpu.ID_BYTES)), dtype=torch.uint8, device="cuda")
         dist.broadcast(uid_t, 0)
         mg = mgpu.MultiGpu(rank=rank, world=world, uid=bytes(uid_t.cpu().tolist()))
+        mg.set_query_groups(qg)
         io = torch.full((nq,), -1, dtype=torch.int32, device="cuda")
 
     def match_step():
@@ -738,6 +745,7 @@ def match_leg(nm, torch, dist, synth, shard_bounds, rank, world, args, barrier, 
            "config": {"workload": "100k x 100k 128-D fp32 descriptors, k=2 ratio test "
                                   "(BASELINE.json configs[3]); database rows sharded over the ranks, "
                                   "NCCL all-gather of per-shard top-2 records + merge",
+                      "sharding": f"{qg} query groups x {n_db_shards} database shards",
                       "matched": int((mh >= 0).sum()), "index_hash": index_hash}}
     if mg is not None:
         mg.set_trace(True)
