@@ -4,6 +4,12 @@
 // (gpu/kernels/ransac.cu:50-59, :526-694) and the one-sided Jacobi SVD they call (gpu/kernels/svd.cu:
 // 200-360, the reference's port of GSL's gsl_linalg_SV_decomp_jacobi).
 //
+// Provenance note: the reference's svd.cu carries a GNU GPL header of its own (svd.cu:1-20, derived from GSL),
+// unlike the rest of the reference.  jacobi_right_vectors below is a restructured restatement of that published
+// algorithm (fused dot / norm loop, lane-interleaved shared-memory matrices, templated sizes, no singular-value
+// tail), but it follows the same order of operations -- bitwise hypotheses require it -- so whoever ships this
+// file should treat it under the terms that apply to svd.cu.
+//
 // What is kept: the arithmetic of a hypothesis (normalised 4-point DLT / 2-point similarity / 1-point
 // translation, Jacobi sweeps with GSL's error-estimate skip rule, the expanded de-normalisation) in the
 // reference's order of operations, the inlier rule (squared reprojection error < threshold over the
