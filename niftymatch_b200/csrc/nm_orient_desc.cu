@@ -67,42 +67,34 @@ __global__ void __launch_bounds__(OR_WARPS * 32) orient_kernel(const NmOctaveTab
         // :55 compares (double)r2 < W*W + 0.6; W*W + 0.6 is not an fp32 number, so for fp32 r2 that is
         // r2 < (the smallest fp32 above it)
         const float lim_f = __double2float_ru(__dadd_rn((double)(W * W), 0.6));
-        // Window samples in raster order, 32 per step; (cx, cy) advance incrementally (no division per
-        // sample).  The gradient maps of a batch live in HBM and only 8 warps per scheduler are resident,
-        // so OR_DEPTH steps of gradient loads stay in flight per lane (ncu: long-scoreboard waits on the
-        // single prefetched value were the top stall).
-        constexpr int OR_DEPTH = 4;
-        int cx = xmin + lane % max(nx, 1), cy = ymin + lane / max(nx, 1);
-        const int adv_y = 32 / max(nx, 1), adv_x = 32 % max(nx, 1);
-        int pcx[OR_DEPTH], pcy[OR_DEPTH];
-        float2 pg[OR_DEPTH];
+        // Window samples in raster order, 32 per step, four steps per round: the four gradient loads of a lane are issued
+        // first (the maps of a batch live in HBM), then the four samples are accumulated.  Sample s sits at row s / nx,
+        // column s % nx of the clipped window; nx <= 21 and s < 512, for which (s * ceil(2^16 / nx)) >> 16 is the exact
+        // quotient -- no division and no carried position per sample.
+        const int inv_nx = (65536 + max(nx, 1) - 1) / max(nx, 1);
+        const float fx0 = (float)(xmin + g.xi), fy0 = (float)(ymin + g.yi);
+        for (int s0 = lane; s0 < total; s0 += 128) {
+            float2 gv[4];
+            int rx[4], ry[4];
 #pragma unroll
-        for (int d = 0; d < OR_DEPTH; ++d) {
-            pcx[d] = cx; pcy[d] = cy;
-            pg[d] = make_float2(0.f, 0.f);
-            if (lane + 32 * d < total) pg[d] = __ldg(G + (cy * pitch + cx));
-            cx += adv_x; cy += adv_y;
-            if (cx > xmax) { cx -= nx; ++cy; }
-        }
-        for (int s = lane; s < total; s += 32 * OR_DEPTH) {
+            for (int d = 0; d < 4; ++d) {
+                const int sd = s0 + 32 * d;
+                ry[d] = (sd * inv_nx) >> 16;
+                rx[d] = sd - ry[d] * nx;
+                gv[d] = make_float2(0.f, 0.f);
+                if (sd < total) gv[d] = __ldg(G + ((ymin + ry[d]) * pitch + xmin + rx[d]));
+            }
 #pragma unroll
-            for (int d = 0; d < OR_DEPTH; ++d) {
-                const int ccx = pcx[d], ccy = pcy[d];
-                const float2 gv = pg[d];
-                const bool valid = s + 32 * d < total;
-                pcx[d] = cx; pcy[d] = cy;
-                if (s + 32 * (d + OR_DEPTH) < total) pg[d] = __ldg(G + (cy * pitch + cx));
-                cx += adv_x; cy += adv_y;
-                if (cx > xmax) { cx -= nx; ++cy; }
-                const float dx = __fsub_rn((float)(ccx + g.xi), g.x);  // :52-53
-                const float dy = __fsub_rn((float)(ccy + g.yi), g.y);
+            for (int d = 0; d < 4; ++d) {
+                const float dx = __fsub_rn(__fadd_rn(fx0, (float)rx[d]), g.x);   // :52-53 (integers: the sums are exact)
+                const float dy = __fsub_rn(__fadd_rn(fy0, (float)ry[d]), g.y);
                 const float r2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));         // :54
-                if (valid && r2 < lim_f) {                            // :55
-                    const float wgt = exp2f_approx(__fmul_rn(r2, k_exp));   // :56 (positive exponent)
+                if (s0 + 32 * d < total && r2 < lim_f) {                      // :55
+                    const float wgt = exp2f_approx(__fmul_rn(r2, k_exp));     // :56 (positive exponent)
                     // :57  bin = floor((float)((double)(36 theta) / 2 pi)).  The fp32 product v * (1 / 2 pi) is within
                     // 7e-6 of that quotient (v <= 227), so its floor is the reference's unless it lies within 1e-5
                     // of an integer; only then (2e-5 of the samples) the double division decides.
-                    const float v36 = __fmul_rn(36.0f, gv.y);
+                    const float v36 = __fmul_rn(36.0f, gv[d].y);
                     const float qf = __fmul_rn(v36, 0.15915494309189535f);
                     float qfl = floorf(qf);
                     const float fr = __fsub_rn(qf, qfl);
@@ -110,7 +102,7 @@ __global__ void __launch_bounds__(OR_WARPS * 32) orient_kernel(const NmOctaveTab
                     int bin = (int)qfl;                               // theta in [0, 2 pi]: 0 .. 36
                     if ((unsigned)bin >= (unsigned)NBINS) { bin %= NBINS; if (bin < 0) bin += NBINS; }   // :58 bin % NBINS
                     float* p = priv + bin * OR_HP + lane;             // bank == lane: conflict free
-                    *p = __fadd_rn(*p, __fmul_rn(gv.x, wgt));         // :58
+                    *p = __fmaf_rn(gv[d].x, wgt, *p);                 // :58
                 }
             }
         }
@@ -125,19 +117,15 @@ __global__ void __launch_bounds__(OR_WARPS * 32) orient_kernel(const NmOctaveTab
         }
         __syncwarp();
         // 6x circular 3-tap box smoothing, Jacobi (intended semantics = orientation.cu:181-192)
+        const int bm0 = (lane + NBINS - 1) % NBINS, bp0 = lane + 1;                    // neighbours of bin `lane` (< 32)
+        const int b1 = lane + 32, bm1 = b1 - 1, bp1 = (b1 + 1) % NBINS;                // ... of bin `lane + 32` (lanes 0..3)
         for (int iter = 0; iter < 6; ++iter) {
-            float n0 = 0.f, n1 = 0.f;
-            {
-                const int b = lane;
-                n0 = __fdiv_rn(__fadd_rn(__fadd_rn(hist[(b + NBINS - 1) % NBINS], hist[b]), hist[(b + 1) % NBINS]), 3.0f);
-            }
-            if (lane < NBINS - 32) {
-                const int b = lane + 32;
-                n1 = __fdiv_rn(__fadd_rn(__fadd_rn(hist[(b + NBINS - 1) % NBINS], hist[b]), hist[(b + 1) % NBINS]), 3.0f);
-            }
+            const float n0 = __fdiv_rn(__fadd_rn(__fadd_rn(hist[bm0], hist[lane]), hist[bp0]), 3.0f);
+            float n1 = 0.f;
+            if (lane < NBINS - 32) n1 = __fdiv_rn(__fadd_rn(__fadd_rn(hist[bm1], hist[b1]), hist[bp1]), 3.0f);
             __syncwarp();
             hist[lane] = n0;
-            if (lane < NBINS - 32) hist[lane + 32] = n1;
+            if (lane < NBINS - 32) hist[b1] = n1;
             __syncwarp();
         }
         float m = fmaxf(0.f, hist[lane]);                          // :93-95

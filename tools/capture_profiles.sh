@@ -1,15 +1,33 @@
 #!/usr/bin/env bash
 # Round-2 profile capture on the GPU box (gpurun): the plain bench line, the ncu launch list of the same command, and
-# one `--set full` capture per hot kernel.  Outputs go to gpurun_out/r02_*; summaries are made here afterwards.
+# one `--set full` capture per hot kernel (octave-0 launch of the second iteration), exported to CSV pages on the box
+# (gpurun brings back at most 64 MiB, the .ncu-rep files are deleted).
 set -u
 O=gpurun_out
 BENCH="python bench.py --steps 5 --warmup 3 --no-cpu --no-extra --no-match"
 $BENCH > $O/r02_bench_sift_only.json 2> $O/r02_bench_sift_only.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 420 --csv --log-file $O/r02_launches_bench.csv $BENCH > $O/r02_ncu_launches.log 2>&1
 QB="python tools/quick_bench.py 1920 1080 16"
-$QB > $O/r02_qb16.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"blur_strip_kernel|extrema_kernel|refine_list|gradmap_kernel|orient_kernel|describe_fast|kprefine|emit_kernel|rank_kernel" -s 57 -c 57 -o $O/r02_prof_sift $QB > $O/r02_ncu_sift.log 2>&1
+$QB > $O/r02_qb16.log 2>&1 || exit 1
+cap() {   # name regex skip
+  ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c 1 -o $O/r02_$1 $QB > $O/r02_ncu_$1.log 2>&1
+  ncu -i $O/r02_$1.ncu-rep --page raw --csv > $O/r02_$1_raw.csv 2>/dev/null
+  ncu -i $O/r02_$1.ncu-rep --page source --csv > $O/r02_$1_source.csv 2>/dev/null
+  rm -f $O/r02_$1.ncu-rep
+}
+cap blur_strip13 blur_strip_kernel 16
+cap blur_strip5 blur_strip_kernel 12
+cap extrema extrema_kernel 6
+cap refine_list refine_list_kernel 6
+cap gradmap gradmap_kernel 6
+cap orient orient_kernel 1
+cap describe describe_fast_kernel 1
+cap kprefine kprefine_kernel 1
 M="python tools/match_once.py 100000 100000 1"
 $M > $O/r02_match_once.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"tc_scan_kernel|tc_rerank_kernel" -s 2 -c 3 -o $O/r02_prof_match $M > $O/r02_ncu_match.log 2>&1
-tail -2 $O/r02_ncu_sift.log $O/r02_ncu_match.log
+ncu --set full --clock-control none --import-source on -k regex:"tc_scan_kernel" -s 3 -c 1 -o $O/r02_tc_scan $M > $O/r02_ncu_tc_scan.log 2>&1
+ncu -i $O/r02_tc_scan.ncu-rep --page raw --csv > $O/r02_tc_scan_raw.csv 2>/dev/null
+ncu -i $O/r02_tc_scan.ncu-rep --page source --csv > $O/r02_tc_scan_source.csv 2>/dev/null
+rm -f $O/r02_tc_scan.ncu-rep
+ls -la $O | tail -30
+du -sh $O
