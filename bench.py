@@ -229,6 +229,16 @@ def run_reference_arm(args, rank, world):
                   "hoisted, because detect_orientations deadlocks on sm_70+ as shipped); one host thread")
         kind, cores = "reference", 1
         kp = items.value / (n * args.steps)
+        # for the record: the same run with the reference's OTHER orientation kernel (kernel_orientations_naive, one thread
+        # per keypoint, no window clamp) -- round 1 timed that one, because the public kernel cannot run unpatched
+        alt = None
+        try:
+            cfg1 = np.array([0.0, -1, -1, CAPACITY, 1, 1], np.float32)
+            ms1, it1 = C.c_float(), C.c_longlong()
+            if lib.nmref_sift_bench(C.c_void_p(dev.data_ptr()), n, W, H, cfg1.ctypes.data_as(C.c_void_p), 2, C.byref(ms1), C.byref(it1)) == 0:
+                alt = {"frames_per_s": n / (ms1.value / 2) * 1e3, "orientation_kernel": "kernel_orientations_naive (orientation.cu:132-216)"}
+        except Exception as exc:
+            alt = {"error": repr(exc)}
         del dev
         # the matcher half of the metric at the sizes the reference's 32-bit indexing can address
         try:
@@ -252,6 +262,8 @@ def run_reference_arm(args, rank, world):
         cb = cpu_baseline(frames)
         n = BATCH
         v, per_step, sample, kind, cores, kp = cb["value"], n / cb["value"] * 1e3, cb["sample"], "port", cb["cores"], cb["keypoints_per_frame"]
+    if use_gpu:
+        base["with_naive_orientation_kernel"] = alt
     base.update({"value": v, "ms_per_step": per_step, "keypoints_per_frame": kp,
                  "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
                  "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -553,7 +565,7 @@ def main():
                "design overhead, not credited by SURVEY.md 8d: 3 levels read (12 B) + 3 float2 maps written (24 B) per pixel if every "
                "block were computed; only blocks that keypoint windows read are"),
             st("orientation", "orient_kernel", stage["orientation"], ori_b, 1, "gather: 8 B per window sample of every keypoint + payloads; keypoint-count bound"),
-            st("descriptor", "describe_kernel<0>", stage["descriptor"], desc_b, 1, "gather: 8 B per sample of the diagonal 16x16 chunks + 512 B descriptor per keypoint"),
+            st("descriptor", "describe_fast_kernel<16, 4>", stage["descriptor"], desc_b, 1, "gather: 8 B per sample of the diagonal 16x16 chunks + 512 B descriptor per keypoint"),
         ]
         single = [s for s in stages if s["stage"] in ("extrema", "gradient", "orientation", "descriptor")]
         dom = max(single, key=lambda s: s["ms"])
