@@ -610,14 +610,15 @@ __global__ void __launch_bounds__(256, MINB) gradmap_kernel(const NmOctave oc, i
 // occupy neither registers nor load/store slots, the four neighbours of a pixel are shared-memory reads at immediate
 // offsets, and a tile none of whose twelve (level, 8-row block) need bytes is set is neither loaded nor visited.
 constexpr uint32_t GM_TILE_BYTES = 3u * EX_ROWS * EX_P * sizeof(float);     // 16 320
-constexpr int GM_SMEM = 2 * (int)GM_TILE_BYTES + 64;
+constexpr int GM_BUF_STRIDE = 16384;                                        // TMA destinations are 128-byte aligned
+constexpr int GM_SMEM = 2 * GM_BUF_STRIDE + 64;
 
 __global__ void __launch_bounds__(256, 4) gradmap_tma_kernel(const NmOctave oc, const __grid_constant__ CUtensorMap tmap,
                                                              int tiles_x, int tiles_y, int n_tiles, int dense)
 {
     extern __shared__ __align__(128) unsigned char gm_smem[];
-    float (*s_win)[3][EX_ROWS][EX_P] = reinterpret_cast<float (*)[3][EX_ROWS][EX_P]>(gm_smem);       // [2]
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(gm_smem + 2 * GM_TILE_BYTES);                      // [2]
+    auto win = [&](int buf) { return reinterpret_cast<float (*)[EX_ROWS][EX_P]>(gm_smem + buf * GM_BUF_STRIDE); };   // [3][34][40]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(gm_smem + 2 * GM_BUF_STRIDE);                      // [2]
     unsigned* s_mask = reinterpret_cast<unsigned*>(s_bar + 2);                                       // [2]: bit l * 4 + k
     const int tid = threadIdx.y * 32 + threadIdx.x, lane = threadIdx.x, wy = threadIdx.y;
     const int nrb = (oc.h + NM_NEED_ROWS - 1) / NM_NEED_ROWS;
@@ -640,7 +641,7 @@ __global__ void __launch_bounds__(256, 4) gradmap_tma_kernel(const NmOctave oc, 
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(GM_TILE_BYTES) : "memory");
                 asm volatile(
                     "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                    ::"r"(ex_smem_u32(&s_win[buf][0][0][0])), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(tx * EX_TW - EX_HL),
+                    ::"r"(ex_smem_u32(win(buf))), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(tx * EX_TW - EX_HL),
                       "r"(ty * EX_TH - 1), "r"(f * 6 + 1), "r"(bar) : "memory");
             }
         }
@@ -682,7 +683,7 @@ __global__ void __launch_bounds__(256, 4) gradmap_tma_kernel(const NmOctave oc, 
 #pragma unroll
                 for (int l = 0; l < 3; ++l) {
                     if (!((mask >> (l * 4 + k)) & 1u)) continue;                // warp uniform
-                    const float (*L)[EX_P] = s_win[buf][l];
+                    const float (*L)[EX_P] = win(buf)[l];
                     float2 g[4];
                     float dxs[4], dys[4];
                     unsigned bad = 0;
@@ -1045,10 +1046,12 @@ bool nm_gradmap_make_tma(CUtensorMap* map, const NmOctave& oc, int batch)
 int nm_gradmap_launch(const NmOctaveTable& tab, int batch, int dense, cudaStream_t stream, const NmBlurTma* ex_tma)
 {
     if (batch * 3 > 65535) return NM_ERR_OVERFLOW;
-    // NM_GRADMAP (tuning aid; 64 x 1080p): 7: TMA-staged tiles; 1: direct loads, 64 registers, 4 CTAs / SM: 1.32 ms; 0: 72
-    // registers, 3 CTAs: 1.49; 2: next block's loads prefetched, 117 registers: 1.87; 3..6: 4- / 2-row sub-blocks at 5..8
-    // CTAs / SM: 1.34 .. 1.53 (the direct-load kernel waits on its global loads: resident warps are what it needs)
-    static const int variant = getenv("NM_GRADMAP") ? atoi(getenv("NM_GRADMAP")) : 7;
+    // NM_GRADMAP (tuning aid; 64 x 1080p): 1 (default): direct loads, 64 registers, 4 CTAs / SM: 1.32 ms; 0: 72 registers,
+    // 3 CTAs: 1.49; 2: next block's loads prefetched, 117 registers: 1.87; 3..6: 4- / 2-row sub-blocks at 5..8 CTAs / SM:
+    // 1.34 .. 1.53 (the direct-load kernel waits on its global loads: resident warps are what it needs); 7: TMA-staged
+    // 32 x 32 tiles in persistent CTAs (gradmap_tma_kernel): 1.57 -- one barrier per tile and the uneven need bits of a
+    // tile's warps cost more than the load slots the bulk copies save
+    static const int variant = getenv("NM_GRADMAP") ? atoi(getenv("NM_GRADMAP")) : 1;
     for (int o = 0; o < tab.n_oct; ++o) {
         const NmOctave& oc = tab.o[o];
         if (variant == 7 && ex_tma && ex_tma[o].valid_strip) {
