@@ -459,8 +459,19 @@ extern "C" int nm_sift_run_host(nm_sift_ctx* c, const float* frames_host, int n_
     if (n_frames <= 8 && forced <= 0) {
         bounds[++n_chunks] = n_frames;
     } else {
-        const int per = std::max(stage, nm_div_up(n_frames, NM_MAX_CHUNKS));
-        for (int f = 0; f < n_frames; f += per) bounds[++n_chunks] = f + per < n_frames ? f + per : n_frames;
+        // uniform stages, tapered at the end (2, 1, 1 frames): what remains to be done when the LAST frame has landed
+        // is that frame's kernels and its result copy, not a whole 3-frame stage (NM_HOST_TAPER=0 disables)
+        static const bool taper = !(getenv("NM_HOST_TAPER") && getenv("NM_HOST_TAPER")[0] == '0');
+        const int per = std::max(stage, nm_div_up(n_frames, NM_MAX_CHUNKS - 4));
+        int f = 0;
+        while (f < n_frames) {
+            const int left = n_frames - f;
+            int take = per;
+            if (taper && per >= 2 && left <= per + 1) take = left >= 4 ? 2 : left >= 3 ? 2 : 1;
+            if (take > left) take = left;
+            f += take;
+            bounds[++n_chunks] = f;
+        }
     }
     if (n_chunks > NM_MAX_CHUNKS) return NM_ERR_INVALID;
     int launches = 0;
