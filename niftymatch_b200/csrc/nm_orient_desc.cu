@@ -25,6 +25,18 @@ __device__ __forceinline__ float exp2f_approx(float x)
     return r;
 }
 
+// Packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: two independent IEEE operations per instruction).  A packed
+// instruction holds the FMA pipe for two cycles but takes ONE issue slot, and instructions of the other pipes issue
+// in its shadow (tools/fma_probe.cu: 8 FFMA2 + 8 LOP3 per round take 17 cycles, 16 FFMA + 8 LOP3 take 26) -- in the
+// issue-bound gather kernels that is where the floating-point half of the instruction count goes.
+typedef unsigned long long nm_f2;
+__device__ __forceinline__ nm_f2 pk2(float lo, float hi) { nm_f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(nm_f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ nm_f2 fma2(nm_f2 a, nm_f2 b, nm_f2 c) { nm_f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ nm_f2 add2(nm_f2 a, nm_f2 b) { nm_f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ nm_f2 sub2(nm_f2 a, nm_f2 b) { nm_f2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ nm_f2 mul2(nm_f2 a, nm_f2 b) { nm_f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 constexpr int OR_WARPS = 8;      // warps per block, orientation
 constexpr int NBINS = 36;
 constexpr int OR_HP = 32;        // lane pitch of the private histograms (bank == lane)
@@ -356,8 +368,8 @@ __global__ void __launch_bounds__(DE_WARPS * 32) describe_kernel(const NmOctaveT
 //   * COPIES = 32: one private histogram copy per lane, a single accumulation phase (16 KB per keypoint in flight);
 //     COPIES = 16: lanes l and l + 16 share a copy and take turns (8 KB).
 // Reduction order over the copies is fixed, so the output is bit-reproducible run to run.
-template <int COPIES, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) describe_fast_kernel(const NmOctaveTable tab, int capacity,
+template <int COPIES, int WARPS, bool PACKED, int MINB = 0>
+__global__ void __launch_bounds__(WARPS * 32, MINB) describe_fast_kernel(const NmOctaveTable tab, int capacity,
                                                                       const int* __restrict__ counts,
                                                                       const float4* __restrict__ kpts,
                                                                       const int* __restrict__ meta,
@@ -412,6 +424,78 @@ __global__ void __launch_bounds__(WARPS * 32) describe_fast_kernel(const NmOctav
         const float dx = __fsub_rn((float)(g.xi + bx), g.x);                   // :102
         const float ax = __fmul_rn(cs, dx), ay = -__fmul_rn(sn, dx);
         const float fy0 = (float)(g.yi + by);
+        if (PACKED) {
+            // two samples of the lane (rows 2 i and 2 i + 2 below the chunk's first row) per packed instruction
+            const nm_f2 sn2 = pk2(sn, sn), cs2 = pk2(cs, cs), ax2 = pk2(ax, ax), ay2 = pk2(ay, ay);
+            const nm_f2 gy2 = pk2(g.y, g.y), th2 = pk2(th0, th0), half2v = pk2(0.5f, 0.5f), one2 = pk2(1.f, 1.f);
+#pragma unroll
+            for (int ip = 0; ip < 4; ++ip) {
+                const int i0 = 2 * ip, i1 = 2 * ip + 1;
+                const nm_f2 dy2 = sub2(pk2(__fadd_rn(fy0, (float)(2 * i0)), __fadd_rn(fy0, (float)(2 * i1))), gy2);   // :103
+                const nm_f2 nx2 = fma2(sn2, dy2, ax2), ny2 = fma2(cs2, dy2, ay2);                            // :104-105
+                const nm_f2 ux2 = sub2(nx2, half2v), uy2 = sub2(ny2, half2v);
+                float ux[2], uy[2];
+                upk2(ux2, ux[0], ux[1]); upk2(uy2, uy[0], uy[1]);
+                const float fx[2] = {floorf(ux[0]), floorf(ux[1])}, fy[2] = {floorf(uy[0]), floorf(uy[1])};   // :110-111
+                const nm_f2 rbx2 = sub2(nx2, add2(pk2(fx[0], fx[1]), half2v));                               // :113-114
+                const nm_f2 rby2 = sub2(ny2, add2(pk2(fy[0], fy[1]), half2v));
+                // theta = mod_2pi(angle - th0) (:100), nt = 8 theta / 2 pi (:107)
+                float th[2];
+                upk2(sub2(pk2(cur[i0].y, cur[i1].y), th2), th[0], th[1]);
+                th[0] = nm_mod_2pi_once(th[0]); th[1] = nm_mod_2pi_once(th[1]);
+                const nm_f2 nt2 = mul2(pk2(th[0], th[1]), pk2(1.2732395447351628f, 1.2732395447351628f));
+                float nt[2];
+                upk2(nt2, nt[0], nt[1]);
+                const float ft[2] = {floorf(nt[0]), floorf(nt[1])};
+                const nm_f2 rbt2 = sub2(nt2, pk2(ft[0], ft[1]));                                             // :115
+                const nm_f2 r22 = fma2(nx2, nx2, mul2(ny2, ny2));
+                float e[2];
+                upk2(mul2(r22, pk2(0.18033688011112042f, 0.18033688011112042f)), e[0], e[1]);
+                const nm_f2 wm2 = mul2(pk2(exp2f_approx(e[0]), exp2f_approx(e[1])), pk2(cur[i0].x, cur[i1].x));   // :108, :128-129
+                const nm_f2 a12 = mul2(wm2, rbx2), a02 = sub2(wm2, a12);
+                const nm_f2 w012 = mul2(a02, rby2), w002 = sub2(a02, w012);
+                const nm_f2 w112 = mul2(a12, rby2), w102 = sub2(a12, w112);
+                const nm_f2 at02 = sub2(one2, rbt2);
+                float w00[2], w01[2], w10[2], w11[2], at0[2], at1[2];
+                upk2(w002, w00[0], w00[1]); upk2(w012, w01[0], w01[1]); upk2(w102, w10[0], w10[1]); upk2(w112, w11[0], w11[1]);
+                upk2(at02, at0[0], at0[1]); upk2(rbt2, at1[0], at1[1]);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int i = 2 * ip + u;
+                    const int bx0 = (int)fx[u] + 2, by0 = (int)fy[u] + 2, bint = (int)ft[u];
+                    const bool act = vx && by + 2 * i <= ymax && (unsigned)(bx0 + 1) <= 4u && (unsigned)(by0 + 1) <= 4u;
+                    float* hp = hcopy + (by0 * 32 + bx0 * 8) * COPIES;
+                    float* h0 = hp + (bint & 7) * COPIES;
+                    float* h1 = hp + ((bint + 1) & 7) * COPIES;
+                    constexpr int OX = 8 * COPIES, OY = 32 * COPIES;
+                    const bool vx0 = (unsigned)bx0 < 4u, vx1 = (unsigned)(bx0 + 1) < 4u;
+                    const bool vy0 = (unsigned)by0 < 4u, vy1 = (unsigned)(by0 + 1) < 4u;
+                    const bool p00 = vx0 && vy0, p01 = vx0 && vy1, p10 = vx1 && vy0, p11 = vx1 && vy1;
+                    const nm_f2 at2 = pk2(at0[u], at1[u]);
+#pragma unroll
+                    for (int ph = 0; ph < 32 / COPIES; ++ph) {
+                        if (act && (COPIES == 32 || (lane / COPIES) == ph)) {
+                            // the two orientation bins of a cell as one packed FFMA: (v0, v1) += w * (at0, at1)
+                            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f;
+                            if (p00) { v0 = h0[0]; v1 = h1[0]; }
+                            if (p01) { v2 = h0[OY]; v3 = h1[OY]; }
+                            if (p10) { v4 = h0[OX]; v5 = h1[OX]; }
+                            if (p11) { v6 = h0[OX + OY]; v7 = h1[OX + OY]; }
+                            upk2(fma2(pk2(w00[u], w00[u]), at2, pk2(v0, v1)), v0, v1);                       // :135
+                            upk2(fma2(pk2(w01[u], w01[u]), at2, pk2(v2, v3)), v2, v3);
+                            upk2(fma2(pk2(w10[u], w10[u]), at2, pk2(v4, v5)), v4, v5);
+                            upk2(fma2(pk2(w11[u], w11[u]), at2, pk2(v6, v7)), v6, v7);
+                            if (p00) { h0[0] = v0; h1[0] = v1; }
+                            if (p01) { h0[OY] = v2; h1[OY] = v3; }
+                            if (p10) { h0[OX] = v4; h1[OX] = v5; }
+                            if (p11) { h0[OX + OY] = v6; h1[OX + OY] = v7; }
+                        }
+                        if (COPIES < 32) __syncwarp();
+                    }
+                }
+            }
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float dy = __fsub_rn(__fadd_rn(fy0, (float)(2 * i)), g.y);   // :103 (integers: the sum is exact)
@@ -519,23 +603,30 @@ int nm_describe_launch(const NmOctaveTable& tab, int batch, int capacity, const 
     if (once.first()) {
         NM_CUDA_TRY(cudaFuncSetAttribute(describe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         NM_CUDA_TRY(cudaFuncSetAttribute(describe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        NM_CUDA_TRY(cudaFuncSetAttribute((describe_fast_kernel<16, DE_WARPS>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
-        NM_CUDA_TRY(cudaFuncSetAttribute((describe_fast_kernel<32, DE_WARPS>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem32));
-        NM_CUDA_TRY(cudaFuncSetAttribute((describe_fast_kernel<32, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem32 / 2));
+        NM_CUDA_TRY(cudaFuncSetAttribute((describe_fast_kernel<16, DE_WARPS, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
+        NM_CUDA_TRY(cudaFuncSetAttribute((describe_fast_kernel<16, DE_WARPS, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
+        NM_CUDA_TRY(cudaFuncSetAttribute((describe_fast_kernel<32, DE_WARPS, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem32));
+        NM_CUDA_TRY(cudaFuncSetAttribute((describe_fast_kernel<32, DE_WARPS, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem32));
+        NM_CUDA_TRY(cudaFuncSetAttribute((describe_fast_kernel<32, 2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem32 / 2));
         once.done();
     }
-    // NM_DESCRIBE = 0: round-1 kernel, 16 (default): restructured kernel with 16 histogram copies, 32: with 32 (tuning aid;
-    // measured at 64 x 1080p: 2.26 / 1.86 / 1.98 ms)
-    static const int variant = getenv("NM_DESCRIBE") ? atoi(getenv("NM_DESCRIBE")) : 16;
+    // NM_DESCRIBE (tuning aid; 64 x 1080p): 0: round-1 kernel 2.26 ms; 16: restructured kernel, 16 histogram copies 1.87;
+    // 162 (default): the same with packed fp32 pairs 1.84; 32 / 323: 32 copies 1.98 / 2.03; 322: 32 copies in two-warp
+    // CTAs 1.97; register caps for 6 / 7 CTAs per SM: 1.88 - 2.28
+    static const int variant = getenv("NM_DESCRIBE") ? atoi(getenv("NM_DESCRIBE")) : 162;
     dim3 grid(nm_div_up(capacity, DE_WARPS), batch);
     if (exact)
         describe_kernel<true><<<grid, DE_WARPS * 32, smem, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
     else if (variant == 32)
-        describe_fast_kernel<32, DE_WARPS><<<grid, DE_WARPS * 32, smem32, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
+        describe_fast_kernel<32, DE_WARPS, false><<<grid, DE_WARPS * 32, smem32, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
     else if (variant == 322)          // 32 copies, two-warp CTAs: 14 instead of 12 warps per SM
-        describe_fast_kernel<32, 2><<<dim3(nm_div_up(capacity, 2), batch), 64, smem32 / 2, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
+        describe_fast_kernel<32, 2, false><<<dim3(nm_div_up(capacity, 2), batch), 64, smem32 / 2, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
     else if (variant == 16)
-        describe_fast_kernel<16, DE_WARPS><<<grid, DE_WARPS * 32, smem16, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
+        describe_fast_kernel<16, DE_WARPS, false><<<grid, DE_WARPS * 32, smem16, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
+    else if (variant == 162)          // 16 copies, packed fp32 pairs
+        describe_fast_kernel<16, DE_WARPS, true><<<grid, DE_WARPS * 32, smem16, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
+    else if (variant == 323)          // 32 copies, packed fp32 pairs
+        describe_fast_kernel<32, DE_WARPS, true><<<grid, DE_WARPS * 32, smem32, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
     else
         describe_kernel<false><<<grid, DE_WARPS * 32, smem, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
     NM_LAUNCH_CHECK();
