@@ -480,65 +480,37 @@ __device__ __forceinline__ void gradmap_rows(const float* __restrict__ p0, float
     }
 }
 
-template <int MINB, bool PREFETCH, int RSUB>
-__global__ void __launch_bounds__(256, MINB) gradmap_kernel(const NmOctave oc, int strips_x, int dense)
+// What was measured on 64 x 1080p frames (ms for the stage): 72 registers / 3 CTAs per SM 1.49; this version (64
+// registers, 4 CTAs) 1.32; 4- and 2-row sub-blocks at 5 - 8 CTAs (spilling) 1.34 - 1.53; prefetching the next block's
+// loads (117 registers, 2 CTAs) 1.87; TMA-staged 32 x 32 tiles in persistent CTAs (the layout of extrema_kernel) 1.57.
+// The kernel waits on its global loads (long-scoreboard 32 % of the stall samples): resident warps are what it needs.
+__global__ void __launch_bounds__(256, 4) gradmap_kernel(const NmOctave oc, int strips_x, int dense)
 {
     const int lane = threadIdx.x & 31;
     const int cb = (blockIdx.x % strips_x) * 8 + (threadIdx.x >> 5), rb0 = (blockIdx.x / strips_x) * 4;
     const int fl = blockIdx.y;                                  // frame * 3 + level
     const int w = oc.w, h = oc.h, pitch = oc.pitch, wpr = oc.wpr;
     const int x = cb * 32 + lane;
-    if (cb >= wpr) return;
+    if (cb >= wpr || x >= w) return;
     const int nrb = (h + NM_NEED_ROWS - 1) / NM_NEED_ROWS;
     const int f = fl / 3, l = fl - 3 * f;
     const unsigned char* __restrict__ need = oc.need + ((long long)fl * nrb) * wpr + cb;
     const float* __restrict__ src = oc.levels + ((long long)f * 6 + l + 1) * oc.level_elems + x;
     float2* __restrict__ G = oc.grad + (long long)fl * oc.level_elems + x;
     const bool intx = x >= 1 && x <= w - 2;
-    if (x >= w) return;
-
-    // block rb is "inner" when rows y0 - 1 .. y0 + 8 exist: nothing is predicated per row.  The +-1 column neighbours of
-    // the first / last column read a pad element or the neighbouring row (inside the level's allocation; the value is
-    // unused: those lanes store (0, 0)).  Pointer walk: one 64-bit add per row serves its three loads (immediate offsets).
-    auto wanted = [&](int rb) { return rb < nrb && (dense || need[rb * wpr] != 0); };
-    auto inner = [&](int rb) { return rb * NM_NEED_ROWS >= 1 && rb * NM_NEED_ROWS + NM_NEED_ROWS + 1 <= h; };
-    auto load_inner = [&](int rb, float (&ctr)[NM_NEED_ROWS + 2], float (&lf)[NM_NEED_ROWS], float (&rt)[NM_NEED_ROWS]) {
-        const float* __restrict__ p = src + (long long)(rb * NM_NEED_ROWS - 1) * pitch;
-        ctr[0] = __ldg(p);
-#pragma unroll
-        for (int j = 0; j < NM_NEED_ROWS; ++j) {
-            p += pitch;
-            lf[j] = __ldg(p - 1); ctr[j + 1] = __ldg(p); rt[j] = __ldg(p + 1);
-        }
-        ctr[NM_NEED_ROWS + 1] = __ldg(p + pitch);
-    };
-    // all eight gradients through the branch-free main path (their chains interleave), exact zeros (flat image areas)
-    // selected, the rare out-of-range arguments repaired afterwards
-    auto compute_inner = [&](int rb, const float (&ctr)[NM_NEED_ROWS + 2], const float (&lf)[NM_NEED_ROWS], const float (&rt)[NM_NEED_ROWS]) {
-        float2 g[NM_NEED_ROWS];
-        unsigned bad = 0;
-#pragma unroll
-        for (int j = 0; j < NM_NEED_ROWS; ++j) {
-            const float dx = __fsub_rn(rt[j], lf[j]), dy = __fsub_rn(ctr[j + 2], ctr[j]);
-            g[j] = nm_gradient_main(dx, dy);
-            const bool zero = dx == 0.f && dy == 0.f;                   // library result: (0, 0)
-            if (zero || !intx) g[j] = make_float2(0.f, 0.f);
-            if (!zero && intx && !nm_gradient_in_range(dx, dy)) bad |= 1u << j;
-        }
-        if (bad) {
-#pragma unroll
-            for (int j = 0; j < NM_NEED_ROWS; ++j)
-                if ((bad >> j) & 1u) g[j] = nm_gradient_lib(__fsub_rn(rt[j], lf[j]), __fsub_rn(ctr[j + 2], ctr[j]));
-        }
-        float2* __restrict__ q = G + (long long)(rb * NM_NEED_ROWS) * pitch;
-#pragma unroll
-        for (int j = 0; j < NM_NEED_ROWS; ++j) {
-            *q = g[j];
-            q += pitch;
-        }
-    };
-    auto border_block = [&](int rb) {
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        const int rb = rb0 + k;
+        if (rb >= nrb) break;
+        if (!dense && need[rb * wpr] == 0) continue;            // warp uniform
         const int y0 = rb * NM_NEED_ROWS;
+        if (y0 >= 1 && y0 + NM_NEED_ROWS + 1 <= h) {
+            // rows y0 - 1 .. y0 + 8 exist (all but the first and last row block of a level): nothing is predicated per row.
+            // The +-1 column neighbours of the first / last column read a pad element or the neighbouring row (inside
+            // the level's allocation; unused: those lanes store (0, 0)).
+            gradmap_rows<NM_NEED_ROWS>(src + (long long)y0 * pitch, G + (long long)y0 * pitch, pitch, intx);
+            continue;
+        }
         const float* __restrict__ p = src + (long long)y0 * pitch;
         float2* __restrict__ q = G + (long long)y0 * pitch;
         float ctr[NM_NEED_ROWS + 2], lf[NM_NEED_ROWS], rt[NM_NEED_ROWS];
@@ -564,154 +536,6 @@ __global__ void __launch_bounds__(256, MINB) gradmap_kernel(const NmOctave oc, i
                 q[j * pitch] = g;
             }
         }
-    };
-
-    if (PREFETCH) {
-        // the loads of the next wanted inner block are in flight while the current one is evaluated
-        float ca[NM_NEED_ROWS + 2], la[NM_NEED_ROWS], ra[NM_NEED_ROWS];
-        float cn[NM_NEED_ROWS + 2], ln[NM_NEED_ROWS], rn[NM_NEED_ROWS];
-        int cur = -1;
-#pragma unroll 1
-        for (int k = 0; k <= 4; ++k) {
-            const int rb = rb0 + k;
-            const bool go = k < 4 && wanted(rb);                    // warp uniform
-            if (go && !inner(rb)) { border_block(rb); continue; }
-            if (go) load_inner(rb, cn, ln, rn);
-            if (cur >= 0) compute_inner(cur, ca, la, ra);
-            cur = -1;
-            if (go) {
-                cur = rb;
-#pragma unroll
-                for (int j = 0; j < NM_NEED_ROWS + 2; ++j) ca[j] = cn[j];
-#pragma unroll
-                for (int j = 0; j < NM_NEED_ROWS; ++j) { la[j] = ln[j]; ra[j] = rn[j]; }
-            }
-        }
-        return;
-    }
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-        const int rb = rb0 + k;
-        if (rb >= nrb) break;
-        if (!wanted(rb)) continue;                              // warp uniform
-        if (inner(rb)) {
-            // RSUB rows at a time: fewer live registers (more resident warps) against a few more halo-row loads
-#pragma unroll 1
-            for (int r0 = 0; r0 < NM_NEED_ROWS; r0 += RSUB)
-                gradmap_rows<RSUB>(src + (long long)(rb * NM_NEED_ROWS + r0) * pitch, G + (long long)(rb * NM_NEED_ROWS + r0) * pitch, pitch, intx);
-        } else {
-            border_block(rb);
-        }
-    }
-}
-
-// Gradient maps from TMA-staged tiles: the layout of extrema_kernel (persistent CTAs, 32 x 32 tiles with a one-pixel
-// halo, the window of the next tile in flight while the current one is evaluated), for levels 1..3 only.  The loads
-// occupy neither registers nor load/store slots, the four neighbours of a pixel are shared-memory reads at immediate
-// offsets, and a tile none of whose twelve (level, 8-row block) need bytes is set is neither loaded nor visited.
-constexpr uint32_t GM_TILE_BYTES = 3u * EX_ROWS * EX_P * sizeof(float);     // 16 320
-constexpr int GM_BUF_STRIDE = 16384;                                        // TMA destinations are 128-byte aligned
-constexpr int GM_SMEM = 2 * GM_BUF_STRIDE + 64;
-
-__global__ void __launch_bounds__(256, 4) gradmap_tma_kernel(const NmOctave oc, const __grid_constant__ CUtensorMap tmap,
-                                                             int tiles_x, int tiles_y, int n_tiles, int dense)
-{
-    extern __shared__ __align__(128) unsigned char gm_smem[];
-    auto win = [&](int buf) { return reinterpret_cast<float (*)[EX_ROWS][EX_P]>(gm_smem + buf * GM_BUF_STRIDE); };   // [3][34][40]
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(gm_smem + 2 * GM_BUF_STRIDE);                      // [2]
-    unsigned* s_mask = reinterpret_cast<unsigned*>(s_bar + 2);                                       // [2]: bit l * 4 + k
-    const int tid = threadIdx.y * 32 + threadIdx.x, lane = threadIdx.x, wy = threadIdx.y;
-    const int nrb = (oc.h + NM_NEED_ROWS - 1) / NM_NEED_ROWS;
-    const int w = oc.w, h = oc.h, pitch = oc.pitch;
-
-    // need bits of a tile (thread 0 only) and, if any is set, the load of its window
-    auto prepare = [&](int tile, int buf) {
-        unsigned mask = 0;
-        if (tile < n_tiles) {
-            const int tx = tile % tiles_x, q = tile / tiles_x, ty = q % tiles_y, f = q / tiles_y;
-#pragma unroll
-            for (int l = 0; l < 3; ++l)
-#pragma unroll
-                for (int k = 0; k < EX_TH / NM_NEED_ROWS; ++k) {
-                    const int rb = ty * (EX_TH / NM_NEED_ROWS) + k;
-                    if (rb < nrb && (dense || oc.need[(((long long)f * 3 + l) * nrb + rb) * oc.wpr + tx] != 0)) mask |= 1u << (l * 4 + k);
-                }
-            if (mask) {
-                const uint32_t bar = ex_smem_u32(&s_bar[buf]);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(GM_TILE_BYTES) : "memory");
-                asm volatile(
-                    "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                    ::"r"(ex_smem_u32(win(buf))), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(tx * EX_TW - EX_HL),
-                      "r"(ty * EX_TH - 1), "r"(f * 6 + 1), "r"(bar) : "memory");
-            }
-        }
-        s_mask[buf] = mask;
-    };
-
-    int tile = blockIdx.x;
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ex_smem_u32(&s_bar[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ex_smem_u32(&s_bar[1])));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        prepare(tile, 0);
-    }
-    __syncthreads();
-    unsigned used0 = 0, used1 = 0;                 // loads consumed so far per buffer (mbarrier phase), same in every thread
-    for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
-        const int buf = it & 1;
-        // the other buffer was last read before the closing barrier of the previous iteration
-        if (tid == 0) prepare(tile + gridDim.x, buf ^ 1);
-        const unsigned mask = s_mask[buf];
-        if (mask) {
-            const unsigned parity = (buf ? used1 : used0) & 1u;
-            if (buf) ++used1; else ++used0;
-            asm volatile(
-                "{\n"
-                ".reg .pred p;\n"
-                "LAB_WAIT_%=:\n"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-                "@p bra LAB_DONE_%=;\n"
-                "bra LAB_WAIT_%=;\n"
-                "LAB_DONE_%=:\n"
-                "}\n" ::"r"(ex_smem_u32(&s_bar[buf])), "r"(parity) : "memory");
-            const int tx = tile % tiles_x, q = tile / tiles_x, ty = q % tiles_y, f = q / tiles_y;
-            const int gx = tx * EX_TW + lane, gy0 = ty * EX_TH + wy * 4;        // this thread: column gx, rows gy0 .. gy0 + 3
-            const int k = wy >> 1;                                              // its 8-row block inside the tile
-            const bool intx = gx >= 1 && gx <= w - 2;
-            const int c = lane + EX_HL, r0 = wy * 4 + 1;
-            if (gx < w && gy0 < h) {
-#pragma unroll
-                for (int l = 0; l < 3; ++l) {
-                    if (!((mask >> (l * 4 + k)) & 1u)) continue;                // warp uniform
-                    const float (*L)[EX_P] = win(buf)[l];
-                    float2 g[4];
-                    float dxs[4], dys[4];
-                    unsigned bad = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int r = r0 + j;
-                        const float dx = __fsub_rn(L[r][c + 1], L[r][c - 1]), dy = __fsub_rn(L[r + 1][c], L[r - 1][c]);
-                        dxs[j] = dx; dys[j] = dy;
-                        g[j] = nm_gradient_main(dx, dy);
-                        const int gy = gy0 + j;
-                        const bool interior = intx && gy >= 1 && gy <= h - 2;
-                        const bool zero = dx == 0.f && dy == 0.f;               // library result: (0, 0)
-                        if (zero || !interior) g[j] = make_float2(0.f, 0.f);
-                        if (!zero && interior && !nm_gradient_in_range(dx, dy)) bad |= 1u << j;
-                    }
-                    if (bad) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if ((bad >> j) & 1u) g[j] = nm_gradient_lib(dxs[j], dys[j]);
-                    }
-                    float2* __restrict__ q2 = oc.grad + ((long long)f * 3 + l) * oc.level_elems + (long long)gy0 * pitch + gx;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (gy0 + j < h) q2[j * pitch] = g[j];
-                }
-            }
-        }
-        __syncthreads();
     }
 }
 
@@ -972,18 +796,13 @@ __global__ void __launch_bounds__(256) collate_write_kernel(const float4* __rest
 
 } // namespace
 
-bool nm_gradmap_make_tma(CUtensorMap* map, const NmOctave& oc, int batch);
-
 bool nm_extrema_make_tma(NmBlurTma* t, const NmOctave& oc, int batch)
 {
     // (x, y, level of frame): 6 * batch planes of h rows
     const unsigned long long dims[3] = {(unsigned long long)oc.w, (unsigned long long)oc.h, 6ull * batch};
     const unsigned long long strides[2] = {(unsigned long long)oc.pitch * 4, (unsigned long long)oc.level_elems * 4};
     const unsigned box[3] = {EX_P, EX_ROWS, 6};
-    const bool ok = nm_tma_encode_3d(t, oc.levels, dims, strides, box);
-    // map_strip of this descriptor set = the three-level window of gradmap_tma_kernel (same tensor, box of 3 planes)
-    t->valid_strip = ok && nm_gradmap_make_tma(&t->map_strip, oc, batch);
-    return ok;
+    return nm_tma_encode_3d(t, oc.levels, dims, strides, box);
 }
 
 // Split pipeline (default): extrema_kernel here, gradmap_kernel after the compaction.  The fused round-1 kernel
@@ -1031,57 +850,14 @@ int nm_extrema_launch(const NmOctave& oc, int, int, const NmDetectParams& dp, in
     return NM_OK;
 }
 
-bool nm_gradmap_make_tma(CUtensorMap* map, const NmOctave& oc, int batch)
-{
-    // (x, y, level of frame) like nm_extrema_make_tma, box = the window of levels 1..3
-    NmBlurTma t;
-    const unsigned long long dims[3] = {(unsigned long long)oc.w, (unsigned long long)oc.h, 6ull * batch};
-    const unsigned long long strides[2] = {(unsigned long long)oc.pitch * 4, (unsigned long long)oc.level_elems * 4};
-    const unsigned box[3] = {EX_P, EX_ROWS, 3};
-    if (!nm_tma_encode_3d(&t, oc.levels, dims, strides, box)) return false;
-    *map = t.map;
-    return true;
-}
-
-int nm_gradmap_launch(const NmOctaveTable& tab, int batch, int dense, cudaStream_t stream, const NmBlurTma* ex_tma)
+int nm_gradmap_launch(const NmOctaveTable& tab, int batch, int dense, cudaStream_t stream)
 {
     if (batch * 3 > 65535) return NM_ERR_OVERFLOW;
-    // NM_GRADMAP (tuning aid; 64 x 1080p): 1 (default): direct loads, 64 registers, 4 CTAs / SM: 1.32 ms; 0: 72 registers,
-    // 3 CTAs: 1.49; 2: next block's loads prefetched, 117 registers: 1.87; 3..6: 4- / 2-row sub-blocks at 5..8 CTAs / SM:
-    // 1.34 .. 1.53 (the direct-load kernel waits on its global loads: resident warps are what it needs); 7: TMA-staged
-    // 32 x 32 tiles in persistent CTAs (gradmap_tma_kernel): 1.57 -- one barrier per tile and the uneven need bits of a
-    // tile's warps cost more than the load slots the bulk copies save
-    static const int variant = getenv("NM_GRADMAP") ? atoi(getenv("NM_GRADMAP")) : 1;
     for (int o = 0; o < tab.n_oct; ++o) {
         const NmOctave& oc = tab.o[o];
-        if (variant == 7 && ex_tma && ex_tma[o].valid_strip) {
-            static NmDeviceOnce once;
-            static std::atomic<int> ctas_cfg{4};
-            if (once.first()) {
-                int per_sm = 4;
-                NM_CUDA_TRY(cudaFuncSetAttribute(gradmap_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM));
-                NM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gradmap_tma_kernel, 256, GM_SMEM));
-                ctas_cfg.store(per_sm < 1 ? 1 : per_sm);
-                once.done();
-            }
-            const int tiles_x = nm_div_up(oc.w, EX_TW), tiles_y = nm_div_up(oc.h, EX_TH);
-            const long long n_tiles = (long long)tiles_x * tiles_y * batch;
-            if (n_tiles >= (1LL << 31)) return NM_ERR_OVERFLOW;
-            const long long cap = (long long)nm_sm_count() * ctas_cfg.load();
-            gradmap_tma_kernel<<<(unsigned)(n_tiles < cap ? n_tiles : cap), dim3(32, 8), GM_SMEM, stream>>>(
-                oc, ex_tma[o].map_strip, tiles_x, tiles_y, (int)n_tiles, dense);
-            NM_LAUNCH_CHECK();
-            continue;
-        }
         const int strips_x = nm_div_up(oc.wpr, 8), nrb = nm_div_up(oc.h, NM_NEED_ROWS);
         dim3 grid(strips_x * nm_div_up(nrb, 4), batch * 3);
-        if (variant == 0) gradmap_kernel<3, false, 8><<<grid, 256, 0, stream>>>(oc, strips_x, dense);
-        else if (variant == 2) gradmap_kernel<2, true, 8><<<grid, 256, 0, stream>>>(oc, strips_x, dense);
-        else if (variant == 3) gradmap_kernel<5, false, 4><<<grid, 256, 0, stream>>>(oc, strips_x, dense);
-        else if (variant == 4) gradmap_kernel<6, false, 4><<<grid, 256, 0, stream>>>(oc, strips_x, dense);
-        else if (variant == 5) gradmap_kernel<8, false, 2><<<grid, 256, 0, stream>>>(oc, strips_x, dense);
-        else if (variant == 6) gradmap_kernel<6, false, 2><<<grid, 256, 0, stream>>>(oc, strips_x, dense);
-        else gradmap_kernel<4, false, 8><<<grid, 256, 0, stream>>>(oc, strips_x, dense);
+        gradmap_kernel<<<grid, 256, 0, stream>>>(oc, strips_x, dense);
         NM_LAUNCH_CHECK();
     }
     return NM_OK;

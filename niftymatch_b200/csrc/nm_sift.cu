@@ -401,7 +401,7 @@ static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, in
     if (timing) cudaEventRecord(c->ev[3], st);
     // ---- gradient maps of the marked blocks ----------------------------------------------
     if (!fused) {
-        if ((rc = nm_gradmap_launch(tab, n, c->dense_grad, st, ts->ex)) != NM_OK) return rc;
+        if ((rc = nm_gradmap_launch(tab, n, c->dense_grad, st)) != NM_OK) return rc;
         launches += c->n_oct;
     }
     if (timing) cudaEventRecord(c->ev[4], st);

@@ -56,8 +56,7 @@ int nm_extrema_launch(const NmOctave& oc, int octave_index, int n_oct, const NmD
 // true when nm_extrema_launch takes the fused round-1 kernel (which also writes dense gradient maps) for this source
 bool nm_extrema_is_fused(const NmBlurTma* tma);
 // gradient maps of levels 1..3 for all octaves; dense = 0: only the blocks marked in NmOctave::need
-// ex_tma: the per-octave descriptors of nm_extrema_make_tma (their map_strip is the gradient window), or null
-int nm_gradmap_launch(const NmOctaveTable& tab, int batch, int dense, cudaStream_t stream, const NmBlurTma* ex_tma = nullptr);
+int nm_gradmap_launch(const NmOctaveTable& tab, int batch, int dense, cudaStream_t stream);
 int nm_rank_launch(const NmOctaveTable& tab, int batch, int* seg_raw, cudaStream_t stream);
 int nm_plan_launch(const int* seg_raw, int* seg_cnt, int* seg_off, int* counts, int n_oct, int batch,
                    int capacity, cudaStream_t stream);
