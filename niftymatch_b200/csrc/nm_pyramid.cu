@@ -443,6 +443,269 @@ __global__ void __launch_bounds__(kThreads, 2) blur_strip_kernel(const NmBlurArg
     }
 }
 
+// ---- streaming variant: warp-specialised, no CTA-wide barrier in the steady state ---------------
+// blur_strip_kernel's CTAs alternate a row-pass phase and a column-pass phase between __syncthreads(): every phase
+// opens with a burst of shared-memory loads and closes with a burst of stores, and all warps of a CTA reach them
+// together, so the FMA pipe -- the unit that bounds the blur -- idles 40-50 % of the time (ncu, round 2).  Here a CTA
+// of four warps walks down a 128-column strip in GROUPS of kGR rows with the two passes running concurrently:
+//   producers (2 warps)  row pass of group n from TMA stage n % kNS into ring slot n % kNG; lane 0 of the first one
+//                        also issues the TMA loads, kNS - 1 groups ahead
+//   consumers (2 warps)  column pass in SCATTER form: a lane owns one column pair and walks down the rows holding
+//                        the 2R+1 outputs in flight in registers -- input row i adds in[i] * t[2R-kk] to output
+//                        i - kk for kk = 0..2R, so every output still accumulates its taps in the reference's order
+//                        (bitwise the reference), each row-pass value is read from shared memory exactly once
+//                        (one LDS.64 per 2R+1 FFMA2), and one output row completes per input row
+// with mbarrier full/empty pairs per stage and per ring slot as the only synchronisation.  Work split, halo reuse
+// through L2 and the piece rule are blur_strip_kernel's, in units of groups; a piece that starts inside a strip is
+// preceded by ceil(2R / kGR) groups whose outputs are not stored (they fill the accumulators).
+// Measured (64 x 1080p, B200; pyramid stage of the step, blur_strip_kernel = 2.25 ms):
+//   8-row groups, 3 + 3 buffers, roles rotating over the SM sub-partitions   2.29 ms
+//   the same, fixed roles (warps 0-1 produce, 2-3 consume in every CTA)       2.18 ms   (each sub-partition's
+//                                                                             instruction cache sees one role)
+//   16-row groups, 2 + 2 buffers                                              2.06 ms   (half the hand-overs)
+//   deeper rings (3 or 4 slots) or 3 stages: no change / slower (fewer resident CTAs)
+// Per launch (octave 0, ncu): R = 5 192 us, 7 215, 8 (+ decimated copy) 269, 10 261, 13 326 against
+// 216 / 245 / 282 / 303 / 368 for blur_strip_kernel; the HBM floor of a level is 165 us, the FMA floor of R = 13 192 us.
+#ifndef NM_STREAM_GR
+#define NM_STREAM_GR 16
+#define NM_STREAM_NS 2
+#define NM_STREAM_NG 2
+#endif
+constexpr int kGR = NM_STREAM_GR;  // rows per group (8 or 16)
+constexpr int kNS = NM_STREAM_NS;  // TMA stages
+constexpr int kNG = NM_STREAM_NG;  // ring slots (2 + 2 of 16 rows: 38 KB of shared memory per CTA, 5 CTAs per SM)
+constexpr int kStreamThreads = 128;
+constexpr int kStreamPieces = 32;  // pieces per CTA the schedule table holds
+constexpr int kStreamMaxR = 13;    // 2R+1 float2 accumulators + the row-pass window fit 128 registers up to here
+__host__ __device__ constexpr int stream_smem_bytes(int R)
+{
+    return (kNS * kGR * in_pitch(R) + kNG * kGR * kRowPitch) * (int)sizeof(float) + 2 * (kNS + kNG) * 8 +
+           kStreamPieces * 32 + 128;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct StreamPiece { int gs, g0, g1, c, tx, f, pad0, pad1; };
+struct StreamTaps { float v[33]; };      // by value: kernel parameters live in the constant bank, which the warp-
+                                          // specialised code can name as an FFMA operand (taps loaded from global memory
+                                          // ended up in 2R+1 ordinary registers there and spilled for R >= 11)   // groups [gs, g1) are walked, [g0, g1) are owned
+
+struct StreamWalk {
+    int g, g0, g1, ri, c, tx, f;
+    bool valid;
+    __device__ __forceinline__ void enter(const StreamPiece* tab, int n_pieces)
+    {
+        valid = ri < n_pieces;
+        if (!valid) return;
+        const int4 a = *reinterpret_cast<const int4*>(&tab[ri].gs);
+        const int2 b = *reinterpret_cast<const int2*>(&tab[ri].tx);
+        g = a.x; g0 = a.y; g1 = a.z; c = a.w; tx = b.x; f = b.y;
+    }
+    __device__ __forceinline__ void next(const StreamPiece* tab, int n_pieces, int cg, int tiles_x)
+    {
+        if (++g < g1) {
+            if (++c == cg) { c = 0; if (++tx == tiles_x) { tx = 0; ++f; } }
+        } else { ++ri; enter(tab, n_pieces); }
+    }
+};
+
+// one row-pass item: 8 outputs of one row (the arithmetic of strip_row_pass)
+template <int R>
+__device__ __forceinline__ void stream_row_item(const float* __restrict__ in, float* __restrict__ out,
+                                                const float* __restrict__ t)
+{
+    constexpr int SH = radius_aligned(R) - R, NT = 2 * R + 1;
+    constexpr int P = 8;
+    constexpr int NV = (SH + P + 2 * R + 3) / 4;
+    float wv[NV * 4 + 1];
+    const float4* p4 = reinterpret_cast<const float4*>(in);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const float4 q = p4[j];
+        wv[4 * j] = q.x; wv[4 * j + 1] = q.y; wv[4 * j + 2] = q.z; wv[4 * j + 3] = q.w;
+    }
+    wv[NV * 4] = 0.f;
+    float acc[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NT; ++kk) {
+        if (((SH + kk) & 1) == 0) {
+#pragma unroll
+            for (int j = 0; j < P / 2; ++j) {
+                const float2 d = nm_ffma2(make_float2(wv[SH + 2 * j + kk], wv[SH + 2 * j + kk + 1]), t[2 * R - kk],
+                                          make_float2(acc[2 * j], acc[2 * j + 1]));
+                acc[2 * j] = d.x; acc[2 * j + 1] = d.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < P; ++j) acc[j] = __fmaf_rn(wv[SH + j + kk], t[2 * R - kk], acc[j]);
+        }
+    }
+    float4* o4 = reinterpret_cast<float4*>(out);
+    o4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+__host__ __device__ constexpr int stream_min_ctas(int R) { return R <= 10 ? 5 : 4; }
+
+template <int R, bool DST2>
+__global__ void __launch_bounds__(kStreamThreads, stream_min_ctas(R)) blur_stream_kernel(const NmBlurArgs a, const __grid_constant__ CUtensorMap tmap,
+                                                                         const __grid_constant__ StreamTaps taps,
+                                                                         int tiles_x, int cg, int full_rounds, int total,
+                                                                         int rot_div)
+{
+    constexpr int RA = radius_aligned(R), IP = in_pitch(R), NT = 2 * R + 1;
+    constexpr int PRE = (2 * R + kGR - 1) / kGR;
+    extern __shared__ __align__(128) float smem[];
+    float* s_in = smem;                                  // [kNS][kGR][IP]
+    float* s_ring = smem + kNS * kGR * IP;               // [kNG][kGR][kRowPitch]
+    uint64_t* in_full = reinterpret_cast<uint64_t*>(s_ring + kNG * kGR * kRowPitch);
+    uint64_t* in_empty = in_full + kNS;
+    uint64_t* ring_full = in_empty + kNS;
+    uint64_t* ring_empty = ring_full + kNG;
+    StreamPiece* tab = reinterpret_cast<StreamPiece*>(ring_empty + kNG);
+    __shared__ int s_steps;
+    __shared__ float s_taps[NT];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < NT) s_taps[tid] = taps.v[tid];
+    const int n_pieces = full_rounds + 1;                // <= kStreamPieces (launcher); the last one may be empty
+    if (tid < n_pieces) {
+        const long long G = gridDim.x, rem0 = (long long)full_rounds * G * cg, rem = total - rem0;
+        long long g0, g1;
+        if (tid < full_rounds) { g0 = ((long long)tid * G + blockIdx.x) * cg; g1 = g0 + cg; }
+        else { g0 = rem0 + rem * blockIdx.x / G; g1 = rem0 + rem * (blockIdx.x + 1) / G; }
+        const int s = (int)(g0 / cg), c0 = (int)(g0 - (long long)s * cg), pre = min(PRE, c0);
+        StreamPiece p;
+        p.gs = (int)g0 - pre; p.g0 = (int)g0; p.g1 = (int)g1; p.c = c0 - pre; p.tx = s % tiles_x; p.f = s / tiles_x;
+        p.pad0 = p.pad1 = 0;
+        if (g0 >= g1) p.gs = p.g0 = p.g1 = 0;            // empty remainder piece: no steps
+        tab[tid] = p;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kNS; ++i) { mbar_init(in_full + i, 1); mbar_init(in_empty + i, 2); }
+        for (int i = 0; i < kNG; ++i) { mbar_init(ring_full + i, 2); mbar_init(ring_empty + i, 2); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int n = 0;
+        for (int i = 0; i < n_pieces; ++i) n += tab[i].g1 - tab[i].gs;
+        s_steps = n;
+    }
+    __syncthreads();
+    const int n_steps = s_steps;
+    if (n_steps == 0) return;
+    // an empty remainder piece is always the last one: walking stops there
+    const int live_pieces = (tab[n_pieces - 1].g1 > tab[n_pieces - 1].gs) ? n_pieces : n_pieces - 1;
+
+    const float* __restrict__ t = taps.v;
+
+    // roles rotate with the CTA's residency slot so that every SM sub-partition hosts both kinds of warp
+    const int role = ((tid >> 5) + (blockIdx.x / rot_div)) & 3;
+    if (role < 2) {
+        // ---------------- producer: row pass ----------------
+        StreamWalk wi;                                    // TMA cursor (meaningful in role 0 only)
+        wi.ri = 0; wi.enter(tab, live_pieces);
+        int issued = 0;
+        auto issue = [&]() {
+            const int slot = issued % kNS, use = issued / kNS;
+            if (lane == 0) {
+                if (use >= 1) mbar_wait(in_empty + slot, (use - 1) & 1);
+                mbar_expect_tx(in_full + slot, kGR * IP * (uint32_t)sizeof(float));
+                tma_load_3d(s_in + slot * kGR * IP, &tmap, in_full + slot, wi.tx * kTW - RA, wi.c * kGR - R, wi.f);
+            }
+            wi.next(tab, live_pieces, cg, tiles_x);
+            ++issued;
+        };
+        if (role == 0)
+            for (int i = 0; i < kNS - 1 && issued < n_steps; ++i) issue();
+        const int r = lane & (kGR - 1), xs0 = lane / kGR + (32 / kGR) * role;   // items: rows r, segments xs0 + (64 / kGR) k
+        for (int n = 0; n < n_steps; ++n) {
+            if (role == 0) {
+                if (issued < n_steps) issue();
+                __syncwarp();
+            }
+            const int slot = n % kNS, q = n % kNG;
+            mbar_wait(in_full + slot, (n / kNS) & 1);
+            if (n >= kNG) mbar_wait(ring_empty + q, ((n / kNG) - 1) & 1);
+            const float* in = s_in + (slot * kGR + r) * IP + xs0 * 8;
+            float* out = s_ring + (q * kGR + r) * kRowPitch + xs0 * 8;
+#pragma unroll 1
+            for (int k = 0; k < kGR / 4; ++k) stream_row_item<R>(in + (512 / kGR) * k, out + (512 / kGR) * k, t);
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(in_empty + slot); mbar_arrive(ring_full + q); }
+        }
+    } else {
+        // ---------------- consumer: column pass, scatter form ----------------
+        // The 2R+1 accumulators rotate through the roles "starts with this row" ... "completes with this row", so the
+        // row step is unrolled 2R+1 times with static register names (NM_STREAM_STEP(U): the step in which acc[U]
+        // starts).  A group is 8 rows and 2R+1 is odd, so a group begins at any phase: the group loop re-enters the
+        // unrolled sequence through a switch (Duff's device).  The group hand-over is outside the sequence, which
+        // keeps the hot code contiguous and at (2R+1) x ~38 instructions within the 32 KB instruction cache -- inlined
+        // into every step it was 53 KB for R = 13 and 18 % of the warp samples were instruction-fetch stalls.
+        const int cp = (role - 2) * 32 + lane;
+        StreamWalk wk;
+        wk.ri = 0; wk.enter(tab, live_pieces);
+        float2 acc[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[j] = make_float2(0.f, 0.f);
+        // taps in ordinary registers, read from shared memory so that the compiler cannot re-materialise them: as
+        // parameters it re-read them into uniform registers in every step of the switch (8 LDCU per 27 FFMA2)
+        float tr[NT];
+#pragma unroll
+        for (int k = 0; k < NT; ++k) tr[k] = s_taps[k];
+        int phase = 0;
+        for (int n = 0; n < n_steps; ++n) {
+            const int q = n % kNG;
+            mbar_wait(ring_full + q, (n / kNG) & 1);
+            const float* rp = s_ring + (q * kGR) * kRowPitch + 2 * cp;   // current input row, this lane's column pair
+            const int gx = wk.tx * kTW + 2 * cp;                         // even, and so is a.w (launcher): gx + 1 < a.w too
+            const int ylim = (wk.g >= wk.g0 && gx < a.w) ? a.h : 0;      // this lane stores rows 0 <= y < ylim
+            int y = wk.c * kGR - 2 * R;                                  // the output row that completes with the current input row
+            float* orow = a.dst + (long long)wk.f * a.dst_fstride + (long long)y * a.dst_pitch + gx;
+            const int half_pitch2 = a.dst2_pitch >> 1;                   // dst2_pitch is even (launcher)
+            float* o2half = DST2 ? a.dst2 + (long long)wk.f * a.dst2_fstride + (long long)y * half_pitch2 + (gx >> 1)
+                                 : nullptr;                              // &dst2[f][y / 2][gx / 2] when y is even
+            float2 v = *reinterpret_cast<const float2*>(rp);
+            int left = kGR;
+#define NM_STREAM_STEP(U)                                                                                              \
+            case U:                                                                                                    \
+                if constexpr (U < NT) {                                                                                \
+                    /* the row after the group's last one is read too (inside the buffer) and never used */          \
+                    const float2 vn = *reinterpret_cast<const float2*>(rp + kRowPitch);                                \
+                    acc[U] = nm_ffma2(v, tr[2 * R], make_float2(0.f, 0.f));                                            \
+                    _Pragma("unroll") for (int kk = 1; kk < NT; ++kk)                                                  \
+                        acc[(U - kk + NT) % NT] = nm_ffma2(v, tr[2 * R - kk], acc[(U - kk + NT) % NT]);                \
+                    if ((unsigned)y < (unsigned)ylim) *reinterpret_cast<float2*>(orow) = acc[(U + 1) % NT];            \
+                    if (DST2) {              /* o2half advances half a decimated row per row: right on even y */     \
+                        if (!(y & 1) && (unsigned)y < (unsigned)(ylim & ~1)) *o2half = acc[(U + 1) % NT].x;            \
+                        o2half += half_pitch2;                                                                         \
+                    }                                                                                                  \
+                    ++y; orow += a.dst_pitch; rp += kRowPitch; v = vn;                                                 \
+                    if (--left == 0) { phase = (U + 1) % NT; break; }                                                  \
+                }
+            switch (phase) {
+                for (;;) {
+                    NM_STREAM_STEP(0) NM_STREAM_STEP(1) NM_STREAM_STEP(2) NM_STREAM_STEP(3) NM_STREAM_STEP(4)
+                    NM_STREAM_STEP(5) NM_STREAM_STEP(6) NM_STREAM_STEP(7) NM_STREAM_STEP(8) NM_STREAM_STEP(9)
+                    NM_STREAM_STEP(10) NM_STREAM_STEP(11) NM_STREAM_STEP(12) NM_STREAM_STEP(13) NM_STREAM_STEP(14)
+                    NM_STREAM_STEP(15) NM_STREAM_STEP(16) NM_STREAM_STEP(17) NM_STREAM_STEP(18) NM_STREAM_STEP(19)
+                    NM_STREAM_STEP(20) NM_STREAM_STEP(21) NM_STREAM_STEP(22) NM_STREAM_STEP(23) NM_STREAM_STEP(24)
+                    NM_STREAM_STEP(25) NM_STREAM_STEP(26)
+                }
+            }
+#undef NM_STREAM_STEP
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ring_empty + q);
+            wk.next(tab, live_pieces, cg, tiles_x);
+        }
+    }
+}
+
 template <int R, bool TMA>
 __global__ void __launch_bounds__(kThreads, 2) blur_tile_kernel(const NmBlurArgs a, const __grid_constant__ CUtensorMap tmap)
 {
@@ -546,6 +809,26 @@ bool strip_eligible(const NmBlurArgs& a, const NmBlurTma* tma)
     return total >= strip_min && strips < (1LL << 31);
 }
 
+// The streaming kernel takes what the strip kernel takes when the destination allows 8-byte stores, the source is
+// float (BGRA conversion stays with the strip kernel) and the CTA's piece table fits.  NM_BLUR_STREAM=0 disables it.
+int stream_ctas_per_sm(int R)
+{
+    static const int cap = getenv("NM_BLUR_STREAM_CTAS") ? atoi(getenv("NM_BLUR_STREAM_CTAS")) : 8;   // tuning aid
+    const int n = stream_min_ctas(R);
+    return cap < 1 ? 1 : n > cap ? cap : n;
+}
+bool stream_eligible(const NmBlurArgs& a, const NmBlurTma* tma)
+{
+    static const bool off = getenv("NM_BLUR_STREAM") != nullptr && atoi(getenv("NM_BLUR_STREAM")) == 0;
+    if (off || !strip_eligible(a, tma) || !tma->valid_stream || a.src_bgra || a.taps_host == nullptr) return false;
+    if (a.radius > kStreamMaxR || (a.w & 1)) return false;
+    if ((a.dst_pitch & 1) || (a.dst_fstride & 1) || (reinterpret_cast<uintptr_t>(a.dst) & 7)) return false;
+    if (a.dst2 != nullptr && (a.dst2_pitch & 1)) return false;
+    const long long strips = (long long)nm_div_up(a.w, kTW) * a.batch, G = (long long)stream_ctas_per_sm(a.radius) * sm_count();
+    const long long total = strips * nm_div_up(a.h + 2 * a.radius, kGR);
+    return total < (1LL << 31) && strips / G + 1 <= kStreamPieces;
+}
+
 template <int R>
 int launch_tile(const NmBlurArgs& a, cudaStream_t stream, const NmBlurTma* tma)
 {
@@ -567,6 +850,31 @@ int launch_tile(const NmBlurArgs& a, cudaStream_t stream, const NmBlurTma* tma)
         static const bool no_walk = getenv("NM_BLUR_TILE") != nullptr;        // tuning aid
         const int chunks = nm_div_up(a.h + 2 * R, kCH);
         const long long total = (long long)grid.x * a.batch * chunks;
+        if constexpr (R <= kStreamMaxR) if (stream_eligible(a, tma)) {
+            static NmDeviceOnce once_stream;
+            if (once_stream.first()) {
+                NM_CUDA_TRY(cudaFuncSetAttribute(blur_stream_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 stream_smem_bytes(R)));
+                NM_CUDA_TRY(cudaFuncSetAttribute(blur_stream_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 stream_smem_bytes(R)));
+                once_stream.done();
+            }
+            const long long n_strips = (long long)grid.x * a.batch;
+            const int cg = nm_div_up(a.h + 2 * R, kGR), G = stream_ctas_per_sm(R) * n_sms;
+            static const int rot_env = getenv("NM_BLUR_STREAM_ROT") ? atoi(getenv("NM_BLUR_STREAM_ROT")) : 0;   // tuning aid
+            const int rot_div = rot_env > 0 ? rot_env : (1 << 30);
+            StreamTaps tp;
+            memset(&tp, 0, sizeof(tp));
+            memcpy(tp.v, a.taps_host, sizeof(float) * (2 * R + 1));
+            if (a.dst2 != nullptr)
+                blur_stream_kernel<R, true><<<G, kStreamThreads, stream_smem_bytes(R), stream>>>(
+                        a, tma->map_stream, tp, (int)grid.x, cg, (int)(n_strips / G), (int)(n_strips * cg), rot_div);
+            else
+                blur_stream_kernel<R, false><<<G, kStreamThreads, stream_smem_bytes(R), stream>>>(
+                    a, tma->map_stream, tp, (int)grid.x, cg, (int)(n_strips / G), (int)(n_strips * cg), rot_div);
+            NM_LAUNCH_CHECK();
+            return NM_OK;
+        }
         if (strip_eligible(a, tma)) {
             const long long n_strips = (long long)grid.x * a.batch;
             blur_strip_kernel<R><<<2 * n_sms, kThreads, strip_smem_bytes(R), stream>>>(a, tma->map_strip, (int)grid.x, chunks,
@@ -637,7 +945,7 @@ __global__ void gradient_kernel(const float* __restrict__ src, float2* __restric
 bool nm_tma_encode_3d(NmBlurTma* t, const float* base, const unsigned long long dims[3],
                       const unsigned long long strides_bytes[2], const unsigned box[3])
 {
-    t->valid = t->valid_strip = false;
+    t->valid = t->valid_strip = t->valid_stream = false;
     if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides_bytes[0] & 15) || (strides_bytes[1] & 15)) return false;
     EncodeTiledFn enc = get_encoder();
     if (!enc) return false;
@@ -658,7 +966,7 @@ bool nm_blur_make_tma(NmBlurTma* t, const float* src, int w, int h, int pitch, l
                       int batch, int radius, bool words_u32)
 {
     const CUtensorMapDataType dtype = words_u32 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    t->valid = t->valid_strip = false;
+    t->valid = t->valid_strip = t->valid_stream = false;
     if (radius < 1 || radius > 16 || w <= 0 || h <= 0 || batch <= 0) return false;
     if ((reinterpret_cast<uintptr_t>(src) & 15) || (pitch & 3) || (batch > 1 && (fstride & 3))) return false;
     EncodeTiledFn enc = get_encoder();
@@ -677,6 +985,11 @@ bool nm_blur_make_tma(NmBlurTma* t, const float* src, int w, int h, int pitch, l
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         t->valid_strip = (r == CUDA_SUCCESS);
+        const cuuint32_t box_stream[3] = {(cuuint32_t)in_pitch(radius), (cuuint32_t)kGR, 1};
+        r = enc(&t->map_stream, dtype, 3, const_cast<float*>(src), dims, strides, box_stream, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        t->valid_stream = (r == CUDA_SUCCESS);
     }
     return t->valid;
 }

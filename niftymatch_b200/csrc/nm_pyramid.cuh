@@ -7,6 +7,7 @@ struct NmBlurArgs {
     const float* src;       // [batch][h][src_pitch]
     float*       dst;       // [batch][h][dst_pitch]
     const float* taps;      // device, 2R+1 floats
+    const float* taps_host; // the same values in host memory, or null (the streaming kernel takes them as parameters)
     float*       dst2;      // optional decimated copy dst2[y/2][x/2] (next octave base), or null
     float*       scratch;   // only for the generic (R > 16) path: [batch][h][w]
     long long    src_fstride, dst_fstride, dst2_fstride;   // floats between frames
@@ -22,6 +23,8 @@ struct NmBlurTma {
     bool        valid;
     CUtensorMap map_strip;      // same tensor, box of 64 rows: the strip-walking kernel's chunk
     bool        valid_strip;
+    CUtensorMap map_stream;     // same tensor, box of 8 rows: one stage of the streaming kernel
+    bool        valid_stream;
 };
 // Returns false when the source cannot be described to TMA (pointer / pitch not 16-byte
 // aligned, radius outside the tiled kernel's range): the caller then uses the plain-load

@@ -39,6 +39,7 @@ struct nm_sift_ctx {
         unsigned long long mask = 0;
     } stage_graph[NM_MAX_CHUNKS];
     float* taps[6];          // 0: base kernel, 1..5: level kernels (device)
+    float  taps_host[6][96]; // the same values on the host (kernel parameters of the streaming blur)
     int    radii[6];
     int *seg_raw, *seg_cnt, *seg_off, *counts, *meta;
     float4* kpts;
@@ -219,7 +220,7 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
     int rc = NM_OK;
     // Gaussian kernels
     for (int i = 0; i < 6 && rc == NM_OK; ++i) {
-        float host[96];
+        float* host = c->taps_host[i];
         rc = nm_gaussian_taps(i == 0 ? P.base_smooth : P.sigmas[i - 1], host, &c->radii[i]);
         if (rc != NM_OK) break;
         rc = dev_alloc(c, &c->taps[i], 96);
@@ -347,7 +348,7 @@ static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, in
             NmBlurArgs a{};
             a.src = frames_dev; a.src_pitch = P.width; a.src_fstride = (long long)P.width * P.height;
             a.dst = oc.levels; a.dst_pitch = oc.pitch; a.dst_fstride = fstride;
-            a.taps = c->taps[0]; a.radius = c->radii[0]; a.w = oc.w; a.h = oc.h; a.batch = n;
+            a.taps = c->taps[0]; a.taps_host = c->taps_host[0]; a.radius = c->radii[0]; a.w = oc.w; a.h = oc.h; a.batch = n;
             a.scratch = c->scratch ? c->scratch + (long long)first * P.width * P.height : nullptr;
             NmBlurTma base;
             nm_blur_make_tma(&base, frames_dev, P.width, P.height, P.width, (long long)P.width * P.height, n, c->radii[0], bgra);
@@ -367,7 +368,8 @@ static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, in
             NmBlurArgs a{};
             a.src = oc.levels + i * oc.level_elems; a.src_pitch = oc.pitch; a.src_fstride = fstride;
             a.dst = oc.levels + (i + 1) * oc.level_elems; a.dst_pitch = oc.pitch; a.dst_fstride = fstride;
-            a.taps = c->taps[i + 1]; a.radius = c->radii[i + 1]; a.w = oc.w; a.h = oc.h; a.batch = n;
+            a.taps = c->taps[i + 1]; a.taps_host = c->taps_host[i + 1]; a.radius = c->radii[i + 1]; a.w = oc.w; a.h = oc.h;
+            a.batch = n;
             a.scratch = c->scratch ? c->scratch + (long long)first * P.width * P.height : nullptr;
             if (i + 1 == P.num_dog_levels && o + 1 < c->n_oct) {
                 // level 3 (sigma doubled) decimated by 2 = next octave's level 0 (downsample.cu:15-16)

@@ -363,6 +363,29 @@ def test_1080p_batch_strip_blur_vs_oracle(nm, oracle):
         assert_frame_matches(out[f], ref[f % 2])
 
 
+def test_stream_blur_piece_table_many_small_frames(nm, oracle):
+    """800 frames of 128 x 199 = 800 one-strip launches for the streaming blur kernel (nm_pyramid.cu,
+    blur_stream_kernel): with 740 persistent CTAs that is one round of whole strips plus 60 strips split into pieces
+    shorter than a 16-row group (most CTAs get an empty piece, the others start inside a strip behind lead-in
+    groups); the odd height exercises the last row of the decimated second output.  Sampled frames, all levels of
+    both octaves bitwise against the CPU oracle."""
+    w, h, n = 128, 199, 800
+    scenes = [synth.scene(w, h, synth.SEED_BASE + 40 + i) for i in range(4)]
+    frames = np.stack([scenes[i % 4] for i in range(n)])
+    P = nm.SiftParams(w, h)
+    sb = nm.SiftBatch(P, n, 2048)
+    sb.run(_cu(frames))
+    torch.cuda.synchronize()
+    ref = [oracle.sift_frame(s, capacity=2048) for s in scenes]
+    counts = sb.results()["counts"].cpu().numpy()
+    assert np.array_equal(counts, np.array([ref[i % 4]["n"] for i in range(n)]))
+    for f in (0, 1, 2, 3, 368, 369, 370, 738, 739, 740, 741, 742, 770, 797, 798, 799):
+        for o in range(P._num_octaves):
+            for l in range(6):
+                assert np.array_equal(sb.level(f, o, l).cpu().numpy(), ref[f % 4]["levels"][o][l]), (f, o, l)
+    sb.close()
+
+
 def test_wide_blur_radius_in_the_batched_path(nm, oracle):
     """SiftParams members are mutable and the reference accepts kernels up to 91 taps (radius 45): a level sigma
     above 4 gives a radius above 16, which the tiled TMA blur does not cover -- the batched path then runs the generic
@@ -436,15 +459,18 @@ def test_fused_extrema_fallback_parity_suite():
     assert " passed" in r.stdout
 
 
-def test_forced_strip_blur_parity_suite():
-    """The strip-walking blur is only chosen for large launches; NM_BLUR_STRIP_MIN=1 forces it for every
+@pytest.mark.parametrize("stream", ["1", "0"])
+def test_forced_strip_blur_parity_suite(stream):
+    """The strip-walking blur kernels are only chosen for large launches; NM_BLUR_STRIP_MIN=1 forces them for every
     TMA-describable source, and the blur / SIFT parity tests are re-run that way in a child process
-    (ranges that start inside a strip, one-chunk strips, 1-row images, the decimated second output)."""
+    (ranges that start inside a strip, one-chunk strips, 1-row images, the decimated second output).
+    stream=1: the SIFT pyramid takes blur_stream_kernel (warp-specialised) and nm_blur_f32 blur_strip_kernel;
+    stream=0 (NM_BLUR_STREAM=0): blur_strip_kernel everywhere."""
     import subprocess
     import sys
     if os.environ.get("NM_BLUR_STRIP_MIN"):
         pytest.skip("already the forced run")
-    env = dict(os.environ, NM_BLUR_STRIP_MIN="1")
+    env = dict(os.environ, NM_BLUR_STRIP_MIN="1", NM_BLUR_STREAM=stream)
     sel = ("test_blur_vs_oracle_bitwise or test_blur_vs_reference_golden or test_sift_vs_oracle or "
            "test_sift_vs_reference_golden or test_4k_six_octave or test_forced_octave_count")
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", __file__, "-k", sel],
