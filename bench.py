@@ -555,7 +555,7 @@ def main():
                     "algorithmic_bytes": int(nbytes), "achieved": ach, "unit": "GB/s", "frac": ach / peak, "note": note}
 
         stages = [
-            st("pyramid", "blur_strip_kernel<R> (octaves 0-1) / blur_walk_kernel<R> / blur_tile_kernel<R>", stage["pyramid"],
+            st("pyramid", "blur_stream_kernel<R> (octaves 0-1) / blur_walk_kernel<R> / blur_tile_kernel<R>", stage["pyramid"],
                PYR_BYTES_PER_FRAME * BATCH, n_blur, "48 B per pixel and octave: 6 levels written once, one level-sized read per blur (SURVEY.md 8d)"),
             st("extrema", "extrema_kernel + refine_list_kernel", stage["extrema"], EXT_BYTES_PER_FRAME * BATCH, 2 * N_OCT,
                "24 B per pixel and octave: each of the 6 levels read once; DoG never materialised"),
@@ -715,7 +715,7 @@ def match_leg(nm, torch, dist, synth, shard_bounds, rank, world, args, barrier, 
     Ah = synth.descriptors(nq, 1, planted_from=Bh)
     # world = Q x D: Q query groups, D database shards (rank r scans query block r // D against shard r % D); Q = 1 is
     # pure database sharding.  The per-row costs of a scan shrink with Q, the scan itself with D.
-    qg = env_int("NM_BENCH_QGROUPS", {8: 4, 4: 2}.get(world, 1))
+    qg = env_int("NM_BENCH_QGROUPS", {8: 4, 4: 4, 2: 2}.get(world, 1))   # measured best grids: 2x1, 4x1, 4x2
     if world % qg:
         qg = 1
     n_db_shards = world // qg

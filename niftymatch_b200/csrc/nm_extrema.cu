@@ -835,7 +835,12 @@ int nm_extrema_launch(const NmOctave& oc, int, int, const NmDetectParams& dp, in
         if (n_sms <= 0) return NM_ERR_NO_DEVICE;
         const long long n_tiles = (long long)grid.x * grid.y * grid.z;
         if (n_tiles >= (1LL << 31) / EX2_LIST || !oc.cand_n || !oc.cand) return NM_ERR_OVERFLOW;
-        const int ctas = (int)(n_tiles < (long long)n_sms * ctas_per_sm ? n_tiles : (long long)n_sms * ctas_per_sm);
+        // 4x the resident count: co-resident CTAs do not advance evenly, and with exactly-resident persistent CTAs the
+        // launch ends on half-empty SMs; the hardware hands an SM its next CTA as one retires (64 x 1080p: 1.27 -> 1.21 ms,
+        // 2x 1.23, 8x 1.21).  NM_EXTREMA_OVER overrides (tuning aid).
+        static const int over = getenv("NM_EXTREMA_OVER") ? atoi(getenv("NM_EXTREMA_OVER")) : 4;
+        const long long want = (long long)n_sms * ctas_per_sm * (over < 1 ? 1 : over);
+        const int ctas = (int)(n_tiles < want ? n_tiles : want);
         extrema_kernel<<<ctas, block, EX2_SMEM, stream>>>(oc, dp, tma->map, (int)grid.x, (int)grid.y, (int)n_tiles, oc.cand_n, oc.cand);
         NM_LAUNCH_CHECK();
         refine_list_kernel<<<(unsigned)nm_div_up64(n_tiles, 8), 256, 0, stream>>>(oc, dp, (int)grid.x, (int)grid.y, (int)n_tiles,

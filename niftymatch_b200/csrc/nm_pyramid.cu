@@ -27,6 +27,9 @@
 // kernel with plain loads.
 #include "nm_pyramid.cuh"
 #include <mutex>
+#include <vector>
+#include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <cstdlib>
 
@@ -556,10 +559,12 @@ template <int R, bool DST2>
 __global__ void __launch_bounds__(kStreamThreads, stream_min_ctas(R)) blur_stream_kernel(const NmBlurArgs a, const __grid_constant__ CUtensorMap tmap,
                                                                          const __grid_constant__ StreamTaps taps,
                                                                          int tiles_x, int cg, int full_rounds, int total,
-                                                                         int rot_div)
+                                                                         int rot_div, unsigned long long* trace)
 {
     constexpr int RA = radius_aligned(R), IP = in_pitch(R), NT = 2 * R + 1;
     constexpr int PRE = (2 * R + kGR - 1) / kGR;
+    unsigned long long t_begin = 0;
+    if (trace != nullptr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
     extern __shared__ __align__(128) float smem[];
     float* s_in = smem;                                  // [kNS][kGR][IP]
     float* s_ring = smem + kNS * kGR * IP;               // [kNG][kGR][kRowPitch]
@@ -572,11 +577,15 @@ __global__ void __launch_bounds__(kStreamThreads, stream_min_ctas(R)) blur_strea
     __shared__ float s_taps[NT];
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid < NT) s_taps[tid] = taps.v[tid];
-    const int n_pieces = full_rounds + 1;                // <= kStreamPieces (launcher); the last one may be empty
+    // full_rounds < 0: oversubscribed launch, -full_rounds CTAs per strip, CTA b = part b / strips of strip b % strips
+    const int n_pieces = full_rounds < 0 ? 1 : full_rounds + 1;   // <= kStreamPieces (launcher); the last one may be empty
     if (tid < n_pieces) {
         const long long G = gridDim.x, rem0 = (long long)full_rounds * G * cg, rem = total - rem0;
         long long g0, g1;
-        if (tid < full_rounds) { g0 = ((long long)tid * G + blockIdx.x) * cg; g1 = g0 + cg; }
+        if (full_rounds < 0) {
+            const int parts = -full_rounds, strips = total / cg, sx = blockIdx.x % strips, px = blockIdx.x / strips;
+            g0 = (long long)sx * cg + (long long)px * cg / parts; g1 = (long long)sx * cg + (long long)(px + 1) * cg / parts;
+        } else if (tid < full_rounds) { g0 = ((long long)tid * G + blockIdx.x) * cg; g1 = g0 + cg; }
         else { g0 = rem0 + rem * blockIdx.x / G; g1 = rem0 + rem * (blockIdx.x + 1) / G; }
         const int s = (int)(g0 / cg), c0 = (int)(g0 - (long long)s * cg), pre = min(PRE, c0);
         StreamPiece p;
@@ -702,6 +711,13 @@ __global__ void __launch_bounds__(kStreamThreads, stream_min_ctas(R)) blur_strea
             __syncwarp();
             if (lane == 0) mbar_arrive(ring_empty + q);
             wk.next(tab, live_pieces, cg, tiles_x);
+        }
+        if (trace != nullptr && role == 3 && lane == 0) {     // tuning aid: CTA residency interval and SM
+            unsigned long long t_end;
+            unsigned smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            trace[3 * blockIdx.x] = t_begin; trace[3 * blockIdx.x + 1] = t_end; trace[3 * blockIdx.x + 2] = smid;
         }
     }
 }
@@ -829,6 +845,36 @@ bool stream_eligible(const NmBlurArgs& a, const NmBlurTma* tma)
     return total < (1LL << 31) && strips / G + 1 <= kStreamPieces;
 }
 
+// NM_BLUR_STREAM_TRACE: per-CTA residency intervals of one launch (synchronises; tuning aid only)
+void stream_trace_report(unsigned long long* trace, int G, int R, const NmBlurArgs& a, cudaStream_t stream)
+{
+    cudaStreamSynchronize(stream);
+    std::vector<unsigned long long> h(3 * (size_t)G);
+    cudaMemcpy(h.data(), trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(trace);
+    unsigned long long t0 = ~0ULL, t1 = 0;
+    for (int i = 0; i < G; ++i) if (h[3 * i + 1]) { t0 = std::min(t0, h[3 * i]); t1 = std::max(t1, h[3 * i + 1]); }
+    std::vector<double> dur, endrel;
+    std::vector<double> sm_first(256, 1e30), sm_last(256, 0);
+    for (int i = 0; i < G; ++i) {
+        if (!h[3 * i + 1]) continue;
+        dur.push_back((h[3 * i + 1] - h[3 * i]) * 1e-3);
+        const double e = (h[3 * i + 1] - t0) * 1e-3;
+        endrel.push_back(e);
+        const int sm = (int)h[3 * i + 2] & 255;
+        sm_first[sm] = std::min(sm_first[sm], e); sm_last[sm] = std::max(sm_last[sm], e);
+    }
+    std::sort(dur.begin(), dur.end()); std::sort(endrel.begin(), endrel.end());
+    double gap = 0; int ns = 0;
+    for (int s = 0; s < 256; ++s) if (sm_last[s] > 0) { gap += sm_last[s] - sm_first[s]; ++ns; }
+    const size_t n = dur.size();
+    if (n)
+        fprintf(stderr, "[stream R=%d %dx%dx%d] span %.1f us; CTA duration min %.1f med %.1f max %.1f; CTA end (from launch) "
+                        "10%% %.1f 50%% %.1f 90%% %.1f; per-SM first-to-last CTA end: mean %.1f us over %d SMs\n",
+                R, a.w, a.h, a.batch, (t1 - t0) * 1e-3, dur[0], dur[n / 2], dur[n - 1], endrel[n / 10], endrel[n / 2],
+                endrel[n * 9 / 10], ns ? gap / ns : 0.0, ns);
+}
+
 template <int R>
 int launch_tile(const NmBlurArgs& a, cudaStream_t stream, const NmBlurTma* tma)
 {
@@ -860,19 +906,44 @@ int launch_tile(const NmBlurArgs& a, cudaStream_t stream, const NmBlurTma* tma)
                 once_stream.done();
             }
             const long long n_strips = (long long)grid.x * a.batch;
-            const int cg = nm_div_up(a.h + 2 * R, kGR), G = stream_ctas_per_sm(R) * n_sms;
+            // Co-resident CTAs do not advance evenly (the same work takes 45 to 105 us, NM_BLUR_STREAM_TRACE), so a launch
+            // of exactly-resident persistent CTAs ends with a long tail of half-empty SMs.  When there are enough strips
+            // the launch is OVERSUBSCRIBED instead: P CTAs per strip (part b / strips of strip b % strips, so CTAs that
+            // start together are neighbours in the image), about 2.5x the resident count, and the hardware hands an SM
+            // its next CTA as soon as one retires.  64 x 1080p: P = 2, pyramid 2.06 -> 1.96 ms (P = 1: 2.11, 3: 2.00).
+            // NM_BLUR_STREAM_PARTS forces P (0: always the persistent split).
+            static const int parts_env = getenv("NM_BLUR_STREAM_PARTS") ? atoi(getenv("NM_BLUR_STREAM_PARTS")) : -1;
+            const int cg = nm_div_up(a.h + 2 * R, kGR);
+            const long long resident = (long long)stream_ctas_per_sm(R) * n_sms;
+            int parts = parts_env;
+            if (parts_env < 0) {
+                // smallest P that reaches 2.5x the resident count with parts of >= 16 groups (the lead-in of a part is
+                // ceil(2R / 16) groups), else the largest such P that still reaches 1.5x, else the persistent split
+                parts = 0;
+                for (int p = 1; p <= 8 && cg >= 16 * p; ++p) {
+                    if (2 * n_strips * p >= 3 * resident) parts = p;
+                    if (2 * n_strips * p >= 5 * resident) break;
+                }
+            }
+            const bool over = parts > 0 && n_strips * parts > resident && n_strips * parts < (1 << 20) && cg >= 4 * parts;
+            const int G = over ? (int)(n_strips * parts) : (int)resident;
+            const int rounds_arg = over ? -parts : (int)(n_strips / G);
             static const int rot_env = getenv("NM_BLUR_STREAM_ROT") ? atoi(getenv("NM_BLUR_STREAM_ROT")) : 0;   // tuning aid
             const int rot_div = rot_env > 0 ? rot_env : (1 << 30);
             StreamTaps tp;
             memset(&tp, 0, sizeof(tp));
             memcpy(tp.v, a.taps_host, sizeof(float) * (2 * R + 1));
+            static const bool trace_on = getenv("NM_BLUR_STREAM_TRACE") != nullptr;                            // tuning aid
+            unsigned long long* trace = nullptr;
+            if (trace_on) cudaMalloc(&trace, sizeof(unsigned long long) * 3 * G);
             if (a.dst2 != nullptr)
                 blur_stream_kernel<R, true><<<G, kStreamThreads, stream_smem_bytes(R), stream>>>(
-                        a, tma->map_stream, tp, (int)grid.x, cg, (int)(n_strips / G), (int)(n_strips * cg), rot_div);
+                        a, tma->map_stream, tp, (int)grid.x, cg, rounds_arg, (int)(n_strips * cg), rot_div, trace);
             else
                 blur_stream_kernel<R, false><<<G, kStreamThreads, stream_smem_bytes(R), stream>>>(
-                    a, tma->map_stream, tp, (int)grid.x, cg, (int)(n_strips / G), (int)(n_strips * cg), rot_div);
+                    a, tma->map_stream, tp, (int)grid.x, cg, rounds_arg, (int)(n_strips * cg), rot_div, trace);
             NM_LAUNCH_CHECK();
+            if (trace_on) stream_trace_report(trace, G, R, a, stream);
             return NM_OK;
         }
         if (strip_eligible(a, tma)) {
