@@ -30,6 +30,8 @@ struct nm_sift_ctx {
     std::vector<TmaSet*> tma_sets;
     cudaStream_t s_in, s_out, s_aux[NM_AUX_STREAMS];   // nm_sift_run_host: H2D / D2H copy streams, extra compute streams
     cudaEvent_t ev_fork, ev_join[NM_AUX_STREAMS];
+    cudaStream_t s_side;                               // nm_sift_run: pyramids of octaves 1.. beside octave 0's last two levels
+    cudaEvent_t ev_side_fork, ev_side_join;
     cudaEvent_t ev_in[NM_MAX_CHUNKS], ev_done[NM_MAX_CHUNKS], ev_out;
     // nm_sift_run_host: the ~47 launches of a pipeline stage replayed as one CUDA graph.  A stage's launch
     // sequence depends only on (first frame, frame count, mask texture, descriptor mode): captured once per key.
@@ -193,6 +195,9 @@ extern "C" int nm_sift_destroy(nm_sift_ctx* c)
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->s_side) cudaStreamDestroy(c->s_side);
+    if (c->ev_side_fork) cudaEventDestroy(c->ev_side_fork);
+    if (c->ev_side_join) cudaEventDestroy(c->ev_side_join);
     delete c;
     return NM_OK;
 }
@@ -215,6 +220,7 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
     c->mask_tex = 0; c->mask_arr = nullptr; c->mask_own = 0;
     for (int i = 0; i < 7; ++i) c->ev[i] = nullptr;
     c->s_in = c->s_out = nullptr; c->ev_out = c->ev_fork = nullptr;
+    c->s_side = nullptr; c->ev_side_fork = c->ev_side_join = nullptr;
     for (int i = 0; i < NM_AUX_STREAMS; ++i) { c->s_aux[i] = nullptr; c->ev_join[i] = nullptr; }
     for (int i = 0; i < NM_MAX_CHUNKS; ++i) c->ev_in[i] = c->ev_done[i] = nullptr;
     int rc = NM_OK;
@@ -276,6 +282,10 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
                         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
                         cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess))
         rc = NM_ERR_ALLOC;
+    if (rc == NM_OK && (cudaStreamCreateWithFlags(&c->s_side, cudaStreamNonBlocking) != cudaSuccess ||
+                        cudaEventCreateWithFlags(&c->ev_side_fork, cudaEventDisableTiming) != cudaSuccess ||
+                        cudaEventCreateWithFlags(&c->ev_side_join, cudaEventDisableTiming) != cudaSuccess))
+        rc = NM_ERR_ALLOC;
     for (int i = 0; i < NM_AUX_STREAMS && rc == NM_OK; ++i)
         if (cudaStreamCreateWithFlags(&c->s_aux[i], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) != cudaSuccess)
@@ -293,7 +303,7 @@ extern "C" int nm_sift_create(nm_sift_ctx** out, const nm_sift_params* params, i
 // those n frames).  All kernels index frames by block, so a range is the same launch sequence on
 // pointers advanced to the range's first frame.
 static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, int n, cudaStream_t st, bool timing,
-                          bool bgra = false)
+                          bool bgra = false, bool side_octaves = false)
 {
     const nm_sift_params& P = c->P;
     int launches = 0, rc;
@@ -341,44 +351,62 @@ static int sift_run_range(nm_sift_ctx* c, const float* frames_dev, int first, in
     }
     if (timing) cudaEventRecord(c->ev[0], st);
     // ---- pyramid ---------------------------------------------------------------
-    for (int o = 0; o < c->n_oct; ++o) {
+    // side_octaves (large device-resident batches): octave 1's base is ready after octave 0's level 3, so the pyramids
+    // of octaves 1.. run on a second stream beside octave 0's two widest blurs -- the launches of octaves 3+ are a
+    // fraction of a wave each and would otherwise run alone, one after the other.
+    auto level_blur = [&](int o, int i, cudaStream_t s) -> int {
         const NmOctave& oc = tab.o[o];
         const long long fstride = 6 * oc.level_elems;
-        if (o == 0) {
-            NmBlurArgs a{};
-            a.src = frames_dev; a.src_pitch = P.width; a.src_fstride = (long long)P.width * P.height;
-            a.dst = oc.levels; a.dst_pitch = oc.pitch; a.dst_fstride = fstride;
-            a.taps = c->taps[0]; a.taps_host = c->taps_host[0]; a.radius = c->radii[0]; a.w = oc.w; a.h = oc.h; a.batch = n;
-            a.scratch = c->scratch ? c->scratch + (long long)first * P.width * P.height : nullptr;
-            NmBlurTma base;
-            nm_blur_make_tma(&base, frames_dev, P.width, P.height, P.width, (long long)P.width * P.height, n, c->radii[0], bgra);
-            a.src_bgra = bgra ? 1 : 0;
-            if (bgra && !nm_blur_uses_strip(a, &base)) {
-                // small launch: the tile kernels do not convert -- grey frames through the staging buffer first
-                float* gray = c->frames_stage + (long long)first * P.width * P.height;
-                if ((rc = nm_grayscale_launch(frames_dev, gray, (long long)n * P.width * P.height, st)) != NM_OK) return rc;
-                launches += 1;
-                a.src = gray; a.src_bgra = 0;
-                nm_blur_make_tma(&base, gray, P.width, P.height, P.width, (long long)P.width * P.height, n, c->radii[0]);
-            }
-            if ((rc = nm_blur_launch(a, st, &base)) != NM_OK) return rc;
-            ++launches;
+        NmBlurArgs a{};
+        a.src = oc.levels + i * oc.level_elems; a.src_pitch = oc.pitch; a.src_fstride = fstride;
+        a.dst = oc.levels + (i + 1) * oc.level_elems; a.dst_pitch = oc.pitch; a.dst_fstride = fstride;
+        a.taps = c->taps[i + 1]; a.taps_host = c->taps_host[i + 1]; a.radius = c->radii[i + 1]; a.w = oc.w; a.h = oc.h;
+        a.batch = n;
+        a.scratch = c->scratch ? c->scratch + (long long)first * P.width * P.height : nullptr;
+        if (i + 1 == P.num_dog_levels && o + 1 < c->n_oct) {
+            // level 3 (sigma doubled) decimated by 2 = next octave's level 0 (downsample.cu:15-16)
+            const NmOctave& nx = tab.o[o + 1];
+            a.dst2 = nx.levels; a.dst2_pitch = nx.pitch; a.dst2_fstride = 6 * nx.level_elems;
         }
+        ++launches;
+        return nm_blur_launch(a, s, &ts->lvl[o][i]);
+    };
+    {
+        const NmOctave& oc = tab.o[0];
+        NmBlurArgs a{};
+        a.src = frames_dev; a.src_pitch = P.width; a.src_fstride = (long long)P.width * P.height;
+        a.dst = oc.levels; a.dst_pitch = oc.pitch; a.dst_fstride = 6 * oc.level_elems;
+        a.taps = c->taps[0]; a.taps_host = c->taps_host[0]; a.radius = c->radii[0]; a.w = oc.w; a.h = oc.h; a.batch = n;
+        a.scratch = c->scratch ? c->scratch + (long long)first * P.width * P.height : nullptr;
+        NmBlurTma base;
+        nm_blur_make_tma(&base, frames_dev, P.width, P.height, P.width, (long long)P.width * P.height, n, c->radii[0], bgra);
+        a.src_bgra = bgra ? 1 : 0;
+        if (bgra && !nm_blur_uses_strip(a, &base)) {
+            // small launch: the tile kernels do not convert -- grey frames through the staging buffer first
+            float* gray = c->frames_stage + (long long)first * P.width * P.height;
+            if ((rc = nm_grayscale_launch(frames_dev, gray, (long long)n * P.width * P.height, st)) != NM_OK) return rc;
+            launches += 1;
+            a.src = gray; a.src_bgra = 0;
+            nm_blur_make_tma(&base, gray, P.width, P.height, P.width, (long long)P.width * P.height, n, c->radii[0]);
+        }
+        if ((rc = nm_blur_launch(a, st, &base)) != NM_OK) return rc;
+        ++launches;
+    }
+    const bool side = side_octaves && c->n_oct >= 2 && P.num_dog_levels < 5 && c->s_side != nullptr;
+    for (int o = 0; o < c->n_oct; ++o) {
+        cudaStream_t so = (side && o >= 1) ? c->s_side : st;
         for (int i = 0; i < 5; ++i) {
-            NmBlurArgs a{};
-            a.src = oc.levels + i * oc.level_elems; a.src_pitch = oc.pitch; a.src_fstride = fstride;
-            a.dst = oc.levels + (i + 1) * oc.level_elems; a.dst_pitch = oc.pitch; a.dst_fstride = fstride;
-            a.taps = c->taps[i + 1]; a.taps_host = c->taps_host[i + 1]; a.radius = c->radii[i + 1]; a.w = oc.w; a.h = oc.h;
-            a.batch = n;
-            a.scratch = c->scratch ? c->scratch + (long long)first * P.width * P.height : nullptr;
-            if (i + 1 == P.num_dog_levels && o + 1 < c->n_oct) {
-                // level 3 (sigma doubled) decimated by 2 = next octave's level 0 (downsample.cu:15-16)
-                const NmOctave& nx = tab.o[o + 1];
-                a.dst2 = nx.levels; a.dst2_pitch = nx.pitch; a.dst2_fstride = 6 * nx.level_elems;
+            if ((rc = level_blur(o, i, so)) != NM_OK) return rc;
+            if (side && o == 0 && i + 1 == P.num_dog_levels) {
+                // octave 1's base is written: the other octaves start on the side stream
+                NM_CUDA_TRY(cudaEventRecord(c->ev_side_fork, st));
+                NM_CUDA_TRY(cudaStreamWaitEvent(c->s_side, c->ev_side_fork, 0));
             }
-            if ((rc = nm_blur_launch(a, st, &ts->lvl[o][i])) != NM_OK) return rc;
-            ++launches;
         }
+    }
+    if (side) {
+        NM_CUDA_TRY(cudaEventRecord(c->ev_side_join, c->s_side));
+        NM_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_side_join, 0));
     }
     if (timing) cudaEventRecord(c->ev[1], st);
     // ---- DoG + extrema + refinement (+ dense gradient maps in the fused fallback) ----------
@@ -429,7 +457,14 @@ extern "C" int nm_sift_run_bgra(nm_sift_ctx* c, const void* frames_bgra_dev, int
 extern "C" int nm_sift_run(nm_sift_ctx* c, const float* frames_dev, int n_frames, nm_stream_t stream)
 {
     if (!c || !frames_dev || n_frames <= 0 || n_frames > c->B) return NM_ERR_INVALID;
-    return sift_run_range(c, frames_dev, 0, n_frames, (cudaStream_t)stream, c->timing != 0);
+    // octaves 1.. beside octave 0's last levels when octave 0 alone fills the device for a while (NM_SIDE_OCTAVES=0 disables)
+    static const bool side_off = getenv("NM_SIDE_OCTAVES") && getenv("NM_SIDE_OCTAVES")[0] == '0';
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool cap_ok = cudaStreamIsCapturing((cudaStream_t)stream, &cap) == cudaSuccess;
+    if (!cap_ok) cudaGetLastError();
+    const bool side = !side_off && cap_ok && cap == cudaStreamCaptureStatusNone &&
+                      (long long)n_frames * c->P.width * c->P.height >= 16LL * 1920 * 1080;
+    return sift_run_range(c, frames_dev, 0, n_frames, (cudaStream_t)stream, c->timing != 0, false, side);
 }
 
 // End to end from host memory, software pipelined in stages of a few frames: the H2D copy

@@ -19,7 +19,8 @@ KEYS = [("gpu__time_duration.sum", "time"), ("smsp__issue_active.avg.pct_of_peak
         ("launch__registers_per_thread", "regs"), ("smsp__inst_executed.sum", "warp instr"),
         ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %"), ("lts__t_sector_hit_rate.pct", "L2 hit %")]
-NAMES = ["blur_strip5", "blur_strip13", "extrema", "refine_list", "kprefine", "gradmap", "orient", "describe", "tc_scan"]
+NAMES = ["blur_stream5", "blur_stream7", "blur_stream8", "blur_stream10", "blur_stream13", "extrema", "refine_list", "kprefine",
+         "gradmap", "orient", "describe", "tc_scan"]
 
 
 def load(name):
@@ -52,7 +53,7 @@ def to_bytes(x):
 
 def main():
     print("# Round 2 — `ncu --set full --clock-control none` of the hot kernels (one launch each)\n")
-    print("Captured by `tools/capture_profiles.sh` through `gpurun` on a B200: `tools/quick_bench.py 1920 1080 16` (16 frames, "
+    print("Captured by `tools/capture_profiles.sh` through `gpurun` on a B200: `tools/quick_bench.py 1920 1080 64` (64 frames, "
           "octave-0 launch of the second iteration) and `tools/match_once.py 100000 100000 1` (main scan launch).  "
           "Cold-cache, serialised: the percentages are what to read, not the durations.  Raw pages: `r02_<kernel>_raw.csv`.\n")
     print("| kernel | " + " | ".join(t for _, t in KEYS) + " | top stall reasons (% of samples) |")
@@ -79,26 +80,29 @@ def main():
                 cells.append(f"{num(d[k]):.1f}" if "." in v else v)
         print(f"| `{d['Kernel Name'][0].split('(')[0].replace('<unnamed>::', '').replace('void ', '')}` ({n}) | " + " | ".join(cells) + f" | {d['stalls']} |")
         traffic[n] = to_bytes(d["dram__bytes_read.sum"]) + to_bytes(d["dram__bytes_write.sum"])
-    # per-stage DRAM bytes of a 64-frame step: the captured launch is 16 frames of octave 0; a stage's six octave
-    # launches carry 4/3 of octave 0's pixels; single-launch stages (orient, describe) scale with the frames only
+    # per-stage DRAM bytes of a 64-frame step: the captured launch is octave 0 of 64 frames; a stage's six octave launches
+    # carry 4/3 of octave 0's pixels; the pyramid adds the base blur (R = 7 again, octave 0 only)
     stage = {}
+    blur = [traffic.get(f"blur_stream{r}") for r in (5, 7, 8, 10, 13)]
+    if all(b is not None for b in blur):
+        stage["pyramid"] = sum(blur) * 4 / 3 + traffic["blur_stream7"]
     if "extrema" in traffic:
-        stage["extrema"] = (traffic["extrema"] + traffic.get("refine_list", 0.0)) * 4 * 4 / 3
+        stage["extrema"] = (traffic["extrema"] + traffic.get("refine_list", 0.0)) * 4 / 3
     if "gradmap" in traffic:
-        stage["gradient"] = traffic["gradmap"] * 4 * 4 / 3
+        stage["gradient"] = traffic["gradmap"] * 4 / 3
     if "orient" in traffic:
-        stage["orientation"] = traffic["orient"] * 4
+        stage["orientation"] = traffic["orient"]
     if "describe" in traffic:
-        stage["descriptor"] = traffic["describe"] * 4
+        stage["descriptor"] = traffic["describe"]
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
         old = json.load(open(path))
     except Exception:
         old = {}
     old.update(stage)
-    old["r02_note"] = ("extrema / gradient / orientation / descriptor: dram__bytes_read.sum + dram__bytes_write.sum of the stage's "
-                       "kernels per 64-frame step, scaled from the 16-frame octave-0 ncu captures (x4 frames, x4/3 octaves for "
-                       "the per-octave launches); profiles/r02_kernels.md")
+    old["r02_note"] = ("pyramid / extrema / gradient / orientation / descriptor: dram__bytes_read.sum + dram__bytes_write.sum of the stage's "
+                       "kernels per 64-frame step, from the 64-frame octave-0 ncu captures (x4/3 octaves for the per-octave "
+                       "launches; pyramid = five level blurs x4/3 + the base blur); profiles/r02_kernels.md")
     json.dump(old, open(path, "w"), indent=1)
     print("\nPer-stage DRAM traffic of a 64-frame step (scaled from these captures; written to `roofline_traffic.json`): " +
           ", ".join(f"{k} {v / 1e9:.2f} GB" for k, v in stage.items()) + ".")
