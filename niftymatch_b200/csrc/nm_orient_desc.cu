@@ -471,11 +471,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) describe_fast_kernel(const N
                     const bool vx0 = (unsigned)bx0 < 4u, vx1 = (unsigned)(bx0 + 1) < 4u;
                     const bool vy0 = (unsigned)by0 < 4u, vy1 = (unsigned)(by0 + 1) < 4u;
                     const bool p00 = vx0 && vy0, p01 = vx0 && vy1, p10 = vx1 && vy0, p11 = vx1 && vy1;
-                    const nm_f2 at2 = pk2(at0[u], at1[u]);
-#pragma unroll
-                    for (int ph = 0; ph < 32 / COPIES; ++ph) {
-                        if (act && (COPIES == 32 || (lane / COPIES) == ph)) {
+                    if (COPIES == 32) {
+                        if (act) {
                             // the two orientation bins of a cell as one packed FFMA: (v0, v1) += w * (at0, at1)
+                            const nm_f2 at2 = pk2(at0[u], at1[u]);
                             float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f;
                             if (p00) { v0 = h0[0]; v1 = h1[0]; }
                             if (p01) { v2 = h0[OY]; v3 = h1[OY]; }
@@ -490,7 +489,35 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) describe_fast_kernel(const N
                             if (p10) { h0[OX] = v4; h1[OX] = v5; }
                             if (p11) { h0[OX + OY] = v6; h1[OX + OY] = v7; }
                         }
-                        if (COPIES < 32) __syncwarp();
+                    } else {
+                        // 16 copies: lanes l and l + 16 share one.  A sample's two orientation bins have different
+                        // parities, so in the first pass every lane adds to the bin whose parity is its half-warp's
+                        // and in the second to the other one: the two lanes of a copy never meet in a pass, all 32
+                        // lanes work in both (round 2 had two passes of 16 lanes with all eight bins each), and with
+                        // bank = copy + 16 * (bin & 1) each of the four accesses of a pass is conflict free.
+                        const bool sw = ((bint ^ (lane >> 4)) & 1) != 0;
+                        float* pa = sw ? h1 : h0;
+                        float* pb = sw ? h0 : h1;
+                        const float ta = sw ? at1[u] : at0[u], tb = sw ? at0[u] : at1[u];
+#pragma unroll
+                        for (int ph = 0; ph < 2; ++ph) {
+                            float* q = ph ? pb : pa;
+                            const float tq = ph ? tb : ta;
+                            if (act) {
+                                float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+                                if (p00) v0 = q[0];
+                                if (p01) v1 = q[OY];
+                                if (p10) v2 = q[OX];
+                                if (p11) v3 = q[OX + OY];
+                                v0 = __fmaf_rn(w00[u], tq, v0); v1 = __fmaf_rn(w01[u], tq, v1);             // :135
+                                v2 = __fmaf_rn(w10[u], tq, v2); v3 = __fmaf_rn(w11[u], tq, v3);
+                                if (p00) q[0] = v0;
+                                if (p01) q[OY] = v1;
+                                if (p10) q[OX] = v2;
+                                if (p11) q[OX + OY] = v3;
+                            }
+                            __syncwarp();
+                        }
                     }
                 }
             }
@@ -529,9 +556,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) describe_fast_kernel(const N
             // store (the round-1 kernel was bound by exactly that chain: twice the histogram copies, i.e. half the
             // resident warps, made it 2.3x slower).
             const bool p00 = vx0 && vy0, p01 = vx0 && vy1, p10 = vx1 && vy0, p11 = vx1 && vy1;
-#pragma unroll
-            for (int ph = 0; ph < 32 / COPIES; ++ph) {
-                if (act && (COPIES == 32 || (lane / COPIES) == ph)) {
+            if (COPIES == 32) {
+                if (act) {
                     float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f;
                     if (p00) { v0 = h0[0]; v1 = h1[0]; }
                     if (p01) { v2 = h0[OY]; v3 = h1[OY]; }
@@ -546,7 +572,31 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) describe_fast_kernel(const N
                     if (p10) { h0[OX] = v4; h1[OX] = v5; }
                     if (p11) { h0[OX + OY] = v6; h1[OX + OY] = v7; }
                 }
-                if (COPIES < 32) __syncwarp();
+            } else {
+                // 16 copies, two passes by orientation-bin parity (see the packed path above)
+                const bool sw = ((bint ^ (lane >> 4)) & 1) != 0;
+                float* pa = sw ? h1 : h0;
+                float* pb = sw ? h0 : h1;
+                const float ta = sw ? at1 : at0, tb = sw ? at0 : at1;
+#pragma unroll
+                for (int ph = 0; ph < 2; ++ph) {
+                    float* q = ph ? pb : pa;
+                    const float tq = ph ? tb : ta;
+                    if (act) {
+                        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+                        if (p00) v0 = q[0];
+                        if (p01) v1 = q[OY];
+                        if (p10) v2 = q[OX];
+                        if (p11) v3 = q[OX + OY];
+                        v0 = __fmaf_rn(w00, tq, v0); v1 = __fmaf_rn(w01, tq, v1);                                        // :135
+                        v2 = __fmaf_rn(w10, tq, v2); v3 = __fmaf_rn(w11, tq, v3);
+                        if (p00) q[0] = v0;
+                        if (p01) q[OY] = v1;
+                        if (p10) q[OX] = v2;
+                        if (p11) q[OX + OY] = v3;
+                    }
+                    __syncwarp();
+                }
             }
         }
     };
@@ -610,10 +660,11 @@ int nm_describe_launch(const NmOctaveTable& tab, int batch, int capacity, const 
         NM_CUDA_TRY(cudaFuncSetAttribute((describe_fast_kernel<32, 2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem32 / 2));
         once.done();
     }
-    // NM_DESCRIBE (tuning aid; 64 x 1080p): 0: round-1 kernel 2.26 ms; 16: restructured kernel, 16 histogram copies 1.87;
-    // 162 (default): the same with packed fp32 pairs 1.84; 32 / 323: 32 copies 1.98 / 2.03; 322: 32 copies in two-warp
-    // CTAs 1.97; register caps for 6 / 7 CTAs per SM: 1.88 - 2.28
-    static const int variant = getenv("NM_DESCRIBE") ? atoi(getenv("NM_DESCRIBE")) : 162;
+    // NM_DESCRIBE (tuning aid; 64 x 1080p): 0: round-1 kernel 2.26 ms; 16 (default): restructured kernel, 16 histogram
+    // copies, two passes by orientation-bin parity 1.63 (two passes of 16 lanes: 1.87); 162: the same with packed fp32
+    // pairs for the sample arithmetic 1.71 (1.84); 32 / 323: 32 copies 1.97 / 2.03; 322: 32 copies in two-warp CTAs 1.96;
+    // register caps for 6 / 7 CTAs per SM: 1.88 - 2.28
+    static const int variant = getenv("NM_DESCRIBE") ? atoi(getenv("NM_DESCRIBE")) : 16;
     dim3 grid(nm_div_up(capacity, DE_WARPS), batch);
     if (exact)
         describe_kernel<true><<<grid, DE_WARPS * 32, smem, stream>>>(tab, capacity, counts, kpts, meta, orient, desc, x, y, num_dogs);
