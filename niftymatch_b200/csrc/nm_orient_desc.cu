@@ -531,6 +531,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) describe_fast_kernel(const N
             const int bx0 = (int)fx + 2, by0 = (int)fy + 2;
             // about a third of the window (corners outside the rotated 4 x 4 cell grid) lands in no bin (:122-125)
             const bool act = vx && by + 2 * i <= ymax && (unsigned)(bx0 + 1) <= 4u && (unsigned)(by0 + 1) <= 4u;
+            // rows of the chunk in which no lane lands in a cell (below the window, or the chunk's corner outside the
+            // rotated grid) are about four in ten: the weights and the two histogram passes are skipped for them
+            if (!__any_sync(0xffffffffu, act)) continue;
             const float theta = nm_mod_2pi_once(__fsub_rn(cur[i].y, th0));     // :100
             const float nt = __fmul_rn(theta, 1.2732395447351628f);            // :107, 8 / (2 pi)
             const float ft = floorf(nt);
@@ -661,7 +664,8 @@ int nm_describe_launch(const NmOctaveTable& tab, int batch, int capacity, const 
         once.done();
     }
     // NM_DESCRIBE (tuning aid; 64 x 1080p): 0: round-1 kernel 2.26 ms; 16 (default): restructured kernel, 16 histogram
-    // copies, two passes by orientation-bin parity 1.63 (two passes of 16 lanes: 1.87); 162: the same with packed fp32
+    // copies, two passes by orientation-bin parity, sample rows without an active lane skipped 1.54 (1.63 without the skip; two
+    // passes of 16 lanes: 1.87; a test of the row against ymax before the sample arithmetic: 1.60); 162: the same with packed fp32
     // pairs for the sample arithmetic 1.71 (1.84); 32 / 323: 32 copies 1.97 / 2.03; 322: 32 copies in two-warp CTAs 1.96;
     // register caps for 6 / 7 CTAs per SM: 1.88 - 2.28
     static const int variant = getenv("NM_DESCRIBE") ? atoi(getenv("NM_DESCRIBE")) : 16;
