@@ -464,6 +464,7 @@ extern "C" int nm_sift_run(nm_sift_ctx* c, const float* frames_dev, int n_frames
     if (!cap_ok) cudaGetLastError();
     const bool side = !side_off && cap_ok && cap == cudaStreamCaptureStatusNone &&
                       (long long)n_frames * c->P.width * c->P.height >= 16LL * 1920 * 1080;
+    // (measured and not kept: the two halves of the batch as two ranges on two streams, 7.24 -> 7.16 ms per 64 frames)
     return sift_run_range(c, frames_dev, 0, n_frames, (cudaStream_t)stream, c->timing != 0, false, side);
 }
 
