@@ -52,12 +52,16 @@ __global__ void __launch_bounds__(OR_WARPS * 32) orient_kernel(const NmOctaveTab
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int f = blockIdx.y;
     const int j = blockIdx.x * OR_WARPS + wid;
-    if (j >= counts[f]) return;                                   // warp uniform
+    // count, payload and octave index are fetched together (slot j < capacity exists whatever the count): one memory
+    // latency before the first gradient load instead of three dependent ones
     const long long kidx = (long long)f * capacity + j;
-    const float4 kp = kpts[kidx];
+    const int n_kp = counts[f];
+    const float4 kp = __ldg(kpts + kidx);
+    const int oct = __ldg(meta + kidx);
+    if (j >= n_kp) return;                                        // warp uniform
     float2 res = make_float2(-1.f, -1.f);                         // pyramidata.cu:90 fill
     if (!(kp.w < 0.f)) {                                          // orientation.cu:17
-        const NmOctave& oc = tab.o[meta[kidx]];
+        const NmOctave& oc = tab.o[min(max(oct, 0), NM_MAX_OCTAVES - 1)];
         const KpGeom g = kp_geom(kp, oc.xper);
         float sigma_w;                                            // :26-30 (window clamped by the 22x22 block)
         const int W = kp_orient_radius(g, sigma_w);
@@ -390,10 +394,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) describe_fast_kernel(const N
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int f = blockIdx.y;
     const int j = blockIdx.x * WARPS + wid;
-    if (j >= counts[f]) return;                                   // warp uniform
     const long long kidx = (long long)f * capacity + j;
-    const float4 kp = kpts[kidx];
-    const NmOctave& oc = tab.o[meta[kidx]];
+    const int n_kp = counts[f];                                   // fetched together with the slot's payload (see orient_kernel)
+    const float4 kp = __ldg(kpts + kidx);
+    const int oct = __ldg(meta + kidx);
+    const float2 ori = __ldg(orient + kidx);
+    if (j >= n_kp) return;                                        // warp uniform
+    const NmOctave& oc = tab.o[min(max(oct, 0), NM_MAX_OCTAVES - 1)];
     const KpGeom g = kp_geom(kp, oc.xper);                        // descriptor.cu:41-47
     float* dout = desc + kidx * DE_BINS;
     if (g.xi < 0 || g.xi >= oc.w || g.yi < 0 || g.yi >= oc.h || g.level < 0 || g.level >= num_dogs)
@@ -408,7 +415,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) describe_fast_kernel(const N
 
     const KpDescWindow dw = kp_desc_window(g, oc.w, oc.h);        // :54-65
     const int xmin = dw.xmin, xmax = dw.xmax, ymin = dw.ymin, ymax = dw.ymax, chunks = dw.chunks;
-    const float th0 = orient[kidx].x;                             // :89; in [0, 2 pi] or -1 (no peak)
+    const float th0 = ori.x;                                      // :89; in [0, 2 pi] or -1 (no peak)
     const float inv_sbp = __fdiv_rn(1.0f, dw.SBP);
     const float cs = __fmul_rn(cosf(th0), inv_sbp), sn = __fmul_rn(sinf(th0), inv_sbp);   // :90-91 folded with 1 / SBP (:104-105)
     const int pitch = oc.pitch;
