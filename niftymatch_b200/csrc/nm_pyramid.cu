@@ -467,8 +467,10 @@ __global__ void __launch_bounds__(kThreads, 2) blur_strip_kernel(const NmBlurArg
 //                                                                             instruction cache sees one role)
 //   16-row groups, 2 + 2 buffers                                              2.06 ms   (half the hand-overs)
 //   deeper rings (3 or 4 slots) or 3 stages: no change / slower (fewer resident CTAs)
-// Per launch (octave 0, ncu): R = 5 192 us, 7 215, 8 (+ decimated copy) 269, 10 261, 13 326 against
+//   oversubscribed launch, two CTAs per strip (see launch_tile)               1.96 ms
+// Per launch (octave 0, ncu, final): R = 5 188 us, 7 201, 8 (+ decimated copy) 248, 10 247, 13 312 against
 // 216 / 245 / 282 / 303 / 368 for blur_strip_kernel; the HBM floor of a level is 165 us, the FMA floor of R = 13 192 us.
+// The role rotation (rot_div) stays as a tuning aid; the default divisor is so large that no CTA rotates.
 #ifndef NM_STREAM_GR
 #define NM_STREAM_GR 16
 #define NM_STREAM_NS 2
