@@ -577,8 +577,11 @@ def main():
                     "algorithmic_bytes_per_launch": top["algorithmic_bytes"] / top["launches"],
                     "avg_launch_ms": top["ms"] / top["launches"],
                     "traffic": traffic_from_profiles(top["stage"]),
+                    "ncu": (traffic_from_profiles("ncu_limits") or {}).get(top["stage"]),
                     "note": "dominant kernel = the stage kernel with the largest CUDA-event time in this run (the pyramid is 31 "
-                            "launches of five blur instantiations, none of them larger); " + top["note"],
+                            "launches of five blur instantiations, none of them larger); `ncu` = what the committed ncu page of "
+                            "this kernel shows as its limiter (profiles/r02_kernels.md): the gather kernels are bound by "
+                            "instruction issue, so their HBM fraction stays low by construction; " + top["note"],
                     "blur_family": {k: pyr[k] for k in ("kernel", "ms", "launches", "algorithmic_bytes", "achieved", "frac")},
                     "dense_stages": {"ms": stage["pyramid"] + stage["extrema"],
                                      "achieved": 72 * SUM_N * BATCH / ((stage["pyramid"] + stage["extrema"]) * 1e-3) / 1e9,

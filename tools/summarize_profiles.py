@@ -59,6 +59,7 @@ def main():
     print("| kernel | " + " | ".join(t for _, t in KEYS) + " | top stall reasons (% of samples) |")
     print("|---|" + "---:|" * len(KEYS) + "---|")
     traffic = {}
+    limits = {}
     for n in NAMES:
         try:
             d = load(n)
@@ -80,6 +81,11 @@ def main():
                 cells.append(f"{num(d[k]):.1f}" if "." in v else v)
         print(f"| `{d['Kernel Name'][0].split('(')[0].replace('<unnamed>::', '').replace('void ', '')}` ({n}) | " + " | ".join(cells) + f" | {d['stalls']} |")
         traffic[n] = to_bytes(d["dram__bytes_read.sum"]) + to_bytes(d["dram__bytes_write.sum"])
+        limits[n] = {"issue_slots_busy_pct": round(num(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]), 1),
+                     "fma_pipe_pct": round(num(d["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]), 1),
+                     "alu_pipe_pct": round(num(d["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"]), 1),
+                     "dram_busy_pct": round(num(d["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]), 1),
+                     "top_stalls": d["stalls"]}
     # per-stage DRAM bytes of a 64-frame step: the captured launch is octave 0 of 64 frames; a stage's six octave launches
     # carry 4/3 of octave 0's pixels; the pyramid adds the base blur (R = 7 again, octave 0 only)
     stage = {}
@@ -100,6 +106,9 @@ def main():
     except Exception:
         old = {}
     old.update(stage)
+    # what ncu says bounds each stage's kernel (one `--set full` capture each; profiles/r02_kernels.md)
+    old["ncu_limits"] = {"pyramid": limits.get("blur_stream13"), "extrema": limits.get("extrema"), "gradient": limits.get("gradmap"),
+                         "orientation": limits.get("orient"), "descriptor": limits.get("describe")}
     old["r02_note"] = ("pyramid / extrema / gradient / orientation / descriptor: dram__bytes_read.sum + dram__bytes_write.sum of the stage's "
                        "kernels per 64-frame step, from the 64-frame octave-0 ncu captures (x4/3 octaves for the per-octave "
                        "launches; pyramid = five level blurs x4/3 + the base blur); profiles/r02_kernels.md")
