@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(kStreamThreads, stream_min_ctas(R)) blur_strea
         // ---------------- consumer: column pass, scatter form ----------------
         // The 2R+1 accumulators rotate through the roles "starts with this row" ... "completes with this row", so the
         // row step is unrolled 2R+1 times with static register names (NM_STREAM_STEP(U): the step in which acc[U]
-        // starts).  A group is 8 rows and 2R+1 is odd, so a group begins at any phase: the group loop re-enters the
+        // starts).  A group is 16 rows and 2R+1 is odd, so a group begins at any phase: the group loop re-enters the
         // unrolled sequence through a switch (Duff's device).  The group hand-over is outside the sequence, which
         // keeps the hot code contiguous and at (2R+1) x ~38 instructions within the 32 KB instruction cache -- inlined
         // into every step it was 53 KB for R = 13 and 18 % of the warp samples were instruction-fetch stalls.
